@@ -1,0 +1,148 @@
+"""
+Seeded synthetic checkpoints with the reference's state-dict names.
+
+No Emma-X / OpenVLA weights, no Llama-2 tokenizer and no network exist in the build or GPU images,
+so parity tests, `smoke()` and `bench.py` run on random-init weights of the exact reference architecture. The names
+follow the HF export contract of /root/reference/vla-scripts/extern/convert_openvla_weights_to_hf.py:84-116:
+
+    vision_backbone.featurizer.*        timm DINOv2 names, LayerScale as `ls{1,2}.scale_factor`
+    vision_backbone.fused_featurizer.*  timm SigLIP names
+    projector.fc{1,2,3}.{weight,bias}
+    language_model.model.* / language_model.lm_head.weight
+
+"Scripted" heads: greedy token ids of a random-init LM are decided by near-ties that flip under any change of
+reduction order, so bit-exact id parity would be meaningless noise. `script=[...]` therefore plants a known answer:
+`lm_head[script[i+1]] = gain * embed[script[i]]`, which makes the greedy continuation of a prompt ending in
+`script[0]`'s predecessor follow `script` with top-2 margins far above bf16 noise, while every layer still
+contributes O(1) to the hidden state (so logits remain a sensitive numerical probe).
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from .configuration import OpenVLAConfig, ViTDims
+
+
+def _randn(shape, std, gen, device, dtype, mean=0.0):
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    t.normal_(mean, std, generator=gen)
+    return t.to(dtype)
+
+
+def _vit_state(prefix: str, v: ViTDims, gen, device, dtype, sd: Dict[str, torch.Tensor]) -> None:
+    D, P = v.embed_dim, v.patch_size
+    sd[f"{prefix}patch_embed.proj.weight"] = _randn((D, 3, P, P), 0.02, gen, device, dtype)
+    sd[f"{prefix}patch_embed.proj.bias"] = _randn((D,), 0.02, gen, device, dtype)
+    sd[f"{prefix}pos_embed"] = _randn((1, v.num_patches, D), 0.02, gen, device, dtype)
+    if v.num_prefix_tokens > 0:
+        sd[f"{prefix}cls_token"] = _randn((1, 1, D), 0.02, gen, device, dtype)
+        sd[f"{prefix}reg_token"] = _randn((1, v.num_prefix_tokens - 1, D), 0.02, gen, device, dtype)
+    for i in range(v.depth):
+        b = f"{prefix}blocks.{i}."
+        sd[b + "norm1.weight"] = _randn((D,), 0.02, gen, device, dtype, mean=1.0)
+        sd[b + "norm1.bias"] = _randn((D,), 0.02, gen, device, dtype)
+        sd[b + "attn.qkv.weight"] = _randn((3 * D, D), 0.02, gen, device, dtype)
+        sd[b + "attn.qkv.bias"] = _randn((3 * D,), 0.02, gen, device, dtype)
+        sd[b + "attn.proj.weight"] = _randn((D, D), 0.02, gen, device, dtype)
+        sd[b + "attn.proj.bias"] = _randn((D,), 0.02, gen, device, dtype)
+        sd[b + "norm2.weight"] = _randn((D,), 0.02, gen, device, dtype, mean=1.0)
+        sd[b + "norm2.bias"] = _randn((D,), 0.02, gen, device, dtype)
+        sd[b + "mlp.fc1.weight"] = _randn((v.mlp_dim, D), 0.02, gen, device, dtype)
+        sd[b + "mlp.fc1.bias"] = _randn((v.mlp_dim,), 0.02, gen, device, dtype)
+        sd[b + "mlp.fc2.weight"] = _randn((D, v.mlp_dim), 0.02, gen, device, dtype)
+        sd[b + "mlp.fc2.bias"] = _randn((D,), 0.02, gen, device, dtype)
+        if v.layerscale:
+            # not timm's 1e-5 init (blocks would be near-identity): U(0.05, 1) keeps every block numerically relevant
+            for ls in ("ls1", "ls2"):
+                t = torch.empty((D,), dtype=torch.float32, device=device).uniform_(0.05, 1.0, generator=gen)
+                sd[b + f"{ls}.scale_factor"] = t.to(dtype)
+    # final norm exists in the timm state dict but is unused by `get_intermediate_layers` (no norm applied)
+    sd[f"{prefix}norm.weight"] = _randn((D,), 0.02, gen, device, dtype, mean=1.0)
+    sd[f"{prefix}norm.bias"] = _randn((D,), 0.02, gen, device, dtype)
+
+
+def make_state_dict(
+    config: OpenVLAConfig,
+    seed: int = 0,
+    device: str | torch.device = "cpu",
+    dtype: torch.dtype = torch.bfloat16,
+    script: Optional[Sequence[int]] = None,
+    script_prev: Optional[int] = None,
+    head_gain: float = 16.0,
+    resid_scale: float = 0.35,
+) -> Dict[str, torch.Tensor]:
+    """Build a full state dict (reference names). `script`/`script_prev`: see module docstring."""
+    device = torch.device(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    _vit_state("vision_backbone.featurizer.", config.vision_dims[0], gen, device, dtype, sd)
+    _vit_state("vision_backbone.fused_featurizer.", config.vision_dims[1], gen, device, dtype, sd)
+
+    t = config.text_config
+    vd, H = config.vision_embed_dim, t.hidden_size
+    sd["projector.fc1.weight"] = _randn((4 * vd, vd), 0.02, gen, device, dtype)
+    sd["projector.fc1.bias"] = _randn((4 * vd,), 0.02, gen, device, dtype)
+    sd["projector.fc2.weight"] = _randn((H, 4 * vd), 0.02, gen, device, dtype)
+    sd["projector.fc2.bias"] = _randn((H,), 0.02, gen, device, dtype)
+    sd["projector.fc3.weight"] = _randn((H, H), 0.05, gen, device, dtype)
+    sd["projector.fc3.bias"] = _randn((H,), 0.02, gen, device, dtype)
+
+    # Token embeddings at unit scale; the residual branches (o_proj / down_proj) are scaled so the sum of all layer
+    # contributions is comparable to the embedding (see module docstring).
+    p = "language_model.model."
+    emb32 = torch.empty((t.vocab_size, H), dtype=torch.float32, device=device).normal_(0.0, 1.0, generator=gen)
+    sd[p + "embed_tokens.weight"] = emb32.to(dtype)
+    I = t.intermediate_size
+    for i in range(t.num_hidden_layers):
+        b = f"{p}layers.{i}."
+        sd[b + "input_layernorm.weight"] = _randn((H,), 0.02, gen, device, dtype, mean=1.0)
+        for n in ("q_proj", "k_proj", "v_proj"):
+            sd[b + f"self_attn.{n}.weight"] = _randn((H, H), 0.02, gen, device, dtype)
+        sd[b + "self_attn.o_proj.weight"] = _randn((H, H), 0.02 * resid_scale, gen, device, dtype)
+        sd[b + "post_attention_layernorm.weight"] = _randn((H,), 0.02, gen, device, dtype, mean=1.0)
+        sd[b + "mlp.gate_proj.weight"] = _randn((I, H), 0.02, gen, device, dtype)
+        sd[b + "mlp.up_proj.weight"] = _randn((I, H), 0.02, gen, device, dtype)
+        sd[b + "mlp.down_proj.weight"] = _randn((H, I), 0.02 * resid_scale, gen, device, dtype)
+    sd[p + "norm.weight"] = _randn((H,), 0.02, gen, device, dtype, mean=1.0)
+
+    # un-scripted rows give ~N(0,1) logits; a scripted row peaks at ~head_gain * cos(hidden, embed[prev])
+    head = torch.empty((t.vocab_size, H), dtype=torch.float32, device=device).normal_(0.0, H**-0.5, generator=gen)
+    if script is not None:
+        ids = list(script)
+        assert len(set(ids)) == len(ids), "script ids must be unique (successor is a function of the current id)"
+        prev = [script_prev] + ids[:-1]
+        assert script_prev is not None and script_prev not in ids
+        idx_next = torch.tensor(ids, device=device)
+        idx_prev = torch.tensor(prev, device=device)
+        head[idx_next] = (head_gain / H) * sd[p + "embed_tokens.weight"][idx_prev].float()
+    sd["language_model.lm_head.weight"] = head.to(dtype)
+    return sd
+
+
+# === scripted continuation used by bench / smoke / parity ============================================================
+def default_script(tokenizer, n_new: int, seed: int = 0, n_policies: int = 2) -> List[int]:
+    """A unique-id script of `n_new` tokens shaped like the grounded-CoT output grammar
+    (/root/reference/prismatic/vla/datasets/datasets.py:483-581): filler "reasoning", then
+    `MOVEMENT:\\n<7 act>\\nPOLICIES:\\n<7 act>;<7 act>\\n`, then EOS as the last token."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    act = rng.permutation(np.arange(tokenizer.action_id_lo + 1, tokenizer.action_id_hi + 1))  # 31745..31999
+    act = [int(a) for a in act[: 7 * (n_policies + 1)]]
+    tail: List[int] = [tokenizer.key_id("MOVEMENT:"), tokenizer.newline_id(0)]
+    tail += act[:7] + [tokenizer.newline_id(1)]
+    tail += [tokenizer.key_id("POLICIES:"), tokenizer.newline_id(2)]
+    for p in range(n_policies):
+        if p > 0:
+            tail.append(tokenizer.semicolon_id(p - 1))
+        tail += act[7 * (p + 1) : 7 * (p + 2)]
+    tail += [tokenizer.newline_id(3), tokenizer.eos_token_id]
+    n_fill = n_new - len(tail)
+    assert n_fill >= 0, f"n_new={n_new} too short for the scripted tail ({len(tail)})"
+    filler = rng.permutation(np.arange(tokenizer.filler_lo, tokenizer.filler_hi))[:n_fill]
+    return [int(x) for x in filler] + tail

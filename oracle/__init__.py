@@ -1,0 +1,26 @@
+"""
+oracle/ — TEST INFRASTRUCTURE ONLY.
+
+CPU/GPU torch-eager restatement of the reference `generate_actions` path, used as the checker by `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of `bench.py`. Nothing under
+`emmax_b200/` imports it; the product path has no CPU fallback and raises when `libemmax.so` is missing.
+
+What it restates (all paths under /root/reference):
+  * prismatic/extern/hf/modeling_prismatic.py:63-158   vision-backbone wiring, fused-GELU projector
+  * prismatic/extern/hf/modeling_prismatic.py:362-415  multimodal sequence assembly; :325-341 cached step
+  * prismatic/extern/hf/modeling_prismatic.py:495-537  de-tokenise + un-normalise
+  * prismatic/extern/hf/processing_prismatic.py:128-145 image transform
+  * prismatic/vla/action_tokenizer.py:28-68, prismatic/vla/solver.py:42-137
+
+Third-party arithmetic that is NOT in /root/reference (pins from requirements-min.txt:1-5, README.md:76):
+  * timm==0.9.10 `VisionTransformer` — restated from its published semantics in `oracle/vit.py`
+  * transformers==4.40.1 `LlamaForCausalLM` — the container's transformers 5.5.0 class is used directly (same math)
+  * flash-attn==2.5.5 — container has 2.8.3; used on the GPU box via `attn_implementation="flash_attention_2"`
+
+PARITY PINNING: the reference has no tests, fixtures or golden vectors for the neural path, and it
+cannot be imported here (no timm/draccus/tensorflow; gated tokenizer), so for ViT / projector / Llama arithmetic this
+oracle is **parity unpinned** (anchored only on the reference's call sites and on the third-party classes themselves).
+The integer/fp64 de-tokeniser and the Solver text parser ARE pinned: `oracle/gen_golden.py` imports
+`prismatic/vla/action_tokenizer.py` and executes the `Solver` class source of `prismatic/vla/solver.py` from
+/root/reference and freezes their outputs in `tests/golden/detok_golden.json`.
+"""
