@@ -1,0 +1,334 @@
+"""
+GPU engine: packs a reference-named state dict into the layouts the kernels want and drives the hot path
+(vision towers -> projector -> Llama prefill -> persistent decode steps) through the C ABI of libemmax.so.
+
+PyTorch is used for device memory, streams and CUDA-graph capture only; every FLOP runs in the hand-written kernels.
+Reference call stack being replaced: SURVEY.md §3.1 (HF path), i.e.
+/root/reference/prismatic/extern/hf/modeling_prismatic.py:362-415 (multimodal forward), :325-341 (cached step).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EPI_GELU, EPI_SWIGLU, DecodeParams, DecodeState, call, ptr, stream
+from .configuration import OpenVLAConfig, ViTDims
+
+BF16 = torch.bfloat16
+
+
+def _ceil_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class _ViTWeights:
+    dims: ViTDims
+    kpad: int
+    w_pe: torch.Tensor  # [D, kpad]
+    b_pe: torch.Tensor
+    pos: torch.Tensor  # [n_patches, D]
+    prefix: Optional[torch.Tensor]  # [n_prefix, D]
+    blocks: List[Dict[str, torch.Tensor]]
+
+
+class Engine:
+    PAGE = 64
+
+    def __init__(self, config: OpenVLAConfig, state_dict: Dict[str, torch.Tensor], device: torch.device,
+                 max_batch: int = 1, max_context: int = 1024, kv_splits: int = 4) -> None:  # fmt: skip
+        _lib.load()  # raises if libemmax.so is missing: there is no fallback path
+        if device.type != "cuda":
+            raise _lib.EmxError("emmax_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.config, self.device = config, device
+        self.t = config.text_config
+        self.max_batch, self.kv_splits = max_batch, kv_splits
+        self.max_context = _ceil_to(max_context, self.PAGE)
+        self._graphs: Dict[Tuple[int, int], Tuple[torch.cuda.CUDAGraph, dict]] = {}
+        with torch.cuda.device(device):
+            self._pack(state_dict)
+            self._alloc()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _pack(self, sd: Dict[str, torch.Tensor]) -> None:
+        dev = self.device
+
+        def take(name: str) -> torch.Tensor:
+            return sd.pop(name).to(device=dev, dtype=BF16).contiguous()
+
+        self.vits: List[_ViTWeights] = []
+        for prefix, v in zip(("vision_backbone.featurizer.", "vision_backbone.fused_featurizer."), self.config.vision_dims):
+            D, kk = v.embed_dim, 3 * v.patch_size * v.patch_size
+            kpad = _ceil_to(kk, 8)
+            w = take(prefix + "patch_embed.proj.weight").reshape(D, kk)
+            w_pe = torch.zeros((D, kpad), dtype=BF16, device=dev)
+            w_pe[:, :kk] = w
+            pre = None
+            if v.num_prefix_tokens > 0:
+                pre = torch.cat([take(prefix + "cls_token")[0], take(prefix + "reg_token")[0]], dim=0).contiguous()
+            blocks = []
+            for i in range(v.depth):
+                b = f"{prefix}blocks.{i}."
+                names = ["norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
+                         "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"]  # fmt: skip
+                if v.layerscale:
+                    names += ["ls1.scale_factor", "ls2.scale_factor"]
+                if i < v.used_depth:
+                    blocks.append({n: take(b + n) for n in names})
+                else:  # the last block cannot influence `get_intermediate_layers(n={depth-2})`: never uploaded
+                    for n in names:
+                        sd.pop(b + n, None)
+            self.vits.append(_ViTWeights(v, kpad, w_pe, take(prefix + "patch_embed.proj.bias"), take(prefix + "pos_embed")[0], pre, blocks))
+            for k in [k for k in sd if k.startswith(prefix)]:  # unused: final norm, SigLIP attn_pool
+                sd.pop(k)
+
+        self.proj = {n: take(f"projector.{n}") for n in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias")}
+
+        t, p = self.t, "language_model.model."
+        L, H, I = t.num_hidden_layers, t.hidden_size, t.intermediate_size
+        self.embed = take(p + "embed_tokens.weight")
+        self.w_qkv = torch.empty((L, 3 * H, H), dtype=BF16, device=dev)
+        self.w_o = torch.empty((L, H, H), dtype=BF16, device=dev)
+        self.w_gateup = torch.empty((L, 2 * I, H), dtype=BF16, device=dev)  # row 2i = gate_i, row 2i+1 = up_i
+        self.w_down = torch.empty((L, H, I), dtype=BF16, device=dev)
+        self.ln1 = torch.empty((L, H), dtype=BF16, device=dev)
+        self.ln2 = torch.empty((L, H), dtype=BF16, device=dev)
+        for i in range(L):
+            b = f"{p}layers.{i}."
+            for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+                self.w_qkv[i, j * H : (j + 1) * H] = sd.pop(b + f"self_attn.{n}.weight").to(dev)
+            self.w_o[i] = sd.pop(b + "self_attn.o_proj.weight").to(dev)
+            self.w_gateup[i, 0::2] = sd.pop(b + "mlp.gate_proj.weight").to(dev)
+            self.w_gateup[i, 1::2] = sd.pop(b + "mlp.up_proj.weight").to(dev)
+            self.w_down[i] = sd.pop(b + "mlp.down_proj.weight").to(dev)
+            self.ln1[i] = sd.pop(b + "input_layernorm.weight").to(dev)
+            self.ln2[i] = sd.pop(b + "post_attention_layernorm.weight").to(dev)
+        self.final_norm = take(p + "norm.weight")
+        self.lm_head = take("language_model.lm_head.weight")
+
+        # RoPE tables exactly as transformers builds them (fp32 outer product -> cos/sin -> cast to the model dtype)
+        hd = t.head_dim
+        inv_freq = 1.0 / (t.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64, device=dev).float() / hd))
+        pos = torch.arange(self.max_context, device=dev).float()
+        freqs = pos[:, None] * inv_freq[None, :]
+        self.cos_tab, self.sin_tab = freqs.cos().to(BF16).contiguous(), freqs.sin().to(BF16).contiguous()
+
+    def _alloc(self) -> None:
+        dev, t, B = self.device, self.t, self.max_batch
+        H, I, L = t.hidden_size, t.intermediate_size, t.num_hidden_layers
+        self.pages_per_seq = self.max_context // self.PAGE
+        self.n_pages = self.pages_per_seq * B
+        shape = (L, self.n_pages, t.num_attention_heads, self.PAGE, t.head_dim)
+        self.k_cache = torch.zeros(shape, dtype=BF16, device=dev)
+        self.v_cache = torch.zeros(shape, dtype=BF16, device=dev)
+        self.block_table = torch.arange(self.n_pages, dtype=torch.int32, device=dev).reshape(B, self.pages_per_seq).contiguous()
+        self.layer_cache_bytes = self.k_cache[0].numel() * 2
+        # decode scratch
+        grid = _lib.load().emx_decode_grid()
+        self.d_x = torch.zeros(H, dtype=BF16, device=dev)
+        self.d_qkv = torch.zeros(3 * H, dtype=BF16, device=dev)
+        self.d_attn = torch.zeros(H, dtype=BF16, device=dev)
+        self.d_h = torch.zeros(I, dtype=BF16, device=dev)
+        self.d_part = torch.zeros(t.num_attention_heads * self.kv_splits * (t.head_dim + 2), dtype=torch.float32, device=dev)
+        self.d_argmax = torch.zeros(2 * grid, dtype=torch.float32, device=dev)
+        self.d_state = torch.zeros(C.sizeof(DecodeState) // 4, dtype=torch.int32, device=dev)
+        self.max_new = self.max_context
+        self.d_out_tokens = torch.zeros(self.max_new, dtype=torch.int32, device=dev)
+        self.h_flag = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._ws: Dict[Tuple[int, int], dict] = {}
+
+    # ------------------------------------------------------------------------------------------------------------
+    # kernel wrappers
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias=None, ls=None, resid=None, resid_mod: int = 0, flags: int = 0) -> None:
+        M, K = a.shape
+        N = w.shape[0]
+        call("emx_gemm_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias), ptr(ls),
+             ptr(resid), resid.stride(0) if resid is not None else 0, resid_mod, flags, stream())  # fmt: skip
+
+    def _workspace(self, B: int, n_ids: int) -> dict:
+        key = (B, n_ids)
+        if key in self._ws:
+            return self._ws[key]
+        dev, t, cfg = self.device, self.t, self.config
+        P = cfg.num_patches
+        S = n_ids + P
+        ws: dict = {"S": S}
+        e = lambda *s: torch.empty(s, dtype=BF16, device=dev)  # noqa: E731
+        for i, vw in enumerate(self.vits):
+            v = vw.dims
+            T = v.num_tokens
+            ws[f"v{i}"] = dict(im2col=e(B * P, vw.kpad), pe=e(B * P, v.embed_dim), tok=e(B * T, v.embed_dim), n=e(B * T, v.embed_dim),
+                               qkv=e(B * T, 3 * v.embed_dim), att=e(B * T, v.embed_dim), hid=e(B * T, v.mlp_dim))  # fmt: skip
+        vd, H, I = cfg.vision_embed_dim, t.hidden_size, t.intermediate_size
+        ws.update(feats=e(B * P, vd), p1=e(B * P, 4 * vd), p2=e(B * P, H), patches=e(B * P, H),
+                  x=e(B * S, H), n=e(B * S, H), qkv=e(B * S, 3 * H), att=e(B * S, H), h=e(B * S, I),
+                  last_n=e(B, H),
+                  pixels=torch.empty((B, 6, cfg.image_sizes[0], cfg.image_sizes[0]), dtype=BF16, device=dev),
+                  ids=torch.empty((B, n_ids), dtype=torch.int64, device=dev),
+                  logits=torch.empty((B, t.vocab_size), dtype=torch.float32, device=dev),
+                  first=torch.empty(B, dtype=torch.int32, device=dev))  # fmt: skip
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _vision(self, ws: dict, B: int) -> None:
+        """pixels [B,6,h,w] -> feats [B*P, vision_dim]  (modeling_prismatic.py:114-123)"""
+        cfg = self.config
+        P, side = cfg.num_patches, cfg.image_sizes[0]
+        col0 = 0
+        for i, vw in enumerate(self.vits):
+            v, w = vw.dims, ws[f"v{i}"]
+            D, T, hd = v.embed_dim, v.num_tokens, v.head_dim
+            call("emx_patch_im2col", ptr(ws["pixels"]), B, 6, 3 * i, side, side, v.patch_size, ptr(w["im2col"]), vw.kpad, stream())
+            self.gemm(w["im2col"], vw.w_pe, w["pe"], bias=vw.b_pe)
+            call("emx_vit_assemble", ptr(w["pe"]), ptr(vw.pos), ptr(vw.prefix), ptr(w["tok"]), B, P, v.num_prefix_tokens, D, stream())
+            for blk in vw.blocks:
+                call("emx_layernorm", ptr(w["tok"]), ptr(blk["norm1.weight"]), ptr(blk["norm1.bias"]), ptr(w["n"]), B * T, D, v.ln_eps, stream())
+                self.gemm(w["n"], blk["attn.qkv.weight"], w["qkv"], bias=blk["attn.qkv.bias"])
+                call("emx_attn_fwd", ptr(w["qkv"]), ptr(w["att"]), B, T, v.num_heads, hd, 0, hd**-0.5, stream())
+                self.gemm(w["att"], blk["attn.proj.weight"], w["tok"], bias=blk["attn.proj.bias"], ls=blk.get("ls1.scale_factor"), resid=w["tok"])
+                call("emx_layernorm", ptr(w["tok"]), ptr(blk["norm2.weight"]), ptr(blk["norm2.bias"]), ptr(w["n"]), B * T, D, v.ln_eps, stream())
+                self.gemm(w["n"], blk["mlp.fc1.weight"], w["hid"], bias=blk["mlp.fc1.bias"], flags=EPI_GELU)
+                self.gemm(w["hid"], blk["mlp.fc2.weight"], w["tok"], bias=blk["mlp.fc2.bias"], ls=blk.get("ls2.scale_factor"), resid=w["tok"])
+            call("emx_vit_gather_features", ptr(w["tok"]), ptr(ws["feats"]), B, P, v.num_prefix_tokens, D, cfg.vision_embed_dim, col0, stream())
+            col0 += D
+
+    def _projector(self, ws: dict) -> None:
+        """fc1 -> GELU -> fc2 -> GELU -> fc3  (modeling_prismatic.py:152-156)"""
+        pj = self.proj
+        self.gemm(ws["feats"], pj["fc1.weight"], ws["p1"], bias=pj["fc1.bias"], flags=EPI_GELU)
+        self.gemm(ws["p1"], pj["fc2.weight"], ws["p2"], bias=pj["fc2.bias"], flags=EPI_GELU)
+        self.gemm(ws["p2"], pj["fc3.weight"], ws["patches"], bias=pj["fc3.bias"])
+
+    def _layer_cache(self, cache: torch.Tensor, layer: int) -> int:
+        return cache.data_ptr() + layer * self.layer_cache_bytes
+
+    def _llm_prefill(self, ws: dict, B: int, n_ids: int) -> None:
+        """multimodal assembly + full-sequence Llama forward, KV written to the paged cache (modeling_prismatic.py:380-415)"""
+        t, cfg = self.t, self.config
+        H, I, L, S = t.hidden_size, t.intermediate_size, t.num_hidden_layers, ws["S"]
+        heads, hd = t.num_attention_heads, t.head_dim
+        call("emx_embed_assemble", ptr(ws["ids"]), n_ids, ptr(self.embed), ptr(ws["patches"]), cfg.num_patches, ptr(ws["x"]), B, H, stream())
+        for l in range(L):
+            call("emx_rmsnorm", ptr(ws["x"]), ptr(self.ln1[l]), ptr(ws["n"]), B * S, H, t.rms_norm_eps, stream())
+            self.gemm(ws["n"], self.w_qkv[l], ws["qkv"])
+            call("emx_rope_kvstore", ptr(ws["qkv"]), B, S, heads, hd, ptr(self.cos_tab), ptr(self.sin_tab), 0,
+                 self._layer_cache(self.k_cache, l), self._layer_cache(self.v_cache, l), ptr(self.block_table),
+                 self.pages_per_seq, self.PAGE, stream())  # fmt: skip
+            call("emx_attn_fwd", ptr(ws["qkv"]), ptr(ws["att"]), B, S, heads, hd, 1, hd**-0.5, stream())
+            self.gemm(ws["att"], self.w_o[l], ws["x"], resid=ws["x"])
+            call("emx_rmsnorm", ptr(ws["x"]), ptr(self.ln2[l]), ptr(ws["n"]), B * S, H, t.rms_norm_eps, stream())
+            self.gemm(ws["n"], self.w_gateup[l], ws["h"], flags=EPI_SWIGLU)
+            self.gemm(ws["h"], self.w_down[l], ws["x"], resid=ws["x"])
+        # lm_head on the LAST position only (the reference computes all S rows and discards S-1 of them)
+        x3 = ws["x"].view(B, S, H)
+        for b in range(B):
+            call("emx_rmsnorm", ptr(x3[b, S - 1]), ptr(self.final_norm), ptr(ws["last_n"][b]), 1, H, t.rms_norm_eps, stream())
+            call("emx_lmhead_argmax", ptr(self.lm_head), H, ptr(ws["last_n"][b]), t.vocab_size, H, ptr(ws["logits"][b]),
+                 ptr(ws["first"][b : b + 1]), None, stream())  # fmt: skip
+
+    def _prefill_body(self, ws: dict, B: int, n_ids: int) -> None:
+        self._vision(ws, B)
+        self._projector(ws)
+        self._llm_prefill(ws, B, n_ids)
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def prefill(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, use_graph: bool = True) -> dict:
+        """Vision + projector + LLM prefill for B same-length prompts. Returns the workspace (first tokens, logits, features)."""
+        B, n_ids = input_ids.shape
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} exceeds engine capacity {self.max_batch}")
+        S = n_ids + self.config.num_patches
+        if S + 1 > self.max_context:
+            raise ValueError(f"prompt of {S} positions does not fit max_context={self.max_context}")
+        ws = self._workspace(B, n_ids)
+        ws["ids"].copy_(input_ids, non_blocking=True)
+        ws["pixels"].copy_(pixel_values, non_blocking=True)
+        if not use_graph:
+            self._prefill_body(ws, B, n_ids)
+            return ws
+        key = (B, n_ids)
+        if key not in self._graphs:
+            # warm-up once outside capture (sets func attributes / driver entry points), then capture
+            self._prefill_body(ws, B, n_ids)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._prefill_body(ws, B, n_ids)
+            self._graphs[key] = (g, ws)
+        self._graphs[key][0].replay()
+        return ws
+
+    def _decode_params(self, b: int = 0) -> DecodeParams:
+        t = self.t
+        p = DecodeParams()
+        p.hidden, p.inter, p.heads, p.head_dim = t.hidden_size, t.intermediate_size, t.num_attention_heads, t.head_dim
+        p.layers, p.vocab, p.rms_eps = t.num_hidden_layers, t.vocab_size, t.rms_norm_eps
+        p.embed, p.w_qkv, p.w_o, p.w_gateup, p.w_down = ptr(self.embed), ptr(self.w_qkv), ptr(self.w_o), ptr(self.w_gateup), ptr(self.w_down)
+        p.ln1, p.ln2, p.final_norm, p.lm_head = ptr(self.ln1), ptr(self.ln2), ptr(self.final_norm), ptr(self.lm_head)
+        p.cos_tab, p.sin_tab = ptr(self.cos_tab), ptr(self.sin_tab)
+        p.k_cache, p.v_cache = ptr(self.k_cache), ptr(self.v_cache)
+        p.block_table = self.block_table[b].data_ptr()
+        p.page_size, p.n_pages, p.max_pages = self.PAGE, self.n_pages, self.pages_per_seq
+        p.x, p.qkv, p.attn, p.h = ptr(self.d_x), ptr(self.d_qkv), ptr(self.d_attn), ptr(self.d_h)
+        p.part, p.argmax_part = ptr(self.d_part), ptr(self.d_argmax)
+        p.out_tokens, p.logits_out = ptr(self.d_out_tokens), None
+        p.eos_token, p.kv_splits, p.state = -1, self.kv_splits, ptr(self.d_state)
+        return p
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, max_new_tokens: int, eos_token_id: Optional[int] = 2,
+                 return_logits: bool = False, forced: Optional[List[int]] = None, use_graph: bool = True,
+                 poll_every: int = 32) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:  # fmt: skip
+        """Greedy decode for ONE sequence (the reference asserts bs == 1 for cached generation,
+        modeling_prismatic.py:326, :460-463). Returns (new token ids [n] int32 on device, optional per-step logits)."""
+        if input_ids.shape[0] != 1:
+            raise ValueError("Generation with batch size > 1 is not currently supported!")
+        n_ids = input_ids.shape[1]
+        S = n_ids + self.config.num_patches
+        if S + max_new_tokens > self.max_context:
+            raise ValueError(f"{S} prompt positions + {max_new_tokens} new tokens exceed max_context={self.max_context}")
+        ws = self.prefill(input_ids, pixel_values, use_graph=use_graph)
+        V = self.t.vocab_size
+        logits = torch.empty((max_new_tokens, V), dtype=torch.float32, device=self.device) if return_logits else None
+        if return_logits:
+            logits[0].copy_(ws["logits"][0])
+        # hand-off: first token, position, counters (kernel-private words 4.. of the state are left alone)
+        first = ws["first"][0:1]
+        self.d_out_tokens[0:1].copy_(first)
+        st = self.d_state
+        st[0:1].copy_(first if forced is None else torch.tensor([forced[0]], dtype=torch.int32, device=self.device))
+        st[1].fill_(S)
+        st[2].fill_(1)
+        st[3].zero_()
+        if eos_token_id is not None and forced is None:
+            st[3:4].copy_((first == eos_token_id).to(torch.int32))
+        p = self._decode_params(0)
+        p.eos_token = -1 if (eos_token_id is None or forced is not None) else int(eos_token_id)
+        lib = _lib.load()
+        s = stream()
+        pending = None
+        for step in range(1, max_new_tokens):
+            if return_logits:
+                p.logits_out = logits[step].data_ptr()
+            _lib.check(lib.emx_decode_step(C.byref(p), s))
+            if forced is not None:
+                st[0].fill_(int(forced[step]))  # teacher forcing: overwrite the token the next step will embed
+            if p.eos_token >= 0 and step % poll_every == 0:
+                # lagging, non-blocking EOS poll: look at the flag copied one chunk ago, then queue a fresh copy
+                if pending is not None and pending.query() and int(self.h_flag[3]) != 0:
+                    break
+                self.h_flag.copy_(st[0:4], non_blocking=True)
+                pending = torch.cuda.Event()
+                pending.record()
+        n = int(st[2].item())  # device -> host sync point (the reference syncs every token)
+        return self.d_out_tokens[:n].clone(), (logits[:n] if return_logits else None)

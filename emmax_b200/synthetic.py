@@ -19,7 +19,7 @@ contributes O(1) to the hidden state (so logits remain a sensitive numerical pro
 
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -71,6 +71,7 @@ def make_state_dict(
     dtype: torch.dtype = torch.bfloat16,
     script: Optional[Sequence[int]] = None,
     script_prev: Optional[int] = None,
+    extra_chains: Optional[Sequence[Tuple[int, Sequence[int]]]] = None,
     head_gain: float = 16.0,
     resid_scale: float = 0.35,
 ) -> Dict[str, torch.Tensor]:
@@ -112,11 +113,19 @@ def make_state_dict(
 
     # un-scripted rows give ~N(0,1) logits; a scripted row peaks at ~head_gain * cos(hidden, embed[prev])
     head = torch.empty((t.vocab_size, H), dtype=torch.float32, device=device).normal_(0.0, H**-0.5, generator=gen)
+    chains: List[Tuple[int, List[int]]] = []
     if script is not None:
-        ids = list(script)
-        assert len(set(ids)) == len(ids), "script ids must be unique (successor is a function of the current id)"
-        prev = [script_prev] + ids[:-1]
-        assert script_prev is not None and script_prev not in ids
+        assert script_prev is not None
+        chains.append((int(script_prev), list(script)))
+    for prev0, ids in extra_chains or []:
+        chains.append((int(prev0), list(ids)))
+    if script is not None and not extra_chains:
+        chains.append(predict_action_chain(list(script)))
+    all_next = [i for _, ids in chains for i in ids]
+    assert len(set(all_next)) == len(all_next), "scripted ids must be unique (successor is a function of the current id)"
+    for prev0, ids in chains:
+        assert prev0 not in all_next
+        prev = [prev0] + ids[:-1]
         idx_next = torch.tensor(ids, device=device)
         idx_prev = torch.tensor(prev, device=device)
         head[idx_next] = (head_gain / H) * sd[p + "embed_tokens.weight"][idx_prev].float()
@@ -125,6 +134,14 @@ def make_state_dict(
 
 
 # === scripted continuation used by bench / smoke / parity ============================================================
+def predict_action_chain(main_script: Sequence[int], action_dim: int = 7) -> Tuple[int, List[int]]:
+    """Second planted chain for `predict_action` (which appends id 29871 and decodes `action_dim` tokens,
+    /root/reference/prismatic/extern/hf/modeling_prismatic.py:513-519): 29871 -> 7 action ids unused by the main script."""
+    used = set(main_script)
+    free = [i for i in range(31999, 31744, -1) if i not in used]
+    return 29871, free[3 : 3 + 5 * action_dim : 5]
+
+
 def default_script(tokenizer, n_new: int, seed: int = 0, n_policies: int = 2) -> List[int]:
     """A unique-id script of `n_new` tokens shaped like the grounded-CoT output grammar
     (/root/reference/prismatic/vla/datasets/datasets.py:483-581): filler "reasoning", then

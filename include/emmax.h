@@ -1,0 +1,153 @@
+/*
+ * libemmax — C ABI of the B200-native `generate_actions` hot path (Emma-X / OpenVLA).
+ *
+ * The reference (/root/reference) has NO native code and no FFI: every FLOP of its hot path runs inside un-vendored
+ * third-party packages (timm ViT, transformers Llama, flash-attn, ATen). The drop-in boundary a user sees is the Python
+ * class surface (emmax_b200.modeling), and THIS header is the boundary between that Python host code and the
+ * hand-written sm_100a kernels: plain pointers and sizes, no torch types, loaded with ctypes (emmax_b200/_lib.py).
+ * Each entry point cites the reference call site whose third-party kernel(s) it replaces.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (emx_last_error() gives the text); all pointers are
+ * DEVICE pointers unless stated; bf16 = 16-bit brain float, row-major, `ld*` = leading dimension in elements;
+ * nothing allocates, nothing synchronises; work is enqueued on `stream`.
+ */
+#ifndef EMMAX_H_
+#define EMMAX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* emx_stream_t; /* == cudaStream_t */
+
+const char* emx_last_error(void);
+int emx_abi_version(void);
+/* "sm_100a" — the only architecture the library is built for. */
+const char* emx_arch(void);
+
+/* ---- GEMM (tcgen05 / TMEM / TMA) -----------------------------------------------------------------------------
+ * C[M,N] = epilogue(A[M,K] * W[N,K]^T), bf16 in/out, fp32 accumulate.
+ * Replaces the cuBLASLt GEMMs behind: timm ViT Linears (modeling_prismatic.py:121), PrismaticProjector.fc1-3
+ * (modeling_prismatic.py:152-156), Llama q/k/v/o/gate/up/down at prefill (modeling_prismatic.py:404-415).
+ * Epilogue order (each step rounded to bf16 like the unfused reference ops):
+ *   +bias -> [GELU(erf)] -> [*layerscale] -> [+resid] -> [SwiGLU over interleaved (gate,up) column pairs]
+ * resid_mod > 0: residual row index is (m % resid_mod) (position-embedding broadcast over the batch). */
+#define EMX_EPI_GELU 1
+#define EMX_EPI_SWIGLU 2
+int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const void* bias,
+                  const void* layerscale, const void* resid, int ldr, int resid_mod, int flags, emx_stream_t stream);
+
+/* ---- normalisation ------------------------------------------------------------------------------------------
+ * LayerNorm (ViT blocks, eps 1e-6; ATen vectorized_layer_norm in the reference, via timm Block.norm1/norm2) and
+ * Llama RMSNorm (transformers LlamaRMSNorm: fp32 normalise -> bf16 -> * weight). */
+int emx_layernorm(const void* x, const void* weight, const void* bias, void* y, int rows, int dim, float eps, emx_stream_t stream);
+int emx_rmsnorm(const void* x, const void* weight, void* y, int rows, int dim, float eps, emx_stream_t stream);
+
+/* ---- ViT front end ------------------------------------------------------------------------------------------
+ * Patch-embed conv as im2col + GEMM (timm PatchEmbed.proj = Conv2d(3,D,14,14), invoked at modeling_prismatic.py:121).
+ * pixels: [B, C_total, H, W] bf16; channels [chan0, chan0+3) are gathered into rows of (c,ky,kx)-ordered patches,
+ * zero-padded to `kpad` columns: out [B*gh*gw, kpad]. */
+int emx_patch_im2col(const void* pixels, int B, int c_total, int chan0, int H, int W, int patch, void* out, int kpad, emx_stream_t stream);
+/* tokens[b, 0:prefix] = prefix_tokens; tokens[b, prefix+i] = bf16(patch_out[b,i] + pos[i])  (timm _pos_embed) */
+int emx_vit_assemble(const void* patch_out, const void* pos, const void* prefix_tokens, void* tokens, int B, int n_patches, int prefix,
+                     int D, emx_stream_t stream);
+/* features[b, i, col0:col0+D] = tokens[b, prefix+i, :]   (prefix strip + torch.cat(dim=2), modeling_prismatic.py:123) */
+int emx_vit_gather_features(const void* tokens, void* features, int B, int n_patches, int prefix, int D, int ld_features, int col0,
+                            emx_stream_t stream);
+
+/* ---- attention, full sequence (ViT: non-causal d=64/72; Llama prefill: causal d=128) ------------------------
+ * qkv: [B*T, 3*heads*hd] packed as the fused timm `qkv` Linear / the concatenated q,k,v Llama projections produce it
+ * (q | k | v, head-major inside each). out: [B*T, heads*hd]. Replaces F.scaled_dot_product_attention (timm Attention)
+ * and flash_attn_varlen_func (transformers LlamaFlashAttention2, selected at openvla_utils.py:45). */
+int emx_attn_fwd(const void* qkv, void* out, int B, int T, int heads, int head_dim, int causal, float scale, emx_stream_t stream);
+
+/* ---- Llama prefill helpers ----------------------------------------------------------------------------------
+ * RoPE (rotate_half form, bf16 cos/sin tables [max_pos, hd/2]) applied in place to q and k of a packed qkv buffer,
+ * then K and V rows are stored into the paged KV cache. positions: pos0 + t for t in [0,T).
+ * KV cache page layout: [page][head][page_size][hd] bf16; block_table[b*max_pages + p/page_size] = page id. */
+int emx_rope_kvstore(void* qkv, int B, int T, int heads, int head_dim, const void* cos_tab, const void* sin_tab, int pos0, void* k_cache,
+                     void* v_cache, const int32_t* block_table, int max_pages, int page_size, emx_stream_t stream);
+/* x[b, 0] = E[ids[b,0]]; x[b, 1:1+P] = patches[b]; x[b, 1+P+j] = E[ids[b,1+j]]   (modeling_prismatic.py:380-385) */
+int emx_embed_assemble(const int64_t* ids, int n_ids, const void* embed, const void* patches, int n_patches, void* x, int B, int H,
+                       emx_stream_t stream);
+/* h[m, i] = bf16(bf16(silu(gu[m, 2i])) * gu[m, 2i+1]) — unfused SwiGLU (transformers LlamaMLP) for interleaved gate/up */
+int emx_swiglu(const void* gate_up, void* h, int M, int I, emx_stream_t stream);
+
+/* ---- single-token kernels (building blocks; the decode product path is emx_decode_step) ---------------------- */
+/* y[N] = bf16(W[N,K] x[K]) (+ resid). */
+int emx_gemv_bf16(const void* W, int ldw, const void* x, void* y, const void* resid, int N, int K, emx_stream_t stream);
+/* logits = bf16(W x), argmax with lowest-index tie break (GenerationMixin greedy). logits_out (fp32 [N]) optional. */
+int emx_lmhead_argmax(const void* W, int ldw, const void* x, int N, int K, float* logits_out, int32_t* token_out, void* scratch,
+                      emx_stream_t stream);
+
+/* ---- persistent decode step ---------------------------------------------------------------------------------
+ * ONE launch = one new token for one sequence: embedding gather, 32 x (RMSNorm + QKV GEMV + RoPE + paged-KV append +
+ * split-KV attention + o_proj + residual + RMSNorm + gate/up GEMV + SwiGLU + down GEMV + residual), final norm,
+ * lm_head GEMV + greedy argmax, all inside one persistent kernel (1 CTA/SM) that streams the 13.2 GB of weights through
+ * a bulk-async (TMA) shared-memory ring and separates phases with grid barriers.
+ * Replaces the cached branch of PrismaticForConditionalGeneration.forward (modeling_prismatic.py:325-341) + one
+ * iteration of GenerationMixin's greedy loop (called at modeling_prismatic.py:519). */
+typedef struct emx_decode_state {
+  int32_t cur_token; /* token fed to this step (written by the previous step / prefill) */
+  int32_t pos;       /* number of tokens already in the KV cache == position id of cur_token */
+  int32_t n_generated;
+  int32_t finished;  /* set when EOS was produced; later launches return immediately */
+  /* kernel-private, zero once at allocation and never touched by the host afterwards: */
+  uint32_t barrier;  /* grid-barrier ticket counter (monotonic) */
+  uint32_t epoch;    /* completed launches (monotonic); barrier tickets are derived from it */
+  uint32_t pad0_[2];
+  uint32_t head_ticket[64]; /* per-head split-KV arrival counters */
+} emx_decode_state;
+
+typedef struct emx_decode_params {
+  /* model */
+  int32_t hidden, inter, heads, head_dim, layers, vocab;
+  float rms_eps;
+  const void* embed;     /* [vocab, hidden] */
+  const void* w_qkv;     /* [layers][3*hidden, hidden]  (q rows | k rows | v rows) */
+  const void* w_o;       /* [layers][hidden, hidden] */
+  const void* w_gateup;  /* [layers][2*inter, hidden]   row 2i = gate_i, row 2i+1 = up_i */
+  const void* w_down;    /* [layers][hidden, inter] */
+  const void* ln1;       /* [layers][hidden] input_layernorm */
+  const void* ln2;       /* [layers][hidden] post_attention_layernorm */
+  const void* final_norm;/* [hidden] */
+  const void* lm_head;   /* [vocab, hidden] */
+  const void* cos_tab;   /* [max_pos, head_dim/2] bf16 */
+  const void* sin_tab;
+  /* KV cache (paged) */
+  void* k_cache;         /* [layers][n_pages][heads][page_size][head_dim] */
+  void* v_cache;
+  const int32_t* block_table; /* [max_pages] page ids of this sequence */
+  int32_t page_size, n_pages, max_pages;
+  /* scratch (device) */
+  void* x;        /* [hidden] bf16 residual stream */
+  void* qkv;      /* [3*hidden] bf16 */
+  void* attn;     /* [hidden] bf16 */
+  void* h;        /* [inter] bf16 */
+  float* part;    /* [heads][kv_splits][head_dim + 2] fp32 split-KV partials */
+  float* argmax_part; /* [grid][2] */
+  /* outputs */
+  int32_t* out_tokens;  /* out_tokens[n_generated] = new token */
+  float* logits_out;    /* optional [vocab] fp32 (bf16-rounded values), for parity tests */
+  int32_t eos_token;    /* -1 disables EOS handling */
+  int32_t kv_splits;
+  emx_decode_state* state;
+} emx_decode_params;
+
+int emx_decode_step(const emx_decode_params* params, emx_stream_t stream);
+/* number of CTAs emx_decode_step launches (== SM count) and its dynamic shared memory, for sizing scratch buffers */
+int emx_decode_grid(void);
+
+/* ---- action de-tokeniser (device twin of ActionTokenizer.decode_token_ids_to_actions + un-normalise) ---------
+ * ids [n] int32 -> normalized[n], actions[n] fp64:  k = clip(vocab - id - 1, 0, n_bins-2); c = centres[k];
+ * actions = mask ? 0.5*(c+1)*(q99-q01)+q01 : c.   action_tokenizer.py:49-68; modeling_prismatic.py:522-535.
+ * stats arrays (q01,q99 fp64; mask uint8; length action_dim) may be null -> only `normalized` is written. */
+int emx_detokenize_actions(const int32_t* ids, int n, int vocab_size, int n_bins, const double* q01, const double* q99,
+                           const uint8_t* mask, int action_dim, double* normalized, double* actions, emx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMMAX_H_ */

@@ -1,0 +1,215 @@
+"""Per-kernel parity (through the C ABI) against torch restatements of the reference ops, on seeded inputs.
+bf16 outputs are compared with a 1-ulp-of-bf16 style tolerance (the kernels round at the same points as the eager ops
+but sum in a different order); integer / fp64 de-tokeniser output must be bit-exact."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from emmax_b200 import _lib
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _lib
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(BF)
+
+
+def assert_close_bf16(got, want, rel=2 ** -7, abs_=1e-3, frac=1.0, name=""):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    tol = abs_ + rel * want.abs()
+    bad = (err > tol).float().mean().item()
+    assert bad <= 1.0 - frac + 1e-12, f"{name}: {bad:.3%} of elements outside tolerance; max err {err.max().item():.4g}"
+
+
+GEMM_SHAPES = [
+    (261, 3072, 1024), (256, 1152, 4304), (256, 4304, 1152), (296, 12288, 4096), (256, 1024, 592), (1, 64, 64),
+    (130, 136, 72), (300, 8704, 2176), (261, 1024, 4096), (5, 32064, 256), (512, 688 * 2, 256),
+]  # fmt: skip
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(lib, M, N, K):
+    from emmax_b200.engine import Engine
+
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    out = torch.zeros(M, N, dtype=BF, device="cuda")
+    Engine.gemm(a, w, out)
+    torch.cuda.synchronize()
+    want = (a.float() @ w.float().T).to(BF)
+    assert_close_bf16(out, want, name=f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_epilogues(lib):
+    from emmax_b200._lib import EPI_GELU, EPI_SWIGLU
+    from emmax_b200.engine import Engine
+
+    M, N, K = 261, 1024, 512
+    a, w = rnd(M, K, seed=3), rnd(N, K, scale=K ** -0.5, seed=4)
+    bias, ls, res = rnd(N, seed=5), rnd(N, seed=6).abs(), rnd(M, N, seed=7)
+    acc = a.float() @ w.float().T
+    # bias + GELU
+    out = torch.zeros(M, N, dtype=BF, device="cuda")
+    Engine.gemm(a, w, out, bias=bias, flags=EPI_GELU)
+    want = torch.nn.functional.gelu((acc + bias.float()).to(BF))
+    assert_close_bf16(out, want, name="bias+gelu")
+    # bias + LayerScale + residual, in place on the residual buffer (how the ViT block uses it)
+    buf = res.clone()
+    Engine.gemm(a, w, buf, bias=bias, ls=ls, resid=buf)
+    want = ((acc + bias.float()).to(BF) * ls).to(BF) + res
+    assert_close_bf16(buf, want, name="bias+ls+resid")
+    # residual only (Llama o_proj / down_proj)
+    buf = res.clone()
+    Engine.gemm(a, w, buf, resid=buf)
+    assert_close_bf16(buf, acc.to(BF) + res, name="resid")
+    # broadcast residual rows (position embedding)
+    pos = rnd(29, N, seed=8)
+    out = torch.zeros(M, N, dtype=BF, device="cuda")
+    Engine.gemm(a, w, out, bias=bias, resid=pos, resid_mod=29)
+    want = (acc + bias.float()).to(BF) + pos[torch.arange(M, device="cuda") % 29]
+    assert_close_bf16(out, want, name="resid_mod")
+    # SwiGLU over interleaved (gate, up) columns
+    out = torch.zeros(M, N // 2, dtype=BF, device="cuda")
+    Engine.gemm(a, w, out, flags=EPI_SWIGLU)
+    gu = acc.to(BF)
+    want = torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2]
+    assert_close_bf16(out, want, name="swiglu")
+    torch.cuda.synchronize()
+
+
+def test_norms(lib):
+    from emmax_b200._lib import call, ptr, stream
+
+    for rows, dim in [(261, 1024), (256, 1152), (296, 4096), (3, 256), (7, 144)]:
+        x, w, b = rnd(rows, dim, seed=1), (1 + 0.1 * rnd(dim, seed=2).float()).to(BF), rnd(dim, scale=0.1, seed=3)
+        y = torch.empty_like(x)
+        call("emx_layernorm", ptr(x), ptr(w), ptr(b), ptr(y), rows, dim, 1e-6, stream())
+        want = torch.nn.functional.layer_norm(x, (dim,), w, b, 1e-6)
+        assert_close_bf16(y, want, name=f"layernorm {rows}x{dim}")
+        call("emx_rmsnorm", ptr(x), ptr(w), ptr(y), rows, dim, 1e-5, stream())
+        xf = x.float()
+        n = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(BF)
+        assert_close_bf16(y, w * n, name=f"rmsnorm {rows}x{dim}")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("B,T,heads,hd,causal", [(1, 261, 16, 64, 0), (2, 256, 16, 72, 0), (1, 296, 32, 128, 1), (3, 37, 2, 128, 1), (1, 5, 2, 72, 0)])
+def test_attention(lib, B, T, heads, hd, causal):
+    from emmax_b200._lib import call, ptr, stream
+
+    qkv = rnd(B * T, 3 * heads * hd, seed=11)
+    out = torch.empty(B * T, heads * hd, dtype=BF, device="cuda")
+    call("emx_attn_fwd", ptr(qkv), ptr(out), B, T, heads, hd, causal, hd ** -0.5, stream())
+    q, k, v = qkv.view(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4).float()
+    want = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=bool(causal))
+    want = want.transpose(1, 2).reshape(B * T, heads * hd)
+    assert_close_bf16(out, want, rel=2 ** -6, abs_=4e-3, name="attention")
+
+
+def test_rope_kvstore(lib):
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+
+    from emmax_b200._lib import call, ptr, stream
+
+    B, T, heads, hd, page, max_pages = 2, 70, 4, 128, 64, 3
+    qkv = rnd(B * T, 3 * heads * hd, seed=21)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64, device="cuda").float() / hd))
+    pos = torch.arange(256, device="cuda").float()
+    fr = pos[:, None] * inv[None]
+    cos_t, sin_t = fr.cos().to(BF).contiguous(), fr.sin().to(BF).contiguous()
+    kc = torch.zeros(B * max_pages, heads, page, hd, dtype=BF, device="cuda")
+    vc = torch.zeros_like(kc)
+    # deliberately scrambled page ids
+    tbl = torch.tensor([[4, 0, 2], [1, 5, 3]], dtype=torch.int32, device="cuda")
+    ref = qkv.clone().view(B, T, 3, heads, hd)
+    call("emx_rope_kvstore", ptr(qkv), B, T, heads, hd, ptr(cos_t), ptr(sin_t), 0, ptr(kc), ptr(vc), ptr(tbl), max_pages, page, stream())
+    torch.cuda.synchronize()
+    q, k, v = ref[:, :, 0].transpose(1, 2), ref[:, :, 1].transpose(1, 2), ref[:, :, 2].transpose(1, 2)  # [B, heads, T, hd]
+    cos = torch.cat([cos_t[:T], cos_t[:T]], -1)[None].expand(B, -1, -1)
+    sin = torch.cat([sin_t[:T], sin_t[:T]], -1)[None].expand(B, -1, -1)
+    qe, ke = apply_rotary_pos_emb(q, k, cos, sin)
+    got = qkv.view(B, T, 3, heads, hd)
+    assert torch.equal(got[:, :, 0].transpose(1, 2), qe), "RoPE(q) must be bit-exact with transformers' bf16 formula"
+    assert torch.equal(got[:, :, 1].transpose(1, 2), ke)
+    for b in range(B):
+        for t in (0, 1, 63, 64, 69):
+            pg = int(tbl[b, t // page])
+            assert torch.equal(kc[pg, :, t % page], ke[b, :, t])
+            assert torch.equal(vc[pg, :, t % page], v[b, :, t])
+
+
+def test_gemv_and_argmax(lib):
+    from emmax_b200._lib import call, ptr, stream
+
+    N, K = 32064, 4096
+    w, x, r = rnd(N, K, scale=K ** -0.5, seed=31), rnd(K, seed=32), rnd(N, seed=33)
+    y = torch.empty(N, dtype=BF, device="cuda")
+    call("emx_gemv_bf16", ptr(w), K, ptr(x), ptr(y), ptr(r), N, K, stream())
+    want = (w.float() @ x.float()).to(BF) + r
+    assert_close_bf16(y, want, name="gemv+resid")
+    logits = torch.empty(N, dtype=torch.float32, device="cuda")
+    tok = torch.zeros(1, dtype=torch.int32, device="cuda")
+    call("emx_lmhead_argmax", ptr(w), K, ptr(x), N, K, ptr(logits), ptr(tok), None, stream())
+    torch.cuda.synchronize()
+    assert int(tok) == int(torch.argmax(logits))
+    assert_close_bf16(logits, (w.float() @ x.float()).to(BF), name="lm_head logits")
+    # tie break: lowest index
+    w2 = w.clone()
+    w2[100] = w2[7]
+    call("emx_lmhead_argmax", ptr(w2), K, ptr(w2[7].contiguous()), N, K, ptr(logits), ptr(tok), None, stream())
+    torch.cuda.synchronize()
+    assert int(tok) == int(torch.argmax(logits)) == 7
+
+
+def test_vit_frontend_kernels(lib):
+    from emmax_b200._lib import call, ptr, stream
+
+    B, D, P, prefix = 2, 128, 14, 5
+    pix = rnd(B, 6, 224, 224, seed=41)
+    kpad = 592
+    out = torch.empty(B * 256, kpad, dtype=BF, device="cuda")
+    call("emx_patch_im2col", ptr(pix), B, 6, 3, 224, 224, P, ptr(out), kpad, stream())
+    want = torch.nn.functional.unfold(pix[:, 3:6].float(), kernel_size=P, stride=P).transpose(1, 2).reshape(B * 256, 588).to(BF)
+    assert torch.equal(out[:, :588], want) and torch.all(out[:, 588:] == 0)
+    pe, pos, pre = rnd(B * 256, D, seed=42), rnd(256, D, seed=43), rnd(prefix, D, seed=44)
+    tok = torch.empty(B * 261, D, dtype=BF, device="cuda")
+    call("emx_vit_assemble", ptr(pe), ptr(pos), ptr(pre), ptr(tok), B, 256, prefix, D, stream())
+    want = torch.cat([pre[None].expand(B, -1, -1), pe.view(B, 256, D) + pos[None]], 1)
+    assert torch.equal(tok.view(B, 261, D), want)
+    feats = torch.zeros(B * 256, 272, dtype=BF, device="cuda")
+    call("emx_vit_gather_features", ptr(tok), ptr(feats), B, 256, prefix, D, 272, 144, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(feats[:, 144:], tok.view(B, 261, D)[:, prefix:].reshape(B * 256, D)) and torch.all(feats[:, :144] == 0)
+
+
+def test_detokenize_bit_exact(lib, golden_dir):
+    from emmax_b200._lib import call, ptr, stream
+
+    with open(os.path.join(golden_dir, "detok_golden.json")) as f:
+        g = json.load(f)
+    ids = torch.tensor(g["ids"], dtype=torch.int32, device="cuda")
+    norm = torch.empty(ids.numel(), dtype=torch.float64, device="cuda")
+    call("emx_detokenize_actions", ptr(ids), ids.numel(), g["vocab_size"], 256, None, None, None, 0, ptr(norm), None, stream())
+    want = np.array([float.fromhex(x) for x in g["decoded"]])
+    assert np.array_equal(norm.cpu().numpy(), want), "device de-tokeniser must be bit-exact with the reference's numpy"
+    u = g["unnorm"]
+    ids = torch.tensor(u["ids"], dtype=torch.int32, device="cuda")
+    q01 = torch.tensor(u["stats"]["q01"], dtype=torch.float64, device="cuda")
+    q99 = torch.tensor(u["stats"]["q99"], dtype=torch.float64, device="cuda")
+    mask = torch.tensor(u["stats"]["mask"], dtype=torch.uint8, device="cuda")
+    norm, act = torch.empty(7, dtype=torch.float64, device="cuda"), torch.empty(7, dtype=torch.float64, device="cuda")
+    call("emx_detokenize_actions", ptr(ids), 7, g["vocab_size"], 256, ptr(q01), ptr(q99), ptr(mask), 7, ptr(norm), ptr(act), stream())
+    assert np.array_equal(act.cpu().numpy(), np.array([float.fromhex(x) for x in u["actions_hex"]]))
