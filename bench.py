@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the `generate_actions` hot path (BASELINE.json: actions/sec at bs=1).
+
+A "step" is one complete action request: one synthetic 224x224 image + a fixed 40-id prompt -> DINOv2+SigLIP ViT
+-> projector -> Llama-2-7B prefill -> greedy decode of 512 reasoning+action tokens -> action de-tokenise
+(BASELINE.json configs[1]; full Emma-X architecture, seeded random-init bf16 weights, EOS planted at token 512).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (N>1: torchrun, one replica per GPU + one NCCL
+                                                               all-gather of the 7 action tokens per step)
+  python bench.py --impl reference [...]                       the reference's own CPU path (torch-eager oracle port),
+                                                               bounded sample, host cores only
+
+`value`  : actions/s with inputs already resident in HBM (engine.generate on device tensors).
+`e2e`    : actions/s through the public API (`model.generate_actions(inputs, tokenizer, ...)`) from PINNED HOST
+           buffers: H2D of pixels+ids, D2H of the generated ids, host text decode + Solver parse, every step.
+`roofline`: the decode-step kernel (99 % of a step): algorithmic bytes per launch / measured launch duration vs the
+           measured HBM peak in MEASURED_PEAKS.json.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_NEW = 512
+PROMPT_LEN = 40
+WORKLOAD = "bs=1 single-GPU bf16, 224x224 image, max_new_tokens=512 grounded-CoT decode (BASELINE.json configs[1])"
+
+
+def synthetic_request(seed: int):
+    """image = default_rng(seed).integers(0,256,(224,224,3)); prompt = [1] + rng(1234).integers(3,31744,39)."""
+    from PIL import Image
+
+    image = Image.fromarray(np.random.default_rng(seed).integers(0, 256, (224, 224, 3), dtype=np.uint8))
+    ids = [1] + np.random.default_rng(1234).integers(3, 31744, PROMPT_LEN - 1).tolist()
+    return image, torch.tensor([ids], dtype=torch.long)
+
+
+def build_weights(device):
+    from emmax_b200 import SyntheticLlamaTokenizer, emma_x_config
+    from emmax_b200.synthetic import default_script, make_state_dict
+
+    cfg = emma_x_config()
+    tok = SyntheticLlamaTokenizer()
+    _, ids = synthetic_request(0)
+    script = default_script(tok, N_NEW, seed=0)
+    sd = make_state_dict(cfg, seed=0, device=device, script=script, script_prev=int(ids[0, -1]))
+    return cfg, tok, sd, script
+
+
+def decode_bytes(cfg, ctx: int) -> int:
+    """Algorithmic bytes of one decode step at context `ctx` (tokens already cached): SURVEY.md §8d / BASELINE.md §3."""
+    t = cfg.text_config
+    H, I, L, V = t.hidden_size, t.intermediate_size, t.num_hidden_layers, t.vocab_size
+    weights = 2 * (L * (4 * H * H + 3 * H * I) + V * H)
+    kv_row = 2 * 2 * L * H  # K and V, bf16, all layers
+    return weights + kv_row * ctx + kv_row
+
+
+class ClockSampler(threading.Thread):
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int) -> None:
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+
+    def run(self) -> None:
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")  # fmt: skip
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self.join(timeout=6)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}  # fmt: skip
+
+
+# =====================================================================================================================
+# CPU reference arm (oracle port), bounded sample
+# =====================================================================================================================
+def cpu_reference_sample(cfg, sd, n_decode: int = 4):
+    """One bounded sample of the workload on the host cores with the torch-eager oracle (bf16 weights, sdpa):
+    vision + projector + prefill (S = 296) once, then `n_decode` cached decode steps; actions/s is extrapolated to the
+    512-token request as 1 / (t_prefill + 511 * t_token)."""
+    from oracle.model import OracleVLA
+
+    oracle = OracleVLA.from_state_dict(cfg, sd, device="cpu", dtype=torch.bfloat16, attn_implementation="sdpa")
+    image, ids = synthetic_request(0)
+    from emmax_b200 import PrismaticImageProcessor
+
+    pv = PrismaticImageProcessor()(image, return_tensors="pt")["pixel_values"].to(torch.bfloat16)
+    t0 = time.perf_counter()
+    logits, past = oracle.prefill(ids, pv)
+    tok = int(torch.argmax(logits[:, -1], dim=-1)[0])
+    t1 = time.perf_counter()
+    for _ in range(n_decode):
+        logits, past = oracle.step(torch.tensor([[tok]]), past)
+        tok = int(torch.argmax(logits[:, -1], dim=-1)[0])
+    t2 = time.perf_counter()
+    t_prefill, t_token = t1 - t0, (t2 - t1) / n_decode
+    return oracle, {"t_prefill_s": t_prefill, "t_token_s": t_token, "actions_per_s": 1.0 / (t_prefill + (N_NEW - 1) * t_token)}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    cfg, tok, sd, _ = build_weights(dev)
+    sd = {k: v.cpu() for k, v in sd.items()}
+    n_decode = 4
+    oracle, first = cpu_reference_sample(cfg, sd, n_decode)
+    # keep the whole run bounded: each step is one sample (prefill + n_decode tokens)
+    per_step = first["t_prefill_s"] + n_decode * first["t_token_s"]
+    budget_s = 240.0
+    steps = max(1, min(args.steps, int(budget_s / per_step) - 1))
+    warm = max(0, min(args.warmup, int(budget_s / per_step) - 1 - steps))
+    from emmax_b200 import PrismaticImageProcessor
+
+    image, ids = synthetic_request(0)
+    pv = PrismaticImageProcessor()(image, return_tensors="pt")["pixel_values"].to(torch.bfloat16)
+    samples = []
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        logits, past = oracle.prefill(ids, pv)
+        tk = int(torch.argmax(logits[:, -1], dim=-1)[0])
+        t1 = time.perf_counter()
+        for _ in range(n_decode):
+            logits, past = oracle.step(torch.tensor([[tk]]), past)
+            tk = int(torch.argmax(logits[:, -1], dim=-1)[0])
+        t2 = time.perf_counter()
+        if i >= warm:
+            samples.append((t1 - t0, (t2 - t1) / n_decode))
+    if not samples:
+        samples = [(first["t_prefill_s"], first["t_token_s"])]
+    tp = statistics.median(s[0] for s in samples)
+    tt = statistics.median(s[1] for s in samples)
+    step_s = tp + (N_NEW - 1) * tt
+    value = 1.0 / step_s
+    cores = torch.get_num_threads()
+    sample = (f"torch-eager oracle port on CPU, bf16 weights, sdpa: vision+prefill(S=296) + {n_decode} cached decode tokens per step, "
+              f"{len(samples)} timed steps ({warm} warm-up; requested {args.steps}/{args.warmup}); extrapolated to the 512-token request: "
+              f"t_prefill={tp:.2f}s, t_token={tt * 1e3:.0f}ms; os.cpu_count()={os.cpu_count()}")  # fmt: skip
+    line = {
+        "impl": "reference", "metric": "actions/sec (7-DoF)", "value": value, "unit": "actions/s", "n_gpus": args.gpus,
+        "steps": len(samples), "warmup": warm, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "prompt_ids": PROMPT_LEN, "prefill_positions": PROMPT_LEN + 256, "new_tokens": N_NEW,
+                   "weights": "seeded random-init, full Emma-X architecture", "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": "actions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
+def run_ours(args) -> None:
+    import torch.distributed as dist
+
+    from emmax_b200 import AutoProcessor, OpenVLAForActionPrediction, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+
+    cfg, tok, sd, script = build_weights(dev)
+    cpu_sd = {k: v.cpu() for k, v in sd.items()} if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    model = OpenVLAForActionPrediction(cfg, sd, max_context=1024).to(dev)
+    eng = model.engine
+    proc = AutoProcessor.from_pretrained(None)
+
+    # request stream: rank r serves frames r, r+N, ...; same fixed prompt
+    def request(i: int):
+        image, ids = synthetic_request(rank + i * world)
+        return proc.image_processor(image, return_tensors="pt")["pixel_values"].to(torch.bfloat16), ids
+
+    reqs = [request(i) for i in range(W + K)]
+    d_reqs = [(pv.to(dev), ids.to(dev)) for pv, ids in reqs]
+    h_reqs = [(pv.pin_memory(), ids.pin_memory()) for pv, ids in reqs]
+    gathered = torch.zeros((world, 8), dtype=torch.int32, device=dev)
+    mine = torch.zeros(8, dtype=torch.int32, device=dev)
+    act_lo = script.index(tok.key_id("POLICIES:")) + 2  # first policy's 7 action tokens
+
+    def tick_gather(new_tokens: torch.Tensor) -> None:
+        """the ONE collective of the path: all-gather of each replica's action tokens, enqueued on the decode stream"""
+        if world > 1:
+            mine[:7].copy_(new_tokens[act_lo : act_lo + 7])
+            dist.all_gather_into_tensor(gathered.view(-1), mine)
+
+    def sync_all() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n_warm: int, n: int):
+        for i in range(n_warm):
+            fn(i)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count
+        e0.record()
+        for i in range(n_warm, n_warm + n):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), _lib.launch_count - l0
+
+    # ---- device-resident throughput (`value`) + roofline of the decode kernel ------------------------------------
+    decode_ms, decode_launches, decode_bytes_total = [0.0], [0], [0]
+
+    def step_device(i: int) -> None:
+        pv, ids = d_reqs[i]
+        new, _ = eng.generate(ids, pv, N_NEW, eos_token_id=2)
+        tick_gather(new)
+        ev0, ev1, n, S = eng.last_decode
+        if i >= W:
+            decode_ms[0] += ev0.elapsed_time(ev1)
+            decode_launches[0] += n
+            decode_bytes_total[0] += sum(decode_bytes(cfg, S + j) for j in range(n))
+        assert new.numel() == N_NEW, f"expected {N_NEW} tokens, got {new.numel()}"
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    total_ms, launches = timed(step_device, W, K)
+    clocks = sampler.stop()
+    value = world * K / (total_ms / 1e3)
+
+    # ---- end to end through the public API from pinned host memory (`e2e`) ------------------------------------------
+    last_action = [None]
+
+    def step_e2e(i: int) -> None:
+        pv, ids = h_reqs[i]
+        inputs = {"input_ids": ids.to(dev, non_blocking=True), "pixel_values": pv.to(dev, non_blocking=True)}
+        action, text = model.generate_actions(inputs, proc.tokenizer, do_sample=False, max_new_tokens=N_NEW)
+        if world > 1:
+            tick_gather(eng.d_out_tokens)
+        last_action[0] = action
+
+    e2e_ms, _ = timed(step_e2e, 1, K)
+    e2e_value = world * K / (e2e_ms / 1e3)
+    h2d = reqs[0][0].numel() * 2 + reqs[0][1].numel() * 8
+    d2h = N_NEW * 4 + 4
+
+    # ---- per-token latency distribution (untimed extra pass, events around every launch) ---------------------------
+    import ctypes as C
+
+    pv, ids = d_reqs[0]
+    eng.generate(ids, pv, 2, eos_token_id=None)
+    p = eng._decode_params(0)
+    lib = _lib.load()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(129)]
+    evs[0].record()
+    for j in range(128):
+        _lib.check(lib.emx_decode_step(C.byref(p), _lib.stream()))
+        evs[j + 1].record()
+    torch.cuda.synchronize()
+    tok_ms = sorted(evs[j].elapsed_time(evs[j + 1]) for j in range(128))
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        avg_launch_ms = decode_ms[0] / max(decode_launches[0], 1)
+        achieved = decode_bytes_total[0] / max(decode_launches[0], 1) / (avg_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "decode_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        line = {
+            "metric": "actions/sec (7-DoF)", "value": value, "unit": "actions/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "prompt_ids": PROMPT_LEN, "prefill_positions": PROMPT_LEN + 256, "new_tokens": N_NEW,
+                       "weights": "seeded random-init, full Emma-X architecture (DINOv2-L/14-reg4 + SigLIP-so400m/14 + Llama-2-7B)",
+                       "parallelism": f"replicas x{world}" + (" + 1 NCCL all-gather of action tokens per step" if world > 1 else ""),
+                       "l2": "per-step inputs (13.2 GB of weights streamed per token) exceed the 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "decode_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_launch": decode_bytes_total[0] / max(decode_launches[0], 1), "avg_launch_ms": avg_launch_ms,
+                         "launches_timed": decode_launches[0], "share_of_step": decode_ms[0] / total_ms},
+            "decode_ms_per_token": {"p50": tok_ms[64], "p10": tok_ms[12], "p90": tok_ms[115], "context": "296..424"},
+            "action": [round(float(a), 6) for a in last_action[0]],
+        }  # fmt: skip
+        if cpu_sd is not None:
+            try:
+                _, s = cpu_reference_sample(cfg, cpu_sd, 4)
+                line["cpu_baseline"] = {
+                    "value": s["actions_per_s"], "unit": "actions/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": (f"torch-eager oracle port on CPU, bf16 weights: vision+prefill(S=296) once ({s['t_prefill_s']:.2f}s) + 4 cached decode "
+                               f"tokens ({s['t_token_s'] * 1e3:.0f} ms/token), extrapolated to the 512-token request"),
+                }  # fmt: skip
+            except Exception as e:  # the headline number must survive a CPU-side problem
+                line["cpu_baseline"] = {"value": None, "unit": "actions/s", "cores": torch.get_num_threads(), "kind": "port",
+                                        "sample": f"failed: {type(e).__name__}: {e}"}  # fmt: skip
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

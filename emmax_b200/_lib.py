@@ -106,5 +106,16 @@ def check(rc: int) -> None:
         raise EmxError(load().emx_last_error().decode() or f"libemmax error {rc}")
 
 
+# kernels launched per C-ABI call (bookkeeping for bench.py's `gpu_launches`; graph replays add their captured count)
+_KERNELS_PER_CALL = {"emx_lmhead_argmax": 2}
+launch_count = 0
+
+
+def count_launches(n: int) -> None:
+    global launch_count
+    launch_count += n
+
+
 def call(name: str, *args: Any) -> None:
     check(getattr(load(), name)(*args))
+    count_launches(_KERNELS_PER_CALL.get(name, 1))

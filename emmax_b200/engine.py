@@ -50,7 +50,8 @@ class Engine:
         self.t = config.text_config
         self.max_batch, self.kv_splits = max_batch, kv_splits
         self.max_context = _ceil_to(max_context, self.PAGE)
-        self._graphs: Dict[Tuple[int, int], Tuple[torch.cuda.CUDAGraph, dict]] = {}
+        self._graphs: Dict[Tuple[int, int], Tuple[torch.cuda.CUDAGraph, int]] = {}
+        self.last_decode = None
         with torch.cuda.device(device):
             self._pack(state_dict)
             self._alloc()
@@ -261,11 +262,15 @@ class Engine:
             # warm-up once outside capture (sets func attributes / driver entry points), then capture
             self._prefill_body(ws, B, n_ids)
             torch.cuda.current_stream().synchronize()
+            before = _lib.launch_count
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._prefill_body(ws, B, n_ids)
-            self._graphs[key] = (g, ws)
-        self._graphs[key][0].replay()
+            self._graphs[key] = (g, _lib.launch_count - before)
+            _lib.count_launches(before - _lib.launch_count)  # capture enqueued nothing
+        g, n_kernels = self._graphs[key]
+        g.replay()
+        _lib.count_launches(n_kernels)
         return ws
 
     def _decode_params(self, b: int = 0) -> DecodeParams:
@@ -317,10 +322,14 @@ class Engine:
         lib = _lib.load()
         s = stream()
         pending = None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        n_launched = 0
         for step in range(1, max_new_tokens):
             if return_logits:
                 p.logits_out = logits[step].data_ptr()
             _lib.check(lib.emx_decode_step(C.byref(p), s))
+            n_launched += 1
             if forced is not None:
                 st[0].fill_(int(forced[step]))  # teacher forcing: overwrite the token the next step will embed
             if p.eos_token >= 0 and step % poll_every == 0:
@@ -330,5 +339,8 @@ class Engine:
                 self.h_flag.copy_(st[0:4], non_blocking=True)
                 pending = torch.cuda.Event()
                 pending.record()
+        ev1.record()
+        _lib.count_launches(n_launched)
+        self.last_decode = (ev0, ev1, n_launched, S)  # bench.py: average decode-step duration on this stream
         n = int(st[2].item())  # device -> host sync point (the reference syncs every token)
         return self.d_out_tokens[:n].clone(), (logits[:n] if return_logits else None)

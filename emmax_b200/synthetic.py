@@ -73,7 +73,7 @@ def make_state_dict(
     script_prev: Optional[int] = None,
     extra_chains: Optional[Sequence[Tuple[int, Sequence[int]]]] = None,
     head_gain: float = 16.0,
-    resid_scale: float = 0.35,
+    resid_scale: float = 1.0,
 ) -> Dict[str, torch.Tensor]:
     """Build a full state dict (reference names). `script`/`script_prev`: see module docstring."""
     device = torch.device(device)
@@ -93,22 +93,25 @@ def make_state_dict(
     sd["projector.fc3.weight"] = _randn((H, H), 0.05, gen, device, dtype)
     sd["projector.fc3.bias"] = _randn((H,), 0.02, gen, device, dtype)
 
-    # Token embeddings at unit scale; the residual branches (o_proj / down_proj) are scaled so the sum of all layer
-    # contributions is comparable to the embedding (see module docstring).
+    # Token embeddings at unit scale. Projections are scaled so that every Linear output is O(1) at any width
+    # (q/k/v/gate/up: std 1/sqrt(H)), and the residual branches (o_proj / down_proj) so that the SUM of all 2L
+    # branch outputs has rms ~1, i.e. comparable to the embedding: the final hidden state keeps cos ~0.7 with the
+    # current token's embedding (what the scripted head keys on) while every layer still matters numerically.
     p = "language_model.model."
     emb32 = torch.empty((t.vocab_size, H), dtype=torch.float32, device=device).normal_(0.0, 1.0, generator=gen)
     sd[p + "embed_tokens.weight"] = emb32.to(dtype)
-    I = t.intermediate_size
-    for i in range(t.num_hidden_layers):
+    I, L = t.intermediate_size, t.num_hidden_layers
+    a = resid_scale * 1.47 / L**0.5
+    for i in range(L):
         b = f"{p}layers.{i}."
         sd[b + "input_layernorm.weight"] = _randn((H,), 0.02, gen, device, dtype, mean=1.0)
         for n in ("q_proj", "k_proj", "v_proj"):
-            sd[b + f"self_attn.{n}.weight"] = _randn((H, H), 0.02, gen, device, dtype)
-        sd[b + "self_attn.o_proj.weight"] = _randn((H, H), 0.02 * resid_scale, gen, device, dtype)
+            sd[b + f"self_attn.{n}.weight"] = _randn((H, H), H**-0.5, gen, device, dtype)
+        sd[b + "self_attn.o_proj.weight"] = _randn((H, H), a * H**-0.5, gen, device, dtype)
         sd[b + "post_attention_layernorm.weight"] = _randn((H,), 0.02, gen, device, dtype, mean=1.0)
-        sd[b + "mlp.gate_proj.weight"] = _randn((I, H), 0.02, gen, device, dtype)
-        sd[b + "mlp.up_proj.weight"] = _randn((I, H), 0.02, gen, device, dtype)
-        sd[b + "mlp.down_proj.weight"] = _randn((H, I), 0.02 * resid_scale, gen, device, dtype)
+        sd[b + "mlp.gate_proj.weight"] = _randn((I, H), H**-0.5, gen, device, dtype)
+        sd[b + "mlp.up_proj.weight"] = _randn((I, H), H**-0.5, gen, device, dtype)
+        sd[b + "mlp.down_proj.weight"] = _randn((H, I), a * I**-0.5, gen, device, dtype)
     sd[p + "norm.weight"] = _randn((H,), 0.02, gen, device, dtype, mean=1.0)
 
     # un-scripted rows give ~N(0,1) logits; a scripted row peaks at ~head_gain * cos(hidden, embed[prev])
