@@ -43,7 +43,7 @@ class DecodeParams(C.Structure):
         ("x", C.c_void_p), ("qkv", C.c_void_p), ("attn", C.c_void_p), ("h", C.c_void_p),
         ("part", C.c_void_p), ("argmax_part", C.c_void_p),
         ("out_tokens", C.c_void_p), ("logits_out", C.c_void_p),
-        ("eos_token", C.c_int32), ("kv_splits", C.c_int32), ("state", C.c_void_p),
+        ("eos_token", C.c_int32), ("kv_splits", C.c_int32), ("state", C.c_void_p), ("dbg", C.c_void_p),
     ]  # fmt: skip
 
 

@@ -143,7 +143,14 @@ __device__ __forceinline__ void load_vec(const __nv_bfloat16* v, __nv_bfloat16* 
 
 struct RingState {
   uint32_t it;  // stage counter, identical sequence in producer and consumers
+  long long waited;  // profiling: cycles spent waiting on the ring (only meaningful when params.dbg != null)
 };
+
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---- producer: stream one phase's rows of this CTA through the ring --------------------------------------------------
 __device__ __forceinline__ void produce_phase(const PhaseDesc& d, uint8_t* ring, uint64_t* full, uint64_t* empty, RingState& rs,
@@ -157,7 +164,9 @@ __device__ __forceinline__ void produce_phase(const PhaseDesc& d, uint8_t* ring,
       const int slot = rs.it % DEC_STAGES;
       const uint32_t ph = (rs.it / DEC_STAGES) & 1;
       if (lane == 0) {
+        const long long t0 = clock64();
         mbar_wait(&empty[slot], ph ^ 1);
+        rs.waited += clock64() - t0;
         mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(nrows) * klen * 2);
       }
       __syncwarp();
@@ -183,7 +192,9 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
       const int klen = min(DEC_KC, d.K - k0);
       const int slot = rs.it % DEC_STAGES;
       const uint32_t ph = (rs.it / DEC_STAGES) & 1;
+      const long long t0 = clock64();
       mbar_wait(&full[slot], ph);
+      rs.waited += clock64() - t0;
       if (active) {
         const uint4* w0 = reinterpret_cast<const uint4*>(ring + slot * DEC_STAGE_BYTES + (warp * DEC_RPW) * (DEC_KC * 2));
         const uint4* w1 = w0 + (DEC_KC * 2) / 16;
@@ -360,7 +371,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   if (s_state[3]) return;  // sequence already hit EOS: nothing to do (uniform across the grid)
 
   const int L = p.layers, H = p.hidden;
-  RingState rs{0};
+  RingState rs{0, 0};
+  long long* dbg = (blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
+  int dbg_i = 0;
+  auto mark = [&]() {
+    if (dbg && tid == 0) dbg[dbg_i] = global_ns();
+    ++dbg_i;
+  };
 
   if (warp == DEC_CWARPS) {
     // ===================== producer warp =====================
@@ -368,6 +385,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     for (int layer = 0; layer < L; ++layer)
       for (int kind = PH_QKV; kind <= PH_DOWN; ++kind) produce_phase(phase_desc(p, layer, kind), ring, full, empty, rs, policy, lane);
     produce_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, rs, policy, lane);
+    if (dbg && lane == 0) dbg[15 * L + 9] = rs.waited;
     return;
   }
 
@@ -384,39 +402,54 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   for (int layer = 0; layer < L; ++layer) {
     const __nv_bfloat16* resid_src = (layer == 0) ? emb_row : x;
     // ---- P1: RMSNorm + QKV ----
+    mark();
     load_rmsnorm(resid_src, static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
     consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, rs, xs, warp, lane, [&](int row, float a0, float a1) {
       *reinterpret_cast<uint32_t*>(qkv + row) = pack_bf16(a0, a1);
     });
+    mark();
     grid_sync(&st->barrier, target);
+    mark();
     // ---- P2: RoPE + KV append + split-KV attention ----
     for (int item = blockIdx.x; item < p.heads * p.kv_splits; item += gridDim.x)
       attention_item(p, layer, item / p.kv_splits, item % p.kv_splits, pos, reinterpret_cast<float*>(xs), red);
+    mark();
     grid_sync(&st->barrier, target);
+    mark();
     // ---- P3: o_proj + residual ----
     load_vec(static_cast<const __nv_bfloat16*>(p.attn), xs, H);
+    mark();
     consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, rs, xs, warp, lane, [&](int row, float a0, float a1) {
       const uint32_t r = ldg_cg_u32(resid_src + row);
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
+    mark();
     grid_sync(&st->barrier, target);
+    mark();
     // ---- P4: RMSNorm + gate/up + SwiGLU ----
     load_rmsnorm(x, static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
+    mark();
     consume_phase(phase_desc(p, layer, PH_GATEUP), ring, full, empty, rs, xs, warp, lane, [&](int row, float g, float u) {
       hbuf[row >> 1] = __float2bfloat16_rn(bf16_round(silu(bf16_round(g))) * bf16_round(u));
     });
+    mark();
     grid_sync(&st->barrier, target);
+    mark();
     // ---- P5: down_proj + residual ----
     load_vec(hbuf, xs, p.inter);
+    mark();
     consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, rs, xs, warp, lane, [&](int row, float a0, float a1) {
       const uint32_t r = ldg_cg_u32(x + row);
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
+    mark();
     grid_sync(&st->barrier, target);
   }
+  mark();
 
   // ---- final norm + lm_head + greedy argmax ----
   load_rmsnorm(x, static_cast<const __nv_bfloat16*>(p.final_norm), xs, H, p.rms_eps, red);
+  mark();
   float best = -INFINITY;
   int best_i = 0x7fffffff;
   consume_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, rs, xs, warp, lane, [&](int row, float a0, float a1) {
@@ -425,6 +458,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     if (v0 > best) best = v0, best_i = row;  // rows ascend within a warp: strict '>' keeps the lowest index
     if (v1 > best) best = v1, best_i = row + 1;
   });
+  mark();
+  if (dbg && tid == 0) dbg[15 * L + 8] = rs.waited;
   if (lane == 0) s_best[warp] = best, reinterpret_cast<int*>(s_best + 8)[warp] = best_i;
   cbar();
   if (tid == 0) {
@@ -437,6 +472,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     reinterpret_cast<int*>(p.argmax_part)[2 * blockIdx.x + 1] = best_i;
   }
   grid_sync(&st->barrier, target);
+  mark();
   if (blockIdx.x == 0 && warp == 0) {
     float b = -INFINITY;
     int bi = 0x7fffffff;

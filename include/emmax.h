@@ -134,6 +134,9 @@ typedef struct emx_decode_params {
   int32_t eos_token;    /* -1 disables EOS handling */
   int32_t kv_splits;
   emx_decode_state* state;
+  /* optional profiling buffer (device, >= 16*layers + 16 int64): CTA 0 stores %globaltimer at every phase boundary,
+   * then [15*layers + 8 ..] = cycles warp 0 waited for weights / cycles the producer waited for a free ring slot */
+  int64_t* dbg;
 } emx_decode_params;
 
 int emx_decode_step(const emx_decode_params* params, emx_stream_t stream);
