@@ -7,13 +7,17 @@
 //
 // B200 design (HBM-bound: 13.2 GB of bf16 weights per token):
 //   * grid = one CTA per SM (148), 8 consumer warps + 1 producer warp, launched cooperatively (co-residency guaranteed);
-//   * the producer warp walks the STATIC weight schedule of its CTA (layer -> qkv, o, gate/up, down -> row group ->
-//     K chunk) and keeps a 6 x 32 KB shared-memory ring full with cp.async.bulk (TMA engine) copies, L2 evict-first;
-//     it never waits for a grid barrier, so HBM keeps streaming while consumers synchronise or run attention;
-//   * consumer warp w owns 2 rows of every 16-row group: 16-B conflict-free LDS of weights and of the bf16 activation
-//     vector, fp32 FMA, one warp-shuffle reduction per row, fused epilogues (residual add, SwiGLU, argmax);
+//   * the producer warp walks the STATIC weight schedule of its CTA (layer -> qkv, o, gate/up, down -> 16-row group ->
+//     1024-column chunk) and keeps a 6 x 32 KB shared-memory ring full with cp.async.bulk (TMA engine) copies, L2
+//     evict-first, and runs a second, deeper look-ahead with cp.async.bulk.prefetch.L2 so HBM keeps streaming into the
+//     126 MB L2 while the consumers sit in a grid barrier or in the attention phase; it never waits for a grid barrier;
+//   * consumers: the 16 rows x 1024 columns of a stage are one A operand of mma.sync.m16n8k16 (bf16, fp32 accumulate);
+//     each warp owns a 128-column slice (ldmatrix from a 16-B padded, conflict-free row stride), the activation vector is
+//     the B operand straight from shared memory; per-warp partial row sums are combined once per row group. ~10x fewer
+//     issue slots per byte than a SIMT dot product, so the drain rate is far above the HBM feed rate;
 //   * RMSNorm is recomputed per CTA from the 8 KB residual vector (cheaper than a launch + barrier);
-//   * attention: (head, kv-split) items across CTAs, RoPE + KV append fused in, last-arriving split combines;
+//   * attention: (head, kv-split) items across CTAs, RoPE + KV append fused in, lane-per-key scores with all row loads in
+//     flight at once, last-arriving split combines;
 //   * phases are separated by a ticket grid barrier (release/acquire at gpu scope); cross-CTA activations are read
 //     with ld.global.cg (L1 bypass).
 // Rounding points mirror the torch-eager reference (bf16 after every Linear / norm / residual add / activation).
@@ -25,17 +29,18 @@ namespace emx {
 constexpr int DEC_CWARPS = 8;                    // consumer warps
 constexpr int DEC_CTHREADS = DEC_CWARPS * 32;    // 256
 constexpr int DEC_THREADS = DEC_CTHREADS + 32;   // + producer warp
-constexpr int DEC_RPW = 2;                       // rows per consumer warp per group
-constexpr int DEC_GROUP = DEC_CWARPS * DEC_RPW;  // 16 rows per ring stage
-constexpr int DEC_KC = 1024;                     // K elements per ring stage (2 KB per row segment)
+constexpr int DEC_GROUP = 16;                    // rows per ring stage == M of the MMA atom
+constexpr int DEC_KC = 1024;                     // K elements per ring stage
+constexpr int DEC_KW = DEC_KC / DEC_CWARPS;      // 128 columns per consumer warp per stage
+constexpr int DEC_ROWSTRIDE = DEC_KC * 2 + 16;   // padded row stride (bytes): ldmatrix rows land in distinct bank groups
 constexpr int DEC_STAGES = 6;
-constexpr int DEC_STAGE_BYTES = DEC_GROUP * DEC_KC * 2;  // 32 KB
-constexpr int DEC_XS_BYTES = 22528;                      // activation vector (bf16), up to 11264 elements
+constexpr int DEC_STAGE_BYTES = DEC_GROUP * DEC_ROWSTRIDE;  // 33024
+constexpr int DEC_XS_BYTES = 22528;                         // activation vector (bf16), up to 11264 elements
 constexpr int DEC_MISC_BYTES = 2048;
 constexpr int DEC_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128;
 constexpr int DEC_HD = 128;  // head_dim supported by the decode kernel (Llama-2)
 
-enum PhaseKind { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4 };
+enum PhaseKind { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4, PH_END = 5 };
 
 struct PhaseDesc {
   const __nv_bfloat16* W;
@@ -55,11 +60,11 @@ __device__ __forceinline__ PhaseDesc phase_desc(const emx_decode_params& p, int 
   return d;
 }
 
-// rows of a phase owned by this CTA, in units of DEC_RPW rows
+// rows of a phase owned by this CTA (row pairs are never split: gate/up interleave, packed bf16x2 stores)
 __device__ __forceinline__ void cta_rows(int N, int& r_begin, int& r_end) {
-  const long U = N / DEC_RPW;
-  r_begin = static_cast<int>(U * blockIdx.x / gridDim.x) * DEC_RPW;
-  r_end = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x) * DEC_RPW;
+  const long U = N / 2;
+  r_begin = static_cast<int>(U * blockIdx.x / gridDim.x) * 2;
+  r_end = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x) * 2;
 }
 
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(DEC_CTHREADS) : "memory"); }
@@ -69,6 +74,9 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ticket barrier over all CTAs (consumer threads only; the producer warp never synchronises with the grid)
 __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t& target) {
@@ -76,12 +84,11 @@ __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t& target) {
   cbar();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(counter, 1u);
+    red_release_add(counter, 1u);
     uint32_t spins = 0;
     while (static_cast<int32_t>(ld_acquire_u32(counter) - target) < 0) {
       if (++spins > EMX_SPIN_LIMIT) __trap();
     }
-    __threadfence();
   }
   cbar();
 }
@@ -107,31 +114,48 @@ __device__ __forceinline__ float cblock_max(float v, float* red) {
   return t;
 }
 
-// xs = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))  — LlamaRMSNorm, computed redundantly by every CTA
+__device__ __forceinline__ uint4 rms_apply(uint4 v, uint4 ww, float rs) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w}, uw[4] = {ww.x, ww.y, ww.z, ww.w};
+  uint32_t r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    r[j] = pack_bf16(bf16_lo(uw[j]) * bf16_round(bf16_lo(u[j]) * rs), bf16_hi(uw[j]) * bf16_round(bf16_hi(u[j]) * rs));
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
+__device__ __forceinline__ float sumsq8(uint4 v) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = bf16_lo(u[j]), c = bf16_hi(u[j]);
+    ss += a * a + c * c;
+  }
+  return ss;
+}
+
+// xs = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))  — LlamaRMSNorm, computed redundantly by every CTA.
+// x and w loads are issued together (one L2/HBM round trip on the critical path instead of two).
 __device__ __forceinline__ void load_rmsnorm(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* xs, int H, float eps,
                                              float* red) {
   const int nv = H >> 3;
-  float ss = 0.f;
-  for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS) {
-    const uint4 v = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i);
-    reinterpret_cast<uint4*>(xs)[i] = v;
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = bf16_lo(u[j]), c = bf16_hi(u[j]);
-      ss += a * a + c * c;
+  if (nv <= 2 * DEC_CTHREADS) {
+    const int i0 = threadIdx.x, i1 = threadIdx.x + DEC_CTHREADS;
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, w0 = v0, w1 = v0;
+    if (i0 < nv) v0 = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i0), w0 = reinterpret_cast<const uint4*>(w)[i0];
+    if (i1 < nv) v1 = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i1), w1 = reinterpret_cast<const uint4*>(w)[i1];
+    const float rs = 1.0f / sqrtf(cblock_sum(sumsq8(v0) + sumsq8(v1), red) / H + eps);
+    if (i0 < nv) reinterpret_cast<uint4*>(xs)[i0] = rms_apply(v0, w0, rs);
+    if (i1 < nv) reinterpret_cast<uint4*>(xs)[i1] = rms_apply(v1, w1, rs);
+  } else {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS) {
+      const uint4 v = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i);
+      reinterpret_cast<uint4*>(xs)[i] = v;
+      ss += sumsq8(v);
     }
-  }
-  const float rs = 1.0f / sqrtf(cblock_sum(ss, red) / H + eps);
-  for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS) {
-    const uint4 v = reinterpret_cast<uint4*>(xs)[i];
-    const uint4 ww = reinterpret_cast<const uint4*>(w)[i];
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w}, uw[4] = {ww.x, ww.y, ww.z, ww.w};
-    uint32_t r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      r[j] = pack_bf16(bf16_lo(uw[j]) * bf16_round(bf16_lo(u[j]) * rs), bf16_hi(uw[j]) * bf16_round(bf16_hi(u[j]) * rs));
-    reinterpret_cast<uint4*>(xs)[i] = make_uint4(r[0], r[1], r[2], r[3]);
+    const float rs = 1.0f / sqrtf(cblock_sum(ss, red) / H + eps);
+    for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS)
+      reinterpret_cast<uint4*>(xs)[i] = rms_apply(reinterpret_cast<uint4*>(xs)[i], reinterpret_cast<const uint4*>(w)[i], rs);
   }
   cbar();
 }
@@ -141,85 +165,172 @@ __device__ __forceinline__ void load_vec(const __nv_bfloat16* v, __nv_bfloat16* 
   cbar();
 }
 
-struct RingState {
-  uint32_t it;  // stage counter, identical sequence in producer and consumers
-  long long waited;  // profiling: cycles spent waiting on the ring (only meaningful when params.dbg != null)
-};
-
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-// ---- producer: stream one phase's rows of this CTA through the ring --------------------------------------------------
-__device__ __forceinline__ void produce_phase(const PhaseDesc& d, uint8_t* ring, uint64_t* full, uint64_t* empty, RingState& rs,
-                                              uint64_t policy, int lane) {
-  int r_begin, r_end;
-  cta_rows(d.N, r_begin, r_end);
-  for (int r0 = r_begin; r0 < r_end; r0 += DEC_GROUP) {
-    const int nrows = min(DEC_GROUP, r_end - r0);
-    for (int k0 = 0; k0 < d.K; k0 += DEC_KC) {
-      const int klen = min(DEC_KC, d.K - k0);
-      const int slot = rs.it % DEC_STAGES;
-      const uint32_t ph = (rs.it / DEC_STAGES) & 1;
+// ---- static weight schedule of one CTA: (layer, kind) phases -> 16-row groups ------------------------------------------
+struct SchedIter {
+  int layer, kind, r, r_end;
+  PhaseDesc d;
+  __device__ __forceinline__ void load_phase(const emx_decode_params& p) {
+    d = phase_desc(p, layer, kind);
+    cta_rows(d.N, r, r_end);
+  }
+  __device__ __forceinline__ bool done() const { return kind == PH_END; }
+  __device__ __forceinline__ void next_phase(const emx_decode_params& p) {
+    if (kind == PH_LMHEAD) {
+      kind = PH_END;
+      return;
+    }
+    if (kind == PH_DOWN) {
+      kind = PH_QKV;
+      if (++layer == p.layers) kind = PH_LMHEAD;
+    } else {
+      ++kind;
+    }
+    load_phase(p);
+  }
+  __device__ __forceinline__ void skip_empty(const emx_decode_params& p) {
+    while (!done() && r >= r_end) next_phase(p);
+  }
+  __device__ __forceinline__ void init(const emx_decode_params& p) {
+    layer = 0, kind = PH_QKV;
+    load_phase(p);
+    skip_empty(p);
+  }
+  __device__ __forceinline__ void advance(const emx_decode_params& p) {
+    r += DEC_GROUP;
+    skip_empty(p);
+  }
+  __device__ __forceinline__ int nrows() const { return min(DEC_GROUP, r_end - r); }
+  __device__ __forceinline__ long group_bytes() const { return static_cast<long>(nrows()) * d.K * 2; }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+// ---- producer warp --------------------------------------------------------------------------------------------------
+__device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane, long long* dbg) {
+  const uint64_t policy = l2_policy_evict_first();
+  SchedIter cur, pf;
+  cur.init(p);
+  pf.init(p);
+  const long lookahead = static_cast<long>(p.l2_lookahead_kb) * 1024;
+  long pf_ahead = 0;  // bytes prefetched to L2 but not yet pulled into the ring
+  uint32_t it = 0;
+  long long waited = 0;
+  while (!cur.done()) {
+    // deeper look-ahead into L2 (one contiguous block of rows per prefetch)
+    if (lookahead > 0) {
+      while (!pf.done() && pf_ahead < lookahead) {
+        const long gb = pf.group_bytes();
+        if (lane == 0) {
+          const char* src = reinterpret_cast<const char*>(pf.d.W + static_cast<long>(pf.r) * pf.d.K);
+          for (long off = 0; off < gb; off += 65536) prefetch_l2(src + off, static_cast<uint32_t>(min(65536L, gb - off)));
+        }
+        pf_ahead += gb;
+        pf.advance(p);
+      }
+    }
+    const int nrows = cur.nrows();
+    for (int k0 = 0; k0 < cur.d.K; k0 += DEC_KC) {
+      const int klen = min(DEC_KC, cur.d.K - k0);
+      const int slot = it % DEC_STAGES;
+      const uint32_t ph = (it / DEC_STAGES) & 1;
       if (lane == 0) {
         const long long t0 = clock64();
         mbar_wait(&empty[slot], ph ^ 1);
-        rs.waited += clock64() - t0;
+        waited += clock64() - t0;
         mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(nrows) * klen * 2);
       }
       __syncwarp();
       if (lane < nrows)
-        bulk_g2s(ring + slot * DEC_STAGE_BYTES + lane * (DEC_KC * 2), d.W + static_cast<long>(r0 + lane) * d.K + k0, klen * 2, &full[slot],
-                 policy);
-      ++rs.it;
+        bulk_g2s(ring + slot * DEC_STAGE_BYTES + lane * DEC_ROWSTRIDE, cur.d.W + static_cast<long>(cur.r + lane) * cur.d.K + k0, klen * 2,
+                 &full[slot], policy);
+      ++it;
     }
+    pf_ahead -= cur.group_bytes();
+    cur.advance(p);
   }
+  if (dbg && lane == 0) dbg[15 * p.layers + 9] = waited;
 }
 
-// ---- consumer: dot products of this warp's 2 rows of every group against xs ------------------------------------------
+// ---- consumer: tensor-core dot products of one phase ---------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct ConsumerState {
+  uint32_t it;
+  uint32_t group;  // parity selects the partial-sum buffer
+  long long waited;
+};
+
+// epi(row, v0, v1) is called for row pairs (row even) by threads 0..7 of warp 0, rows ascending per thread
 template <typename Epi>
-__device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t* ring, uint64_t* full, uint64_t* empty, RingState& rs,
-                                              const __nv_bfloat16* xs, int warp, int lane, Epi&& epi) {
+__device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t* ring, uint64_t* full, uint64_t* empty, ConsumerState& cs,
+                                              const __nv_bfloat16* xs, float* part, int warp, int lane, Epi&& epi) {
   int r_begin, r_end;
   cta_rows(d.N, r_begin, r_end);
+  // ldmatrix.x4 row address of this lane: matrices (rows 0-7 | 8-15) x (cols 0-7 | 8-15) of a 16x16 A tile
+  const uint32_t a_lane_off = ((lane & 7) + ((lane >> 3) & 1) * 8) * DEC_ROWSTRIDE + (lane >> 4) * 16;
+  const int kbeg = warp * DEC_KW;
   for (int r0 = r_begin; r0 < r_end; r0 += DEC_GROUP) {
     const int nrows = min(DEC_GROUP, r_end - r0);
-    const bool active = warp * DEC_RPW < nrows;
-    float acc0 = 0.f, acc1 = 0.f;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k0 = 0; k0 < d.K; k0 += DEC_KC) {
       const int klen = min(DEC_KC, d.K - k0);
-      const int slot = rs.it % DEC_STAGES;
-      const uint32_t ph = (rs.it / DEC_STAGES) & 1;
+      const int slot = cs.it % DEC_STAGES;
+      const uint32_t ph = (cs.it / DEC_STAGES) & 1;
       const long long t0 = clock64();
       mbar_wait(&full[slot], ph);
-      rs.waited += clock64() - t0;
-      if (active) {
-        const uint4* w0 = reinterpret_cast<const uint4*>(ring + slot * DEC_STAGE_BYTES + (warp * DEC_RPW) * (DEC_KC * 2));
-        const uint4* w1 = w0 + (DEC_KC * 2) / 16;
-        const uint4* xv = reinterpret_cast<const uint4*>(xs + k0);
-        const int nv = klen >> 3;
-#pragma unroll 4
-        for (int c = lane; c < nv; c += 32) {
-          const uint4 x4 = xv[c], a = w0[c], b = w1[c];
-          const uint32_t ux[4] = {x4.x, x4.y, x4.z, x4.w}, ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+      cs.waited += clock64() - t0;
+      const int ksteps = min(DEC_KW / 16, (klen - kbeg) / 16);  // <= 0: this warp's slice is past the K tail
+      if (ksteps > 0) {
+        const uint32_t a_base = smem_u32(ring + slot * DEC_STAGE_BYTES) + a_lane_off + kbeg * 2;
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs + k0 + kbeg) + (lane & 3);
+        if (ksteps == DEC_KW / 16) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float xl = bf16_lo(ux[j]), xh = bf16_hi(ux[j]);
-            acc0 = fmaf(bf16_lo(ua[j]), xl, acc0), acc0 = fmaf(bf16_hi(ua[j]), xh, acc0);
-            acc1 = fmaf(bf16_lo(ub[j]), xl, acc1), acc1 = fmaf(bf16_hi(ub[j]), xh, acc1);
+          for (int j = 0; j < DEC_KW / 16; ++j) {
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
+            mma_bf16_16816(c, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
+          }
+        } else {
+          for (int j = 0; j < ksteps; ++j) {
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
+            mma_bf16_16816(c, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
           }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[slot]);
-      ++rs.it;
+      ++cs.it;
     }
-    if (active) {
-      acc0 = warp_sum(acc0), acc1 = warp_sum(acc1);
-      if (lane == 0) epi(r0 + warp * DEC_RPW, acc0, acc1);
+    // column 0 of the accumulator tile lives in lanes with lane % 4 == 0: c[0] -> row lane/4, c[2] -> row lane/4 + 8
+    float* pb = part + (cs.group & 1) * (DEC_CWARPS * DEC_GROUP);
+    if ((lane & 3) == 0) {
+      pb[warp * DEC_GROUP + (lane >> 2)] = c[0];
+      pb[warp * DEC_GROUP + (lane >> 2) + 8] = c[2];
     }
+    cbar();
+    if (warp == 0 && lane < 8 && 2 * lane < nrows) {
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < DEC_CWARPS; ++w) v0 += pb[w * DEC_GROUP + 2 * lane], v1 += pb[w * DEC_GROUP + 2 * lane + 1];
+      epi(r0 + 2 * lane, v0, v1);
+    }
+    ++cs.group;
   }
 }
 
@@ -230,17 +341,20 @@ __device__ __forceinline__ long kv_row(const emx_decode_params& p, int layer, in
   return layer_off + ((static_cast<long>(page) * p.heads + head) * p.page_size + key % p.page_size) * DEC_HD;
 }
 
-__device__ void attention_item(const emx_decode_params& p, int layer, int head, int split, int pos, float* sm /*>= 5.5 KB*/, float* red) {
+// shared-memory carve-up of the (idle) activation area during attention, in floats
+constexpr int ATT_SQ = 0, ATT_SKNEW = 128, ATT_SVNEW = 256, ATT_SACC = 384 /*[8][128]*/, ATT_SSCORE = 384 + 1024;
+
+__device__ void attention_item(const emx_decode_params& p, int layer, int head, int split, int pos, float* sm, float* red) {
   constexpr int HALF = DEC_HD / 2;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int n = pos + 1, S = p.kv_splits;
   const int k_begin = static_cast<int>(static_cast<long>(n) * split / S), k_end = static_cast<int>(static_cast<long>(n) * (split + 1) / S);
   const int nk = k_end - k_begin;
-  float* sq = sm;                 // [128] rotated q
-  float* sknew = sm + 128;        // [128] rotated new k
-  float* svnew = sm + 256;        // [128] new v
-  float* sacc = sm + 384;         // [4][128] PV partials
-  float* sscore = sm + 896;       // [nk] scores / probabilities (host guarantees capacity)
+  float* sq = sm + ATT_SQ;          // [128] rotated q
+  float* sknew = sm + ATT_SKNEW;    // [128] rotated new k
+  float* svnew = sm + ATT_SVNEW;    // [128] new v
+  float* sacc = sm + ATT_SACC;      // [8][128] PV partials
+  float* sscore = sm + ATT_SSCORE;  // [nk] scores -> probabilities (host guarantees capacity)
   __nv_bfloat16* kc = static_cast<__nv_bfloat16*>(p.k_cache);
   __nv_bfloat16* vc = static_cast<__nv_bfloat16*>(p.v_cache);
   const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(p.qkv);
@@ -252,12 +366,15 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
     const float c = ld_bf16(static_cast<const __nv_bfloat16*>(p.cos_tab) + static_cast<long>(pos) * HALF + j);
     const float s = ld_bf16(static_cast<const __nv_bfloat16*>(p.sin_tab) + static_cast<long>(pos) * HALF + j);
     const float q1 = ldg_cg_bf16(qkv + head * DEC_HD + j), q2 = ldg_cg_bf16(qkv + head * DEC_HD + j + HALF);
+    float k1 = 0.f, k2 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (owns_new) {
+      k1 = ldg_cg_bf16(qkv + H + head * DEC_HD + j), k2 = ldg_cg_bf16(qkv + H + head * DEC_HD + j + HALF);
+      v1 = ldg_cg_bf16(qkv + 2 * H + head * DEC_HD + j), v2 = ldg_cg_bf16(qkv + 2 * H + head * DEC_HD + j + HALF);
+    }
     sq[j] = bf16_round(bf16_round(q1 * c) + bf16_round(-q2 * s));
     sq[j + HALF] = bf16_round(bf16_round(q2 * c) + bf16_round(q1 * s));
     if (owns_new) {
-      const float k1 = ldg_cg_bf16(qkv + H + head * DEC_HD + j), k2 = ldg_cg_bf16(qkv + H + head * DEC_HD + j + HALF);
       const float r1 = bf16_round(bf16_round(k1 * c) + bf16_round(-k2 * s)), r2 = bf16_round(bf16_round(k2 * c) + bf16_round(k1 * s));
-      const float v1 = ldg_cg_bf16(qkv + 2 * H + head * DEC_HD + j), v2 = ldg_cg_bf16(qkv + 2 * H + head * DEC_HD + j + HALF);
       sknew[j] = r1, sknew[j + HALF] = r2, svnew[j] = v1, svnew[j + HALF] = v2;
       const long dst = kv_row(p, layer, head, pos);
       kc[dst + j] = __float2bfloat16_rn(r1), kc[dst + j + HALF] = __float2bfloat16_rn(r2);
@@ -266,51 +383,76 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
   }
   cbar();
 
-  // scores: one warp per key, lane owns 4 consecutive dims (8-byte coalesced loads of the 256-B K row)
+  // scores: one LANE per key — the 16 x 16-B loads of a 256-B K row are all in flight at once (one memory round trip)
   const float scale = rsqrtf(static_cast<float>(DEC_HD));
-  const float q0 = sq[lane * 4], q1 = sq[lane * 4 + 1], q2 = sq[lane * 4 + 2], q3 = sq[lane * 4 + 3];
   float lmax = -INFINITY;
-  for (int kk = warp; kk < nk; kk += DEC_CWARPS) {
+  for (int kk = tid; kk < nk; kk += DEC_CTHREADS) {
     const int key = k_begin + kk;
-    float d;
+    float d = 0.f;
     if (key == pos) {
-      d = q0 * sknew[lane * 4] + q1 * sknew[lane * 4 + 1] + q2 * sknew[lane * 4 + 2] + q3 * sknew[lane * 4 + 3];
+#pragma unroll 8
+      for (int j = 0; j < DEC_HD; ++j) d = fmaf(sq[j], sknew[j], d);
     } else {
-      const uint2 kv = ldg_cg_v2(kc + kv_row(p, layer, head, key) + lane * 4);
-      d = q0 * bf16_lo(kv.x) + q1 * bf16_hi(kv.x) + q2 * bf16_lo(kv.y) + q3 * bf16_hi(kv.y);
+      const uint4* kr = reinterpret_cast<const uint4*>(kc + kv_row(p, layer, head, key));
+      uint4 r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = ldg_nc_v4(kr + j);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 qa = *reinterpret_cast<const float4*>(sq + 8 * j), qb = *reinterpret_cast<const float4*>(sq + 8 * j + 4);
+        d = fmaf(qa.x, bf16_lo(r[j].x), d), d = fmaf(qa.y, bf16_hi(r[j].x), d);
+        d = fmaf(qa.z, bf16_lo(r[j].y), d), d = fmaf(qa.w, bf16_hi(r[j].y), d);
+        d = fmaf(qb.x, bf16_lo(r[j].z), d), d = fmaf(qb.y, bf16_hi(r[j].z), d);
+        d = fmaf(qb.z, bf16_lo(r[j].w), d), d = fmaf(qb.w, bf16_hi(r[j].w), d);
+      }
     }
-    d = warp_sum(d) * scale;
-    if (lane == 0) sscore[kk] = d;
+    d *= scale;
+    sscore[kk] = d;
     lmax = fmaxf(lmax, d);
   }
-  const float m = cblock_max(lmax, red);  // includes the barrier that publishes sscore
+  const float m = cblock_max(lmax, red);
   float lsum = 0.f;
   for (int kk = tid; kk < nk; kk += DEC_CTHREADS) {
     const float pr = __expf(sscore[kk] - m);
     lsum += pr;
     sscore[kk] = bf16_round(pr);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
   }
-  const float l = cblock_sum(lsum, red);
+  const float l = cblock_sum(lsum, red);  // its barriers also publish the probabilities
 
-  // PV: thread = (key slice, dim pair); 64 threads read one 256-B V row coalesced
-  const int pr_idx = tid & 63, slice = tid >> 6;
-  float a0 = 0.f, a1 = 0.f;
-  for (int kk = slice; kk < nk; kk += 4) {
-    const int key = k_begin + kk;
-    const float pw = sscore[kk];
-    float v0, v1;
-    if (key == pos) {
-      v0 = svnew[2 * pr_idx], v1 = svnew[2 * pr_idx + 1];
-    } else {
-      const uint32_t w = ldg_cg_u32(vc + kv_row(p, layer, head, key) + 2 * pr_idx);
-      v0 = bf16_lo(w), v1 = bf16_hi(w);
+  // PV: thread = (key slice of 8, 4 output dims); 32 threads read one 256-B V row coalesced; loads unrolled x4
+  const int quad = tid & 31, slice = tid >> 5;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kk0 = slice; kk0 < nk; kk0 += 8 * 4) {
+    uint2 vv[4];
+    float pw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kk = kk0 + 8 * u;
+      pw[u] = 0.f, vv[u] = make_uint2(0, 0);
+      if (kk < nk) {
+        pw[u] = sscore[kk];
+        const int key = k_begin + kk;
+        if (key == pos)
+          vv[u] = make_uint2(pack_bf16(svnew[4 * quad], svnew[4 * quad + 1]), pack_bf16(svnew[4 * quad + 2], svnew[4 * quad + 3]));
+        else
+          vv[u] = ldg_cg_v2(vc + kv_row(p, layer, head, key) + 4 * quad);
+      }
     }
-    a0 = fmaf(pw, v0, a0), a1 = fmaf(pw, v1, a1);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[0] = fmaf(pw[u], bf16_lo(vv[u].x), a[0]), a[1] = fmaf(pw[u], bf16_hi(vv[u].x), a[1]);
+      a[2] = fmaf(pw[u], bf16_lo(vv[u].y), a[2]), a[3] = fmaf(pw[u], bf16_hi(vv[u].y), a[3]);
+    }
   }
-  sacc[slice * 128 + 2 * pr_idx] = a0, sacc[slice * 128 + 2 * pr_idx + 1] = a1;
+  *reinterpret_cast<float4*>(sacc + slice * 128 + 4 * quad) = make_float4(a[0], a[1], a[2], a[3]);
   cbar();
   float* part = p.part + (static_cast<long>(head) * S + split) * (DEC_HD + 2);
-  if (tid < DEC_HD) part[2 + tid] = sacc[tid] + sacc[128 + tid] + sacc[256 + tid] + sacc[384 + tid];
+  if (tid < DEC_HD) {
+    float t = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2) t += sacc[s2 * 128 + tid];
+    part[2 + tid] = t;
+  }
   if (tid == 0) part[0] = m, part[1] = l;
 
   // last-arriving split of this head combines the partials
@@ -323,16 +465,23 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
     __threadfence();
     if (tid < DEC_HD) {
       const float* ph = p.part + static_cast<long>(head) * S * (DEC_HD + 2);
+      float ms[8], ls[8], as[8];  // S <= 8
       float M = -INFINITY;
-      for (int s2 = 0; s2 < S; ++s2)
-        if (ldg_cg_f32(ph + s2 * (DEC_HD + 2) + 1) > 0.f) M = fmaxf(M, ldg_cg_f32(ph + s2 * (DEC_HD + 2)));
+#pragma unroll
+      for (int s2 = 0; s2 < 8; ++s2) {
+        ms[s2] = -INFINITY, ls[s2] = 0.f, as[s2] = 0.f;
+        if (s2 < S) {
+          ms[s2] = ldg_cg_f32(ph + s2 * (DEC_HD + 2)), ls[s2] = ldg_cg_f32(ph + s2 * (DEC_HD + 2) + 1);
+          as[s2] = ldg_cg_f32(ph + s2 * (DEC_HD + 2) + 2 + tid);
+          if (ls[s2] > 0.f) M = fmaxf(M, ms[s2]);
+        }
+      }
       float num = 0.f, den = 0.f;
-      for (int s2 = 0; s2 < S; ++s2) {
-        const float ls = ldg_cg_f32(ph + s2 * (DEC_HD + 2) + 1);
-        if (ls > 0.f) {
-          const float w = __expf(ldg_cg_f32(ph + s2 * (DEC_HD + 2)) - M);
-          num = fmaf(w, ldg_cg_f32(ph + s2 * (DEC_HD + 2) + 2 + tid), num);
-          den = fmaf(w, ls, den);
+#pragma unroll
+      for (int s2 = 0; s2 < 8; ++s2) {
+        if (s2 < S && ls[s2] > 0.f) {
+          const float w = __expf(ms[s2] - M);
+          num = fmaf(w, as[s2], num), den = fmaf(w, ls[s2], den);
         }
       }
       static_cast<__nv_bfloat16*>(p.attn)[head * DEC_HD + tid] = __float2bfloat16_rn(num / den);
@@ -349,9 +498,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   float* misc = reinterpret_cast<float*>(smem + DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES);
   uint64_t* empty = full + DEC_STAGES;
-  float* red = misc;                // [8]
+  float* red = misc;                                 // [8]
   int* s_state = reinterpret_cast<int*>(misc + 16);  // [4]
-  float* s_best = misc + 32;        // [8] + [8]
+  float* s_best = misc + 32;                         // [8] values + [8] indices
+  float* part = misc + 64;                           // [2][8 warps][16 rows] partial row sums
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   emx_decode_state* st = p.state;
@@ -371,25 +521,20 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   if (s_state[3]) return;  // sequence already hit EOS: nothing to do (uniform across the grid)
 
   const int L = p.layers, H = p.hidden;
-  RingState rs{0, 0};
   long long* dbg = (blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
+
+  if (warp == DEC_CWARPS) {
+    producer_loop(p, ring, full, empty, lane, dbg);
+    return;
+  }
+
+  // ===================== consumer warps =====================
   int dbg_i = 0;
   auto mark = [&]() {
     if (dbg && tid == 0) dbg[dbg_i] = global_ns();
     ++dbg_i;
   };
-
-  if (warp == DEC_CWARPS) {
-    // ===================== producer warp =====================
-    const uint64_t policy = l2_policy_evict_first();
-    for (int layer = 0; layer < L; ++layer)
-      for (int kind = PH_QKV; kind <= PH_DOWN; ++kind) produce_phase(phase_desc(p, layer, kind), ring, full, empty, rs, policy, lane);
-    produce_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, rs, policy, lane);
-    if (dbg && lane == 0) dbg[15 * L + 9] = rs.waited;
-    return;
-  }
-
-  // ===================== consumer warps =====================
+  ConsumerState cs{0, 0, 0};
   // barrier tickets: every non-finished launch performs exactly (5 L + 1) grid syncs
   const uint32_t n_sync = 5u * L + 1u;
   uint32_t target = ldg_cg_u32(&st->epoch) * n_sync * gridDim.x;
@@ -404,9 +549,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     // ---- P1: RMSNorm + QKV ----
     mark();
     load_rmsnorm(resid_src, static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
-    consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, rs, xs, warp, lane, [&](int row, float a0, float a1) {
-      *reinterpret_cast<uint32_t*>(qkv + row) = pack_bf16(a0, a1);
-    });
+    consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, xs, part, warp, lane,
+                  [&](int row, float a0, float a1) { *reinterpret_cast<uint32_t*>(qkv + row) = pack_bf16(a0, a1); });
     mark();
     grid_sync(&st->barrier, target);
     mark();
@@ -419,7 +563,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     // ---- P3: o_proj + residual ----
     load_vec(static_cast<const __nv_bfloat16*>(p.attn), xs, H);
     mark();
-    consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, rs, xs, warp, lane, [&](int row, float a0, float a1) {
+    consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float a0, float a1) {
       const uint32_t r = ldg_cg_u32(resid_src + row);
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
@@ -429,7 +573,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     // ---- P4: RMSNorm + gate/up + SwiGLU ----
     load_rmsnorm(x, static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
     mark();
-    consume_phase(phase_desc(p, layer, PH_GATEUP), ring, full, empty, rs, xs, warp, lane, [&](int row, float g, float u) {
+    consume_phase(phase_desc(p, layer, PH_GATEUP), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float g, float u) {
       hbuf[row >> 1] = __float2bfloat16_rn(bf16_round(silu(bf16_round(g))) * bf16_round(u));
     });
     mark();
@@ -438,7 +582,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     // ---- P5: down_proj + residual ----
     load_vec(hbuf, xs, p.inter);
     mark();
-    consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, rs, xs, warp, lane, [&](int row, float a0, float a1) {
+    consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float a0, float a1) {
       const uint32_t r = ldg_cg_u32(x + row);
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
@@ -452,18 +596,18 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   mark();
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  consume_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, rs, xs, warp, lane, [&](int row, float a0, float a1) {
+  consume_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float a0, float a1) {
     const float v0 = bf16_round(a0), v1 = bf16_round(a1);
     if (p.logits_out) p.logits_out[row] = v0, p.logits_out[row + 1] = v1;
-    if (v0 > best) best = v0, best_i = row;  // rows ascend within a warp: strict '>' keeps the lowest index
+    if (v0 > best) best = v0, best_i = row;  // rows ascend per thread: strict '>' keeps the lowest index
     if (v1 > best) best = v1, best_i = row + 1;
   });
   mark();
-  if (dbg && tid == 0) dbg[15 * L + 8] = rs.waited;
-  if (lane == 0) s_best[warp] = best, reinterpret_cast<int*>(s_best + 8)[warp] = best_i;
+  if (dbg && tid == 0) dbg[15 * L + 8] = cs.waited;
+  if (warp == 0 && lane < 8) s_best[lane] = best, reinterpret_cast<int*>(s_best + 8)[lane] = best_i;
   cbar();
   if (tid == 0) {
-    for (int w = 0; w < DEC_CWARPS; ++w) {
+    for (int w = 1; w < 8; ++w) {
       const float v = s_best[w];
       const int i = reinterpret_cast<int*>(s_best + 8)[w];
       if (v > best || (v == best && i < best_i)) best = v, best_i = i;
@@ -506,12 +650,11 @@ extern "C" int emx_decode_step(const emx_decode_params* params, cudaStream_t str
   using namespace emx;
   const emx_decode_params& p = *params;
   EMX_REQUIRE(p.head_dim == DEC_HD, "emx_decode_step: head_dim %d not supported (128)", p.head_dim);
-  EMX_REQUIRE(p.hidden % 8 == 0 && p.inter % 8 == 0 && p.vocab % 2 == 0, "emx_decode_step: hidden/inter must be multiples of 8, vocab even");
+  EMX_REQUIRE(p.hidden % 16 == 0 && p.inter % 16 == 0 && p.vocab % 2 == 0, "emx_decode_step: hidden/inter must be multiples of 16, vocab even");
   EMX_REQUIRE(p.inter * 2 <= DEC_XS_BYTES && p.hidden * 2 <= DEC_XS_BYTES, "emx_decode_step: activation vector exceeds %d bytes", DEC_XS_BYTES);
-  EMX_REQUIRE(p.kv_splits >= 1 && (p.kv_splits & (p.kv_splits - 1)) == 0, "emx_decode_step: kv_splits must be a power of two");
+  EMX_REQUIRE(p.kv_splits >= 1 && p.kv_splits <= 8 && (p.kv_splits & (p.kv_splits - 1)) == 0, "emx_decode_step: kv_splits must be 1, 2, 4 or 8");
   EMX_REQUIRE(p.heads <= 64, "emx_decode_step: at most 64 heads");
-  // score buffer lives in the activation area behind 896 floats of q/k/v/acc staging
-  const int max_keys_per_split = (DEC_XS_BYTES / 4 - 896);
+  const int max_keys_per_split = DEC_XS_BYTES / 4 - ATT_SSCORE;
   EMX_REQUIRE((static_cast<long>(p.max_pages) * p.page_size + p.kv_splits - 1) / p.kv_splits + 1 <= max_keys_per_split,
               "emx_decode_step: context capacity %d x %d exceeds the per-split score buffer (%d keys)", p.max_pages, p.page_size,
               max_keys_per_split);

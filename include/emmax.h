@@ -137,6 +137,9 @@ typedef struct emx_decode_params {
   /* optional profiling buffer (device, >= 16*layers + 16 int64): CTA 0 stores %globaltimer at every phase boundary,
    * then [15*layers + 8 ..] = cycles warp 0 waited for weights / cycles the producer waited for a free ring slot */
   int64_t* dbg;
+  /* per-CTA look-ahead (KiB) of cp.async.bulk.prefetch.L2 beyond the shared-memory ring; 0 disables (148 CTAs x 256 KiB
+   * = 37 MB of the 126 MB L2 keeps HBM streaming through grid barriers and the attention phase) */
+  int32_t l2_lookahead_kb;
 } emx_decode_params;
 
 int emx_decode_step(const emx_decode_params* params, emx_stream_t stream);
