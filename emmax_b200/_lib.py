@@ -44,7 +44,7 @@ class DecodeParams(C.Structure):
         ("part", C.c_void_p), ("argmax_part", C.c_void_p),
         ("out_tokens", C.c_void_p), ("logits_out", C.c_void_p),
         ("eos_token", C.c_int32), ("kv_splits", C.c_int32), ("state", C.c_void_p), ("dbg", C.c_void_p),
-        ("l2_lookahead_kb", C.c_int32),
+        ("l2_lookahead_kb", C.c_int32), ("debug_flags", C.c_int32),
     ]  # fmt: skip
 
 

@@ -79,9 +79,13 @@ __device__ __forceinline__ void red_release_add(uint32_t* p, uint32_t v) {
 }
 
 // ticket barrier over all CTAs (consumer threads only; the producer warp never synchronises with the grid)
-__device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t& target) {
+__device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t& target, bool skip = false) {
   target += gridDim.x;
   cbar();
+  if (skip) {  // profiling mode: keep the ticket arithmetic consistent, do not wait
+    if (threadIdx.x == 0) red_release_add(counter, 1u);
+    return;
+  }
   if (threadIdx.x == 0) {
     __threadfence();
     red_release_add(counter, 1u);
@@ -215,7 +219,7 @@ __device__ __forceinline__ void prefetch_l2(const void* gptr, uint32_t bytes) {
 
 // ---- producer warp --------------------------------------------------------------------------------------------------
 __device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane, long long* dbg) {
-  const uint64_t policy = l2_policy_evict_first();
+  const uint64_t policy = (p.debug_flags & 4) ? l2_policy_evict_last() : l2_policy_evict_first();
   SchedIter cur, pf;
   cur.init(p);
   pf.init(p);
@@ -552,13 +556,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, xs, part, warp, lane,
                   [&](int row, float a0, float a1) { *reinterpret_cast<uint32_t*>(qkv + row) = pack_bf16(a0, a1); });
     mark();
-    grid_sync(&st->barrier, target);
+    grid_sync(&st->barrier, target, p.debug_flags & 1);
     mark();
     // ---- P2: RoPE + KV append + split-KV attention ----
-    for (int item = blockIdx.x; item < p.heads * p.kv_splits; item += gridDim.x)
+    for (int item = blockIdx.x; item < p.heads * p.kv_splits && !(p.debug_flags & 2); item += gridDim.x)
       attention_item(p, layer, item / p.kv_splits, item % p.kv_splits, pos, reinterpret_cast<float*>(xs), red);
     mark();
-    grid_sync(&st->barrier, target);
+    grid_sync(&st->barrier, target, p.debug_flags & 1);
     mark();
     // ---- P3: o_proj + residual ----
     load_vec(static_cast<const __nv_bfloat16*>(p.attn), xs, H);
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
     mark();
-    grid_sync(&st->barrier, target);
+    grid_sync(&st->barrier, target, p.debug_flags & 1);
     mark();
     // ---- P4: RMSNorm + gate/up + SwiGLU ----
     load_rmsnorm(x, static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
@@ -577,7 +581,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
       hbuf[row >> 1] = __float2bfloat16_rn(bf16_round(silu(bf16_round(g))) * bf16_round(u));
     });
     mark();
-    grid_sync(&st->barrier, target);
+    grid_sync(&st->barrier, target, p.debug_flags & 1);
     mark();
     // ---- P5: down_proj + residual ----
     load_vec(hbuf, xs, p.inter);
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
     mark();
-    grid_sync(&st->barrier, target);
+    grid_sync(&st->barrier, target, p.debug_flags & 1);
   }
   mark();
 
@@ -615,7 +619,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     p.argmax_part[2 * blockIdx.x] = best;
     reinterpret_cast<int*>(p.argmax_part)[2 * blockIdx.x + 1] = best_i;
   }
-  grid_sync(&st->barrier, target);
+  grid_sync(&st->barrier, target, p.debug_flags & 1);
   mark();
   if (blockIdx.x == 0 && warp == 0) {
     float b = -INFINITY;

@@ -49,7 +49,7 @@ class Engine:
         self.config, self.device = config, device
         self.t = config.text_config
         self.max_batch, self.kv_splits = max_batch, kv_splits
-        self.l2_lookahead_kb = int(os.environ.get("EMX_L2_LOOKAHEAD_KB", "256"))
+        self.l2_lookahead_kb = int(os.environ.get("EMX_L2_LOOKAHEAD_KB", "0"))
         self.max_context = _ceil_to(max_context, self.PAGE)
         self._graphs: Dict[Tuple[int, int], Tuple[torch.cuda.CUDAGraph, int]] = {}
         self.last_decode = None
@@ -289,7 +289,7 @@ class Engine:
         p.part, p.argmax_part = ptr(self.d_part), ptr(self.d_argmax)
         p.out_tokens, p.logits_out = ptr(self.d_out_tokens), None
         p.eos_token, p.kv_splits, p.state = -1, self.kv_splits, ptr(self.d_state)
-        p.dbg, p.l2_lookahead_kb = None, self.l2_lookahead_kb
+        p.dbg, p.l2_lookahead_kb, p.debug_flags = None, self.l2_lookahead_kb, int(os.environ.get("EMX_DECODE_DEBUG_FLAGS", "0"))
         return p
 
     @torch.no_grad()

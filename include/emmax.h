@@ -140,6 +140,8 @@ typedef struct emx_decode_params {
   /* per-CTA look-ahead (KiB) of cp.async.bulk.prefetch.L2 beyond the shared-memory ring; 0 disables (148 CTAs x 256 KiB
    * = 37 MB of the 126 MB L2 keeps HBM streaming through grid barriers and the attention phase) */
   int32_t l2_lookahead_kb;
+  /* profiling only (results become garbage): 1 = skip grid barriers, 2 = skip attention, 4 = no L2 evict-first hint */
+  int32_t debug_flags;
 } emx_decode_params;
 
 int emx_decode_step(const emx_decode_params* params, emx_stream_t stream);
