@@ -8,9 +8,11 @@
 // B200 design (HBM-bound: 13.2 GB of bf16 weights per token):
 //   * grid = one CTA per SM (148), 8 consumer warps + 1 producer warp, launched cooperatively (co-residency guaranteed);
 //   * the producer warp walks the STATIC weight schedule of its CTA (layer -> qkv, o, gate/up, down -> 16-row group ->
-//     1024-column chunk) and keeps a 6 x 32 KB shared-memory ring full with cp.async.bulk (TMA engine) copies, L2
-//     evict-first, and runs a second, deeper look-ahead with cp.async.bulk.prefetch.L2 so HBM keeps streaming into the
-//     126 MB L2 while the consumers sit in a grid barrier or in the attention phase; it never waits for a grid barrier;
+//     2048-column chunk) and two producer warps (alternating stages) keep a 3 x 64 KB shared-memory ring full with
+//     cp.async.bulk (TMA engine) copies, 16 x 4 KB per instruction, L2 evict-first. Measured on B200
+//     (profiles/r01_stream_probe.txt): bulk-copy instructions of one warp do not overlap each other (~1.3 us each
+//     regardless of size), so bytes per instruction x producer warps sets the streaming ceiling: 16 x 2 KB from one warp
+//     tops out at 3.8 TB/s, 16 x 4 KB reaches the 7.4 TB/s HBM read limit. Producers never wait for a grid barrier;
 //   * consumers: the 16 rows x 1024 columns of a stage are one A operand of mma.sync.m16n8k16 (bf16, fp32 accumulate);
 //     each warp owns a 128-column slice (ldmatrix from a 16-B padded, conflict-free row stride), the activation vector is
 //     the B operand straight from shared memory; per-warp partial row sums are combined once per row group. ~10x fewer
@@ -28,13 +30,15 @@ namespace emx {
 
 constexpr int DEC_CWARPS = 8;                    // consumer warps
 constexpr int DEC_CTHREADS = DEC_CWARPS * 32;    // 256
-constexpr int DEC_THREADS = DEC_CTHREADS + 32;   // + producer warp
+constexpr int DEC_PWARPS = 2;                    // producer warps (alternate ring stages)
+constexpr int DEC_THREADS = DEC_CTHREADS + 32 * DEC_PWARPS;
 constexpr int DEC_GROUP = 16;                    // rows per ring stage == M of the MMA atom
-constexpr int DEC_KC = 1024;                     // K elements per ring stage
-constexpr int DEC_KW = DEC_KC / DEC_CWARPS;      // 128 columns per consumer warp per stage
+constexpr int DEC_KC = 2048;                     // K elements per ring stage (4 KB per row segment)
+constexpr int DEC_KW = DEC_KC / DEC_CWARPS;      // 256 columns per consumer warp per stage
 constexpr int DEC_ROWSTRIDE = DEC_KC * 2 + 16;   // padded row stride (bytes): ldmatrix rows land in distinct bank groups
-constexpr int DEC_STAGES = 6;
-constexpr int DEC_STAGE_BYTES = DEC_GROUP * DEC_ROWSTRIDE;  // 33024
+constexpr int DEC_STAGES = 3;
+constexpr int DEC_STAGE_BYTES = DEC_GROUP * DEC_ROWSTRIDE;  // 65792
+constexpr int DEC_MAX_RESID = 192;               // residual pairs of one CTA staged in shared memory
 constexpr int DEC_XS_BYTES = 22528;                         // activation vector (bf16), up to 11264 elements
 constexpr int DEC_MISC_BYTES = 2048;
 constexpr int DEC_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128;
@@ -218,7 +222,8 @@ __device__ __forceinline__ void prefetch_l2(const void* gptr, uint32_t bytes) {
 }
 
 // ---- producer warp --------------------------------------------------------------------------------------------------
-__device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane, long long* dbg) {
+__device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane, int pidx,
+                              long long* dbg) {
   const uint64_t policy = (p.debug_flags & 4) ? l2_policy_evict_last() : l2_policy_evict_first();
   SchedIter cur, pf;
   cur.init(p);
@@ -229,7 +234,7 @@ __device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_
   long long waited = 0;
   while (!cur.done()) {
     // deeper look-ahead into L2 (one contiguous block of rows per prefetch)
-    if (lookahead > 0) {
+    if (lookahead > 0 && pidx == 0) {
       while (!pf.done() && pf_ahead < lookahead) {
         const long gb = pf.group_bytes();
         if (lane == 0) {
@@ -245,22 +250,24 @@ __device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_
       const int klen = min(DEC_KC, cur.d.K - k0);
       const int slot = it % DEC_STAGES;
       const uint32_t ph = (it / DEC_STAGES) & 1;
-      if (lane == 0) {
-        const long long t0 = clock64();
-        mbar_wait(&empty[slot], ph ^ 1);
-        waited += clock64() - t0;
-        mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(nrows) * klen * 2);
+      if ((it % DEC_PWARPS) == static_cast<uint32_t>(pidx)) {
+        if (lane == 0) {
+          const long long t0 = clock64();
+          mbar_wait(&empty[slot], ph ^ 1);
+          waited += clock64() - t0;
+          mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(nrows) * klen * 2);
+        }
+        __syncwarp();
+        if (lane < nrows)
+          bulk_g2s(ring + slot * DEC_STAGE_BYTES + lane * DEC_ROWSTRIDE, cur.d.W + static_cast<long>(cur.r + lane) * cur.d.K + k0,
+                   klen * 2, &full[slot], policy);
       }
-      __syncwarp();
-      if (lane < nrows)
-        bulk_g2s(ring + slot * DEC_STAGE_BYTES + lane * DEC_ROWSTRIDE, cur.d.W + static_cast<long>(cur.r + lane) * cur.d.K + k0, klen * 2,
-                 &full[slot], policy);
       ++it;
     }
     pf_ahead -= cur.group_bytes();
     cur.advance(p);
   }
-  if (dbg && lane == 0) dbg[15 * p.layers + 9] = waited;
+  if (dbg && lane == 0) dbg[15 * p.layers + 9 + pidx] = waited;
 }
 
 // ---- consumer: tensor-core dot products of one phase ---------------------------------------------------------------------
@@ -343,6 +350,22 @@ __device__ __forceinline__ long kv_row(const emx_decode_params& p, int layer, in
   const int page = p.block_table[key / p.page_size];
   const long layer_off = static_cast<long>(layer) * p.n_pages * p.heads * p.page_size * DEC_HD;
   return layer_off + ((static_cast<long>(page) * p.heads + head) * p.page_size + key % p.page_size) * DEC_HD;
+}
+
+// Pull the K/V rows this CTA will read in the attention phase into L2 ahead of time (they do not depend on the token
+// being decoded), so the phase pays L2 latency instead of loaded-HBM latency on its critical path.
+__device__ __forceinline__ void prefetch_kv(const emx_decode_params& p, int layer, int pos) {
+  const int n = pos + 1, S = p.kv_splits;
+  for (int item = blockIdx.x; item < p.heads * S; item += gridDim.x) {
+    const int head = item / S, split = item % S;
+    const int k_begin = static_cast<int>(static_cast<long>(n) * split / S), k_end = static_cast<int>(static_cast<long>(n) * (split + 1) / S);
+    for (int i = threadIdx.x; i < (k_end - k_begin) * 4; i += DEC_CTHREADS) {
+      const int key = k_begin + (i >> 2);
+      if (key == pos) continue;
+      const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>((i & 2) ? p.v_cache : p.k_cache);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + kv_row(p, layer, head, key) + (i & 1) * 64));
+    }
+  }
 }
 
 // shared-memory carve-up of the (idle) activation area during attention, in floats
@@ -506,6 +529,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   int* s_state = reinterpret_cast<int*>(misc + 16);  // [4]
   float* s_best = misc + 32;                         // [8] values + [8] indices
   float* part = misc + 64;                           // [2][8 warps][16 rows] partial row sums
+  uint32_t* s_resid = reinterpret_cast<uint32_t*>(misc + 320);  // [DEC_MAX_RESID] residual bf16 pairs of this CTA's rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   emx_decode_state* st = p.state;
@@ -527,8 +551,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   const int L = p.layers, H = p.hidden;
   long long* dbg = (blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
-  if (warp == DEC_CWARPS) {
-    producer_loop(p, ring, full, empty, lane, dbg);
+  if (warp >= DEC_CWARPS) {
+    producer_loop(p, ring, full, empty, lane, warp - DEC_CWARPS, dbg);
     return;
   }
 
@@ -553,6 +577,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     // ---- P1: RMSNorm + QKV ----
     mark();
     load_rmsnorm(resid_src, static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
+    prefetch_kv(p, layer, pos);
     consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, xs, part, warp, lane,
                   [&](int row, float a0, float a1) { *reinterpret_cast<uint32_t*>(qkv + row) = pack_bf16(a0, a1); });
     mark();
@@ -565,10 +590,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     grid_sync(&st->barrier, target, p.debug_flags & 1);
     mark();
     // ---- P3: o_proj + residual ----
+    int rb, re;
+    cta_rows(H, rb, re);
+    if (tid < (re - rb) / 2) s_resid[tid] = ldg_cg_u32(resid_src + rb + 2 * tid);  // lands while the weights stream
     load_vec(static_cast<const __nv_bfloat16*>(p.attn), xs, H);
     mark();
     consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float a0, float a1) {
-      const uint32_t r = ldg_cg_u32(resid_src + row);
+      const uint32_t r = s_resid[(row - rb) >> 1];
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
     mark();
@@ -584,10 +612,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     grid_sync(&st->barrier, target, p.debug_flags & 1);
     mark();
     // ---- P5: down_proj + residual ----
+    if (tid < (re - rb) / 2) s_resid[tid] = ldg_cg_u32(x + rb + 2 * tid);
     load_vec(hbuf, xs, p.inter);
     mark();
     consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float a0, float a1) {
-      const uint32_t r = ldg_cg_u32(x + row);
+      const uint32_t r = s_resid[(row - rb) >> 1];
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
     mark();
@@ -658,6 +687,7 @@ extern "C" int emx_decode_step(const emx_decode_params* params, cudaStream_t str
   EMX_REQUIRE(p.inter * 2 <= DEC_XS_BYTES && p.hidden * 2 <= DEC_XS_BYTES, "emx_decode_step: activation vector exceeds %d bytes", DEC_XS_BYTES);
   EMX_REQUIRE(p.kv_splits >= 1 && p.kv_splits <= 8 && (p.kv_splits & (p.kv_splits - 1)) == 0, "emx_decode_step: kv_splits must be 1, 2, 4 or 8");
   EMX_REQUIRE(p.heads <= 64, "emx_decode_step: at most 64 heads");
+  EMX_REQUIRE(p.hidden / 2 / kNumSMs + 2 <= DEC_MAX_RESID, "emx_decode_step: hidden too large for the residual staging buffer");
   const int max_keys_per_split = DEC_XS_BYTES / 4 - ATT_SSCORE;
   EMX_REQUIRE((static_cast<long>(p.max_pages) * p.page_size + p.kv_splits - 1) / p.kv_splits + 1 <= max_keys_per_split,
               "emx_decode_step: context capacity %d x %d exceeds the per-split score buffer (%d keys)", p.max_pages, p.page_size,

@@ -155,6 +155,12 @@ int emx_decode_grid(void);
 int emx_detokenize_actions(const int32_t* ids, int n, int vocab_size, int n_bins, const double* q01, const double* q99,
                            const uint8_t* mask, int action_dim, double* normalized, double* actions, emx_stream_t stream);
 
+/* ---- bandwidth probe (profiling aid, not on the product path) -------------------------------------------------
+ * Streams `bytes` from `src` through a cp.async.bulk shared-memory ring exactly like emx_decode_step's producer, with
+ * configurable stage geometry; returns the number of (rows x row_stride) blocks each CTA streamed, or <0 on error. */
+int emx_debug_stream(const void* src, long bytes, int rows, int seg, long row_stride, int stages, int evict_first, int grid,
+                     int npairs, emx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
