@@ -31,7 +31,7 @@ namespace emx {
 constexpr int DEC_CWARPS = 8;                    // consumer warps
 constexpr int DEC_CTHREADS = DEC_CWARPS * 32;    // 256
 constexpr int DEC_PWARPS = 2;                    // producer warps (alternate ring stages)
-constexpr int DEC_THREADS = DEC_CTHREADS + 32 * DEC_PWARPS;
+constexpr int DEC_THREADS = DEC_CTHREADS + 32 * DEC_PWARPS + 32;  // + L2 prefetch warp
 constexpr int DEC_GROUP = 16;                    // rows per ring stage == M of the MMA atom
 constexpr int DEC_KC = 2048;                     // K elements per ring stage (4 KB per row segment)
 constexpr int DEC_KW = DEC_KC / DEC_CWARPS;      // 256 columns per consumer warp per stage
@@ -221,30 +221,16 @@ __device__ __forceinline__ void prefetch_l2(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
-// ---- producer warp --------------------------------------------------------------------------------------------------
+// ---- producer warps -------------------------------------------------------------------------------------------------
+// Both producer warps walk the same schedule; warp `pidx` issues the ring stages with it % DEC_PWARPS == pidx.
 __device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane, int pidx,
-                              long long* dbg) {
+                              volatile uint32_t* s_groups_issued, long long* dbg) {
   const uint64_t policy = (p.debug_flags & 4) ? l2_policy_evict_last() : l2_policy_evict_first();
-  SchedIter cur, pf;
+  SchedIter cur;
   cur.init(p);
-  pf.init(p);
-  const long lookahead = static_cast<long>(p.l2_lookahead_kb) * 1024;
-  long pf_ahead = 0;  // bytes prefetched to L2 but not yet pulled into the ring
-  uint32_t it = 0;
+  uint32_t it = 0, groups = 0;
   long long waited = 0;
   while (!cur.done()) {
-    // deeper look-ahead into L2 (one contiguous block of rows per prefetch)
-    if (lookahead > 0 && pidx == 0) {
-      while (!pf.done() && pf_ahead < lookahead) {
-        const long gb = pf.group_bytes();
-        if (lane == 0) {
-          const char* src = reinterpret_cast<const char*>(pf.d.W + static_cast<long>(pf.r) * pf.d.K);
-          for (long off = 0; off < gb; off += 65536) prefetch_l2(src + off, static_cast<uint32_t>(min(65536L, gb - off)));
-        }
-        pf_ahead += gb;
-        pf.advance(p);
-      }
-    }
     const int nrows = cur.nrows();
     for (int k0 = 0; k0 < cur.d.K; k0 += DEC_KC) {
       const int klen = min(DEC_KC, cur.d.K - k0);
@@ -264,10 +250,49 @@ __device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_
       }
       ++it;
     }
-    pf_ahead -= cur.group_bytes();
+    ++groups;
+    if (pidx == 0 && lane == 0) *s_groups_issued = groups;  // progress for the L2 prefetch warp
     cur.advance(p);
   }
   if (dbg && lane == 0) dbg[15 * p.layers + 9 + pidx] = waited;
+}
+
+// ---- L2 prefetch warp ---------------------------------------------------------------------------------------------------
+// Stays `l2_lookahead_kb` ahead of the ring in the same schedule with cp.async.bulk.prefetch.L2 (one instruction per
+// 16-row group: its rows are contiguous in memory). The ring loads then hit in L2, and HBM keeps streaming into the
+// 126 MB L2 while the consumers sit in a grid barrier or in the attention phase and the 192 KB ring is full.
+__device__ void prefetch_loop(const emx_decode_params& p, int lane, volatile uint32_t* s_groups_issued) {
+  const long lookahead = static_cast<long>(p.l2_lookahead_kb) * 1024;
+  if (lookahead <= 0) return;
+  SchedIter cur, pf;
+  cur.init(p);
+  pf.init(p);
+  uint32_t cur_groups = 0;
+  long ahead = 0;  // bytes prefetched but not yet requested by the ring
+  while (!pf.done()) {
+    // retire groups the producers have already pulled into the ring
+    const uint32_t issued = *s_groups_issued;
+    while (cur_groups < issued) {
+      ahead -= cur.group_bytes();
+      cur.advance(p);
+      ++cur_groups;
+    }
+    if (ahead >= lookahead) {
+      __nanosleep(200);
+      continue;
+    }
+    const long gb = pf.group_bytes();
+    if (ahead >= 0) {  // (if the ring overtook us, skip ahead without prefetching what is already being loaded)
+      const long per_lane = ((gb + 31) / 32 + 15) & ~15L;
+      const long off = per_lane * lane;
+      if (off < gb) {
+        const char* src = reinterpret_cast<const char*>(pf.d.W + static_cast<long>(pf.r) * pf.d.K) + off;
+        prefetch_l2(src, static_cast<uint32_t>(min(per_lane, gb - off)));
+      }
+    }
+    ahead += gb;
+    pf.advance(p);
+  }
 }
 
 // ---- consumer: tensor-core dot products of one phase ---------------------------------------------------------------------
@@ -530,6 +555,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   float* s_best = misc + 32;                         // [8] values + [8] indices
   float* part = misc + 64;                           // [2][8 warps][16 rows] partial row sums
   uint32_t* s_resid = reinterpret_cast<uint32_t*>(misc + 320);  // [DEC_MAX_RESID] residual bf16 pairs of this CTA's rows
+  volatile uint32_t* s_groups_issued = reinterpret_cast<volatile uint32_t*>(misc + 24);  // producer 0 -> prefetch warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   emx_decode_state* st = p.state;
@@ -538,6 +564,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     s_state[1] = static_cast<int>(ldg_cg_u32(&st->pos));
     s_state[2] = static_cast<int>(ldg_cg_u32(&st->n_generated));
     s_state[3] = static_cast<int>(ldg_cg_u32(&st->finished));
+    *reinterpret_cast<volatile uint32_t*>(misc + 24) = 0;
     for (int s = 0; s < DEC_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], DEC_CWARPS);
@@ -551,8 +578,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   const int L = p.layers, H = p.hidden;
   long long* dbg = (blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
+  if (warp >= DEC_CWARPS + DEC_PWARPS) {
+    prefetch_loop(p, lane, s_groups_issued);
+    return;
+  }
   if (warp >= DEC_CWARPS) {
-    producer_loop(p, ring, full, empty, lane, warp - DEC_CWARPS, dbg);
+    producer_loop(p, ring, full, empty, lane, warp - DEC_CWARPS, s_groups_issued, dbg);
     return;
   }
 
