@@ -640,7 +640,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
       hbuf[row >> 1] = __float2bfloat16_rn(bf16_round(silu(bf16_round(g))) * bf16_round(u));
     });
     mark();
+    if (p.dbg && layer == 1 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 16 + 2 * blockIdx.x] = global_ns();
     grid_sync(&st->barrier, target, p.debug_flags & 1);
+    if (p.dbg && layer == 1 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 17 + 2 * blockIdx.x] = global_ns();
     mark();
     // ---- P5: down_proj + residual ----
     if (tid < (re - rb) / 2) s_resid[tid] = ldg_cg_u32(x + rb + 2 * tid);

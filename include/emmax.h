@@ -134,7 +134,7 @@ typedef struct emx_decode_params {
   int32_t eos_token;    /* -1 disables EOS handling */
   int32_t kv_splits;
   emx_decode_state* state;
-  /* optional profiling buffer (device, >= 16*layers + 16 int64): CTA 0 stores %globaltimer at every phase boundary,
+  /* optional profiling buffer (device, >= 15*layers + 16 + 2*grid int64): CTA 0 stores %globaltimer at every phase boundary,
    * then [15*layers + 8 ..] = cycles warp 0 waited for weights / cycles the producer waited for a free ring slot */
   int64_t* dbg;
   /* per-CTA look-ahead (KiB) of cp.async.bulk.prefetch.L2 beyond the shared-memory ring; 0 disables (148 CTAs x 256 KiB

@@ -27,7 +27,9 @@ pv = torch.randn(1, 6, 224, 224, device="cuda").to(torch.bfloat16)
 eng.generate(ids, pv, 2, eos_token_id=None)
 p = eng._decode_params(0)
 lib = _lib.load()
-dbg = torch.zeros(15 * L + 16, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(15 * L + 16 + 2 * 148 + 8, dtype=torch.int64, device="cuda")
+skews = []
+late = []
 names = ["P1 rmsnorm+qkv", "barrier", "attention", "barrier", "load attn", "o_proj", "barrier", "rmsnorm2", "gate/up", "barrier",
          "load h", "down", "barrier"]
 acc = np.zeros(13)
@@ -52,6 +54,9 @@ for s in range(args.warm + args.steps):
         base = 13 * L
         tail += np.array([marks[base + 1] - marks[base], marks[base + 2] - marks[base + 1], marks[base + 3] - marks[base + 2]])
         tot.append(e0.elapsed_time(e1))
+        arr = t[15 * L + 16 : 15 * L + 16 + 296].reshape(148, 2).astype(np.float64)
+        skews.append((arr[:, 0].max() - arr[:, 0].min(), arr[:, 0].max() - np.median(arr[:, 0]), (arr[:, 1] - arr[:, 0].max()).mean(), (arr[:, 1] - arr[:, 0].max()).max()))
+        late.append(arr[:, 0] - np.median(arr[:, 0]))
         cw.append(t[15 * L + 8])
         pw.append(t[15 * L + 9])
 n = args.steps
@@ -63,3 +68,12 @@ print(f"  layer total        {acc.sum() / n / 1e3:8.2f}   x{L} = {acc.sum() / n 
 print("tail (us): final rmsnorm %.2f, lm_head %.2f, final barrier %.2f" % tuple(tail / n / 1e3))
 clk = 1.965e9
 print(f"consumer warp0 waited on weights: {np.mean(cw) / clk * 1e3:.3f} ms/step; producer waited on free slots: {np.mean(pw) / clk * 1e3:.3f} ms/step")
+sk = np.array(skews) / 1e3
+print("gate/up phase end across CTAs (layer 1): max-min %.2f us, max-median %.2f us; release after last arrival: mean %.2f us, max %.2f us" % tuple(sk.mean(0)))
+late = np.array(late) / 1e3  # [steps, 148] us relative to the median CTA
+m, sd = late.mean(0), late.std(0)
+order = np.argsort(-m)
+print("slowest CTAs (mean lateness us +- std over steps):", ", ".join(f"{i}:{m[i]:.2f}+-{sd[i]:.2f}" for i in order[:12]))
+print("fastest CTAs:", ", ".join(f"{i}:{m[i]:.2f}+-{sd[i]:.2f}" for i in order[-8:]))
+print("systematic part: std of per-CTA means %.2f us; mean of per-CTA stds %.2f us" % (m.std(), sd.mean()))
+np.save("gpurun_out/cta_lateness.npy", late)
