@@ -185,6 +185,7 @@ def run_ours(args) -> None:
     import torch.distributed as dist
 
     from emmax_b200 import AutoProcessor, OpenVLAForActionPrediction, _lib
+    from emmax_b200.replicas import gather_action_tokens, pack_action_tokens
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,14 +215,12 @@ def run_ours(args) -> None:
     d_reqs = [(pv.to(dev), ids.to(dev)) for pv, ids in reqs]
     h_reqs = [(pv.pin_memory(), ids.pin_memory()) for pv, ids in reqs]
     gathered = torch.zeros((world, 8), dtype=torch.int32, device=dev)
-    mine = torch.zeros(8, dtype=torch.int32, device=dev)
     act_lo = script.index(tok.key_id("POLICIES:")) + 2  # first policy's 7 action tokens
 
     def tick_gather(new_tokens: torch.Tensor) -> None:
         """the ONE collective of the path: all-gather of each replica's action tokens, enqueued on the decode stream"""
         if world > 1:
-            mine[:7].copy_(new_tokens[act_lo : act_lo + 7])
-            dist.all_gather_into_tensor(gathered.view(-1), mine)
+            gather_action_tokens(pack_action_tokens(new_tokens[act_lo : act_lo + 7]), out=gathered)
 
     def sync_all() -> None:
         if world > 1:

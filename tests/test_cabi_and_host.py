@@ -1,0 +1,104 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/emmax.h declares, the ctypes mirror of
+its structs matches the C layout, and the product path fails loudly without CUDA (no fallback)."""
+
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from emmax_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "emmax.h")).read()
+    declared = set(re.findall(r"\b(emx_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    handle = lib.load()
+    missing = [s for s in sorted(declared) if not hasattr(handle, s)]
+    assert not missing, missing
+    assert set(lib.EXPORTS) == declared, set(lib.EXPORTS) ^ declared
+    assert handle.emx_arch() == b"sm_100a" and handle.emx_abi_version() == 1 and handle.emx_decode_grid() == 148
+
+
+def test_ctypes_structs_match_c_layout(lib):
+    prog = r"""
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "emmax.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(emx_decode_state), offsetof(emx_decode_state, head_ticket),
+             sizeof(emx_decode_params), offsetof(emx_decode_params, embed), offsetof(emx_decode_params, page_size),
+             offsetof(emx_decode_params, out_tokens), offsetof(emx_decode_params, state), offsetof(emx_decode_params, debug_flags));
+      return 0;
+    }"""
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+        open(src, "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    S, P = lib.DecodeState, lib.DecodeParams
+    want = [C.sizeof(S), S.head_ticket.offset, C.sizeof(P), P.embed.offset, P.page_size.offset, P.out_tokens.offset, P.state.offset,
+            P.debug_flags.offset]  # fmt: skip
+    assert got == want, (got, want)
+
+
+def test_argument_validation_without_gpu(lib):
+    handle = lib.load()
+    # error paths that return before any CUDA call
+    assert handle.emx_gemm_bf16(None, 8, None, 8, None, 8, 0, 8, 8, None, None, None, 0, 0, 0, None) != 0
+    assert b"empty problem" in handle.emx_last_error()
+    assert handle.emx_layernorm(None, None, None, None, 4, 7, 1e-6, None) != 0
+    assert b"multiple of 8" in handle.emx_last_error()
+    assert handle.emx_attn_fwd(None, None, 0, 1, 1, 64, 0, 1.0, None) != 0
+
+
+def test_no_cpu_fallback():
+    from emmax_b200 import OpenVLAForActionPrediction, tiny_config
+    from emmax_b200._lib import EmxError
+    from emmax_b200.synthetic import make_state_dict
+
+    cfg = tiny_config()
+    model = OpenVLAForActionPrediction(cfg, make_state_dict(cfg, seed=0))
+    with pytest.raises(EmxError):
+        model.to("cpu")
+    with pytest.raises(EmxError):
+        model.generate(torch.ones((1, 4), dtype=torch.long), pixel_values=torch.zeros(1, 6, 224, 224), max_new_tokens=2)
+    with pytest.raises(ValueError):
+        model._check_unnorm_key(model.norm_stats, "missing")
+    assert model.get_action_dim() == 7 and model.vocab_size == 32000 and model.bin_centers.shape == (255,)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "emmax_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_config_roundtrip(tmp_path):
+    from emmax_b200 import OpenVLAConfig, emma_x_config
+
+    cfg = emma_x_config()
+    cfg.save_pretrained(str(tmp_path))
+    back = OpenVLAConfig.from_pretrained(str(tmp_path))
+    assert back.to_dict() == cfg.to_dict()
+    assert back.text_config.vocab_size == 32064 and back.vision_embed_dim == 2176 and back.num_patches == 256
+    with pytest.raises(ValueError):
+        OpenVLAConfig(vision_backbone_id="clip-vit-l")
