@@ -40,7 +40,8 @@ constexpr int DEC_STAGES = 3;
 constexpr int DEC_STAGE_BYTES = DEC_GROUP * DEC_ROWSTRIDE;  // 65792
 constexpr int DEC_MAX_RESID = 192;               // residual pairs of one CTA staged in shared memory
 constexpr int DEC_XS_BYTES = 22528;                         // activation vector (bf16), up to 11264 elements
-constexpr int DEC_MISC_BYTES = 2048;
+constexpr int DEC_MISC_BYTES = 4096;
+constexpr int DEC_PARTBUFS = 4;                  // partial-sum buffers (a warp is never more than 3 ring stages ahead of warp 0)
 constexpr int DEC_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128;
 constexpr int DEC_HD = 128;  // head_dim supported by the decode kernel (Llama-2)
 
@@ -82,23 +83,22 @@ __device__ __forceinline__ void red_release_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// ticket barrier over all CTAs (consumer threads only; the producer warp never synchronises with the grid)
+// ticket barrier over all CTAs (consumer threads only; the producer warps never synchronise with the grid).
+// Arrival: one red.release.gpu after the CTA-local barrier (cumulativity publishes every consumer thread's writes).
+// Wait: lane 0 of EVERY consumer warp polls on its own — eight naturally staggered pollers per CTA cut the detection
+// delay of a single 0.6 us (loaded-L2 round trip) poll loop, and no second CTA barrier is needed after the release.
 __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t& target, bool skip = false) {
   target += gridDim.x;
   cbar();
-  if (skip) {  // profiling mode: keep the ticket arithmetic consistent, do not wait
-    if (threadIdx.x == 0) red_release_add(counter, 1u);
-    return;
-  }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    red_release_add(counter, 1u);
+  if (threadIdx.x == 0) red_release_add(counter, 1u);
+  if (skip) return;  // profiling mode: keep the ticket arithmetic consistent, do not wait
+  if ((threadIdx.x & 31) == 0) {
     uint32_t spins = 0;
     while (static_cast<int32_t>(ld_acquire_u32(counter) - target) < 0) {
       if (++spins > EMX_SPIN_LIMIT) __trap();
     }
   }
-  cbar();
+  __syncwarp();
 }
 
 __device__ __forceinline__ float cblock_sum(float v, float* red) {
@@ -141,6 +141,14 @@ __device__ __forceinline__ float sumsq8(uint4 v) {
   return ss;
 }
 
+// Activation vector layout in shared memory: inside every block of 16 words (32 bf16) the 4 x 4 word matrix is transposed
+// (word q of 16-byte vector i lands at word (i/4)*16 + 4q + i%4). The two B fragments a lane needs for TWO consecutive
+// k-steps of mma.m16n8k16 (words 8j+t, 8j+4+t, 8j+8+t, 8j+12+t, t = lane%4) are then one 16-byte shared load.
+__device__ __forceinline__ void xs_store8(__nv_bfloat16* xs, int i, uint4 v) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(xs) + (i >> 2) * 16 + (i & 3);
+  w[0] = v.x, w[4] = v.y, w[8] = v.z, w[12] = v.w;
+}
+
 // xs = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))  — LlamaRMSNorm, computed redundantly by every CTA.
 // x and w loads are issued together (one L2/HBM round trip on the critical path instead of two).
 __device__ __forceinline__ void load_rmsnorm(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* xs, int H, float eps,
@@ -152,24 +160,20 @@ __device__ __forceinline__ void load_rmsnorm(const __nv_bfloat16* x, const __nv_
     if (i0 < nv) v0 = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i0), w0 = reinterpret_cast<const uint4*>(w)[i0];
     if (i1 < nv) v1 = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i1), w1 = reinterpret_cast<const uint4*>(w)[i1];
     const float rs = 1.0f / sqrtf(cblock_sum(sumsq8(v0) + sumsq8(v1), red) / H + eps);
-    if (i0 < nv) reinterpret_cast<uint4*>(xs)[i0] = rms_apply(v0, w0, rs);
-    if (i1 < nv) reinterpret_cast<uint4*>(xs)[i1] = rms_apply(v1, w1, rs);
+    if (i0 < nv) xs_store8(xs, i0, rms_apply(v0, w0, rs));
+    if (i1 < nv) xs_store8(xs, i1, rms_apply(v1, w1, rs));
   } else {
     float ss = 0.f;
-    for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS) {
-      const uint4 v = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i);
-      reinterpret_cast<uint4*>(xs)[i] = v;
-      ss += sumsq8(v);
-    }
+    for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS) ss += sumsq8(ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i));
     const float rs = 1.0f / sqrtf(cblock_sum(ss, red) / H + eps);
     for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS)
-      reinterpret_cast<uint4*>(xs)[i] = rms_apply(reinterpret_cast<uint4*>(xs)[i], reinterpret_cast<const uint4*>(w)[i], rs);
+      xs_store8(xs, i, rms_apply(ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i), reinterpret_cast<const uint4*>(w)[i], rs));
   }
   cbar();
 }
 
 __device__ __forceinline__ void load_vec(const __nv_bfloat16* v, __nv_bfloat16* xs, int n) {
-  for (int i = threadIdx.x; i < (n >> 3); i += DEC_CTHREADS) reinterpret_cast<uint4*>(xs)[i] = ldg_cg_v4(reinterpret_cast<const uint4*>(v) + i);
+  for (int i = threadIdx.x; i < (n >> 3); i += DEC_CTHREADS) xs_store8(xs, i, ldg_cg_v4(reinterpret_cast<const uint4*>(v) + i));
   cbar();
 }
 
@@ -258,17 +262,22 @@ __device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_
 }
 
 // ---- L2 prefetch warp ---------------------------------------------------------------------------------------------------
-// Stays `l2_lookahead_kb` ahead of the ring in the same schedule with cp.async.bulk.prefetch.L2 (one instruction per
-// 16-row group: its rows are contiguous in memory). The ring loads then hit in L2, and HBM keeps streaming into the
-// 126 MB L2 while the consumers sit in a grid barrier or in the attention phase and the 192 KB ring is full.
+// Runs `l2_lookahead_kb` ahead of the ring in the same static schedule and pulls the weights HBM -> L2, so that HBM keeps
+// streaming into the 126 MB L2 while the consumers sit in a grid barrier or in the attention phase and the 192 KB ring
+// is full; the ring loads then hit in L2 and the consumers catch up at L2 speed. The prefetches are issued from the LSU
+// (prefetch.global.L2, one 128-B line per lane) and NOT as cp.async.bulk.prefetch: bulk prefetches queue in the same
+// per-SM TMA engine as the ring copies and were measured to slow the kernel down (profiles/r01_decode_l2_prefetch_sweep.txt).
 __device__ void prefetch_loop(const emx_decode_params& p, int lane, volatile uint32_t* s_groups_issued) {
   const long lookahead = static_cast<long>(p.l2_lookahead_kb) * 1024;
   if (lookahead <= 0) return;
+  const int mode = (p.debug_flags >> 4) & 3;  // 0: LSU prefetch per line, 1: bulk (TMA) prefetch, 2: ld with L2::256B hint
+  constexpr long CHUNK = 32 * 1024;
   SchedIter cur, pf;
   cur.init(p);
   pf.init(p);
   uint32_t cur_groups = 0;
-  long ahead = 0;  // bytes prefetched but not yet requested by the ring
+  long ahead = 0;   // bytes prefetched (or skipped) but not yet requested by the ring
+  long pf_off = 0;  // progress inside the group `pf` points at
   while (!pf.done()) {
     // retire groups the producers have already pulled into the ring
     const uint32_t issued = *s_groups_issued;
@@ -278,20 +287,32 @@ __device__ void prefetch_loop(const emx_decode_params& p, int lane, volatile uin
       ++cur_groups;
     }
     if (ahead >= lookahead) {
-      __nanosleep(200);
+      __nanosleep(100);
       continue;
     }
     const long gb = pf.group_bytes();
-    if (ahead >= 0) {  // (if the ring overtook us, skip ahead without prefetching what is already being loaded)
-      const long per_lane = ((gb + 31) / 32 + 15) & ~15L;
-      const long off = per_lane * lane;
-      if (off < gb) {
-        const char* src = reinterpret_cast<const char*>(pf.d.W + static_cast<long>(pf.r) * pf.d.K) + off;
-        prefetch_l2(src, static_cast<uint32_t>(min(per_lane, gb - off)));
+    const long n = min(CHUNK, gb - pf_off);
+    if (ahead + pf_off >= 0) {  // (if the ring overtook us, skip ahead without prefetching what is already being loaded)
+      const char* src = reinterpret_cast<const char*>(pf.d.W + static_cast<long>(pf.r) * pf.d.K) + pf_off;
+      if (mode == 1) {
+        const long per_lane = ((n + 31) / 32 + 15) & ~15L;
+        const long off = per_lane * lane;
+        if (off < n) prefetch_l2(src + off, static_cast<uint32_t>(min(per_lane, n - off)));
+      } else if (mode == 2) {
+        for (long off = lane * 256L; off < n; off += 32 * 256L) {
+          uint32_t sink;
+          asm volatile("ld.global.L1::no_allocate.L2::256B.u32 %0, [%1];" : "=r"(sink) : "l"(src + off));
+        }
+      } else {
+        for (long off = lane * 128L; off < n; off += 32 * 128L) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
       }
     }
-    ahead += gb;
-    pf.advance(p);
+    pf_off += n;
+    if (pf_off >= gb) {
+      ahead += gb;
+      pf_off = 0;
+      pf.advance(p);
+    }
   }
 }
 
@@ -307,9 +328,15 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 
 struct ConsumerState {
   uint32_t it;
-  uint32_t group;  // parity selects the partial-sum buffer
+  uint32_t group;  // selects the partial-sum buffer / named barrier
   long long waited;
 };
+
+// Hand-off of per-warp partial row sums to warp 0: warps 1..7 arrive and run on, warp 0 waits. One named barrier per
+// partial buffer; a warp can be at most DEC_STAGES ring stages (< DEC_PARTBUFS row groups) ahead of warp 0, so neither a
+// buffer nor a barrier id is reused before warp 0 is done with it.
+__device__ __forceinline__ void part_arrive(uint32_t buf) { asm volatile("bar.arrive %0, %1;" ::"r"(2u + buf), "n"(DEC_CTHREADS) : "memory"); }
+__device__ __forceinline__ void part_sync(uint32_t buf) { asm volatile("bar.sync %0, %1;" ::"r"(2u + buf), "n"(DEC_CTHREADS) : "memory"); }
 
 // epi(row, v0, v1) is called for row pairs (row even) by threads 0..7 of warp 0, rows ascending per thread
 template <typename Epi>
@@ -322,30 +349,43 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
   const int kbeg = warp * DEC_KW;
   for (int r0 = r_begin; r0 < r_end; r0 += DEC_GROUP) {
     const int nrows = min(DEC_GROUP, r_end - r0);
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    // four independent accumulator chains (k-step % 4): the HMMA dependency latency is off the critical path
+    float c[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = c[q][2] = c[q][3] = 0.f;
     for (int k0 = 0; k0 < d.K; k0 += DEC_KC) {
       const int klen = min(DEC_KC, d.K - k0);
       const int slot = cs.it % DEC_STAGES;
       const uint32_t ph = (cs.it / DEC_STAGES) & 1;
+      const int ksteps = min(DEC_KW / 16, (klen - kbeg) / 16);  // <= 0: this warp's slice is past the K tail
+      const uint4* xw = reinterpret_cast<const uint4*>(xs + k0 + kbeg) + (lane & 3);
       const long long t0 = clock64();
       mbar_wait(&full[slot], ph);
       cs.waited += clock64() - t0;
-      const int ksteps = min(DEC_KW / 16, (klen - kbeg) / 16);  // <= 0: this warp's slice is past the K tail
       if (ksteps > 0) {
         const uint32_t a_base = smem_u32(ring + slot * DEC_STAGE_BYTES) + a_lane_off + kbeg * 2;
-        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs + k0 + kbeg) + (lane & 3);
         if (ksteps == DEC_KW / 16) {
 #pragma unroll
-          for (int j = 0; j < DEC_KW / 16; ++j) {
-            uint32_t a0, a1, a2, a3;
-            ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
-            mma_bf16_16816(c, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
+          for (int h = 0; h < 2; ++h) {  // two batches of 8 k-steps: 8 ldmatrix in flight, then 8 HMMA
+            uint32_t a[8][4];
+            uint4 b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = xw[(h * 4 + j) * 4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ldmatrix_x4(a_base + (h * 8 + j) * 32, a[j][0], a[j][1], a[j][2], a[j][3]);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const uint4 bb = b[j / 2];
+              mma_bf16_16816(c[j & 3], a[j][0], a[j][1], a[j][2], a[j][3], bb.x, bb.y);
+              mma_bf16_16816(c[(j + 1) & 3], a[j + 1][0], a[j + 1][1], a[j + 1][2], a[j + 1][3], bb.z, bb.w);
+            }
           }
         } else {
           for (int j = 0; j < ksteps; ++j) {
             uint32_t a0, a1, a2, a3;
             ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
-            mma_bf16_16816(c, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
+            const uint4 bb = xw[(j >> 1) * 4];
+            mma_bf16_16816(c[0], a0, a1, a2, a3, (j & 1) ? bb.z : bb.x, (j & 1) ? bb.w : bb.y);
           }
         }
       }
@@ -354,17 +394,22 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
       ++cs.it;
     }
     // column 0 of the accumulator tile lives in lanes with lane % 4 == 0: c[0] -> row lane/4, c[2] -> row lane/4 + 8
-    float* pb = part + (cs.group & 1) * (DEC_CWARPS * DEC_GROUP);
+    const uint32_t buf = cs.group % DEC_PARTBUFS;
+    float* pb = part + buf * (DEC_CWARPS * DEC_GROUP);
     if ((lane & 3) == 0) {
-      pb[warp * DEC_GROUP + (lane >> 2)] = c[0];
-      pb[warp * DEC_GROUP + (lane >> 2) + 8] = c[2];
+      pb[warp * DEC_GROUP + (lane >> 2)] = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+      pb[warp * DEC_GROUP + (lane >> 2) + 8] = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]);
     }
-    cbar();
-    if (warp == 0 && lane < 8 && 2 * lane < nrows) {
-      float v0 = 0.f, v1 = 0.f;
+    if (warp == 0) {
+      part_sync(buf);
+      if (lane < 8 && 2 * lane < nrows) {
+        float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-      for (int w = 0; w < DEC_CWARPS; ++w) v0 += pb[w * DEC_GROUP + 2 * lane], v1 += pb[w * DEC_GROUP + 2 * lane + 1];
-      epi(r0 + 2 * lane, v0, v1);
+        for (int w = 0; w < DEC_CWARPS; ++w) v0 += pb[w * DEC_GROUP + 2 * lane], v1 += pb[w * DEC_GROUP + 2 * lane + 1];
+        epi(r0 + 2 * lane, v0, v1);
+      }
+    } else {
+      part_arrive(buf);
     }
     ++cs.group;
   }
@@ -553,8 +598,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   float* red = misc;                                 // [8]
   int* s_state = reinterpret_cast<int*>(misc + 16);  // [4]
   float* s_best = misc + 32;                         // [8] values + [8] indices
-  float* part = misc + 64;                           // [2][8 warps][16 rows] partial row sums
-  uint32_t* s_resid = reinterpret_cast<uint32_t*>(misc + 320);  // [DEC_MAX_RESID] residual bf16 pairs of this CTA's rows
+  float* part = misc + 64;                           // [DEC_PARTBUFS][8 warps][16 rows] partial row sums
+  uint32_t* s_resid = reinterpret_cast<uint32_t*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP);  // [DEC_MAX_RESID] residual bf16 pairs of this CTA's rows
   volatile uint32_t* s_groups_issued = reinterpret_cast<volatile uint32_t*>(misc + 24);  // producer 0 -> prefetch warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -1,5 +1,7 @@
-"""Phase-level timing of the persistent decode kernel (CTA 0's view, %globaltimer) + ring wait counters.
-Usage (GPU box): python tools/decode_probe.py [--steps 16] [--ctx-extra 0]"""
+"""Phase-level timing of the persistent decode kernel (CTA 0's view, %globaltimer) + ring wait counters, swept over
+(L2 look-ahead KiB, debug_flags) configurations with ONE model build.
+Usage (GPU box): python tools/decode_probe.py [--steps 16] [--configs 0:0,256:0,256:16] [--ctx 296] [--brief]
+debug_flags: 1 skip grid barriers, 2 skip attention, 4 no evict-first hint, 16 bulk (TMA) L2 prefetch, 32 ld.L2::256B prefetch."""
 import argparse
 import ctypes as C
 import os
@@ -15,6 +17,9 @@ from emmax_b200.synthetic import make_state_dict
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=16)
 ap.add_argument("--warm", type=int, default=8)
+ap.add_argument("--configs", default="0:0")
+ap.add_argument("--brief", action="store_true")
+ap.add_argument("--advance", type=int, default=0, help="decode this many extra tokens first (longer context)")
 args = ap.parse_args()
 
 cfg = emma_x_config()
@@ -24,56 +29,57 @@ eng = model.engine
 L = cfg.text_config.num_hidden_layers
 ids = torch.tensor([[1] + np.random.default_rng(1234).integers(3, 31744, 39).tolist()], device="cuda")
 pv = torch.randn(1, 6, 224, 224, device="cuda").to(torch.bfloat16)
-eng.generate(ids, pv, 2, eos_token_id=None)
-p = eng._decode_params(0)
+eng.generate(ids, pv, 2 + args.advance, eos_token_id=None)
 lib = _lib.load()
-dbg = torch.zeros(15 * L + 16 + 2 * 148 + 8, dtype=torch.int64, device="cuda")
-skews = []
-late = []
 names = ["P1 rmsnorm+qkv", "barrier", "attention", "barrier", "load attn", "o_proj", "barrier", "rmsnorm2", "gate/up", "barrier",
-         "load h", "down", "barrier"]
-acc = np.zeros(13)
-tail = np.zeros(3)
-tot = []
-cw, pw = [], []
-for s in range(args.warm + args.steps):
-    p.dbg = dbg.data_ptr() if s >= args.warm else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    _lib.check(lib.emx_decode_step(C.byref(p), _lib.stream()))
-    e1.record()
-    torch.cuda.synchronize()
-    if s >= args.warm:
-        t = dbg.cpu().numpy()
-        marks = t[: 13 * L + 4].astype(np.float64)
-        d = np.diff(marks)
-        per_layer = d[: 13 * L].reshape(L, 13) if False else None
-        # interval k of layer l = marks[13l + k + 1] - marks[13l + k]
-        iv = np.array([[marks[13 * l + k + 1] - marks[13 * l + k] for k in range(13)] for l in range(L)])
-        acc += iv.mean(0)
-        base = 13 * L
-        tail += np.array([marks[base + 1] - marks[base], marks[base + 2] - marks[base + 1], marks[base + 3] - marks[base + 2]])
-        tot.append(e0.elapsed_time(e1))
-        arr = t[15 * L + 16 : 15 * L + 16 + 296].reshape(148, 2).astype(np.float64)
-        skews.append((arr[:, 0].max() - arr[:, 0].min(), arr[:, 0].max() - np.median(arr[:, 0]), (arr[:, 1] - arr[:, 0].max()).mean(), (arr[:, 1] - arr[:, 0].max()).max()))
-        late.append(arr[:, 0] - np.median(arr[:, 0]))
-        cw.append(t[15 * L + 8])
-        pw.append(t[15 * L + 9])
-n = args.steps
-print(f"kernel time: mean {np.mean(tot):.3f} ms  (min {np.min(tot):.3f})")
-print("per-layer phase means (us), CTA 0:")
-for nm, v in zip(names, acc / n / 1e3):
-    print(f"  {nm:18s} {v:8.2f}")
-print(f"  layer total        {acc.sum() / n / 1e3:8.2f}   x{L} = {acc.sum() / n / 1e6 * L:.3f} ms")
-print("tail (us): final rmsnorm %.2f, lm_head %.2f, final barrier %.2f" % tuple(tail / n / 1e3))
+         "load h", "down", "barrier"]  # fmt: skip
 clk = 1.965e9
-print(f"consumer warp0 waited on weights: {np.mean(cw) / clk * 1e3:.3f} ms/step; producer waited on free slots: {np.mean(pw) / clk * 1e3:.3f} ms/step")
-sk = np.array(skews) / 1e3
-print("gate/up phase end across CTAs (layer 1): max-min %.2f us, max-median %.2f us; release after last arrival: mean %.2f us, max %.2f us" % tuple(sk.mean(0)))
-late = np.array(late) / 1e3  # [steps, 148] us relative to the median CTA
-m, sd = late.mean(0), late.std(0)
-order = np.argsort(-m)
-print("slowest CTAs (mean lateness us +- std over steps):", ", ".join(f"{i}:{m[i]:.2f}+-{sd[i]:.2f}" for i in order[:12]))
-print("fastest CTAs:", ", ".join(f"{i}:{m[i]:.2f}+-{sd[i]:.2f}" for i in order[-8:]))
-print("systematic part: std of per-CTA means %.2f us; mean of per-CTA stds %.2f us" % (m.std(), sd.mean()))
-np.save("gpurun_out/cta_lateness.npy", late)
+
+for conf in args.configs.split(","):
+    la, flags = (int(v) for v in conf.split(":"))
+    p = eng._decode_params(0)
+    p.l2_lookahead_kb, p.debug_flags = la, flags
+    dbg = torch.zeros(15 * L + 16 + 2 * 148 + 8, dtype=torch.int64, device="cuda")
+    skews, late, tot, cw, pw = [], [], [], [], []
+    acc, tail = np.zeros(13), np.zeros(3)
+    for s in range(args.warm + args.steps):
+        p.dbg = dbg.data_ptr() if s >= args.warm else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.emx_decode_step(C.byref(p), _lib.stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        if s >= args.warm:
+            t = dbg.cpu().numpy()
+            marks = t[: 13 * L + 4].astype(np.float64)
+            iv = np.array([[marks[13 * l + k + 1] - marks[13 * l + k] for k in range(13)] for l in range(L)])
+            acc += iv.mean(0)
+            base = 13 * L
+            tail += np.array([marks[base + 1] - marks[base], marks[base + 2] - marks[base + 1], marks[base + 3] - marks[base + 2]])
+            tot.append(e0.elapsed_time(e1))
+            arr = t[15 * L + 16 : 15 * L + 16 + 296].reshape(148, 2).astype(np.float64)
+            skews.append((arr[:, 0].max() - arr[:, 0].min(), arr[:, 0].max() - np.median(arr[:, 0]), (arr[:, 1] - arr[:, 0].max()).mean(),
+                          (arr[:, 1] - arr[:, 0].max()).max()))  # fmt: skip
+            late.append(arr[:, 0] - np.median(arr[:, 0]))
+            cw.append(t[15 * L + 8])
+            pw.append(t[15 * L + 9])
+    n = args.steps
+    a = acc / n / 1e3
+    sk = np.array(skews).mean(0) / 1e3
+    print(f"== lookahead {la} KiB, debug_flags {flags}: kernel {np.mean(tot):.3f} ms (min {np.min(tot):.3f}) | per layer {a.sum():.2f} us: "
+          f"weights {a[0] + a[5] + a[8] + a[11]:.2f} (qkv {a[0]:.2f} o {a[5]:.2f} gateup {a[8]:.2f} down {a[11]:.2f}) barriers "
+          f"{a[1] + a[3] + a[6] + a[9] + a[12]:.2f} attention {a[2]:.2f} loads {a[4] + a[7] + a[10]:.2f} | lm_head {tail[1] / n / 1e3:.1f} us | "
+          f"consumer wait {np.mean(cw) / clk * 1e3:.3f} ms | gate/up skew max-min {sk[0]:.2f} us, release {sk[2]:.2f} us", flush=True)  # fmt: skip
+    if args.brief:
+        continue
+    print("per-layer phase means (us), CTA 0:")
+    for nm, v in zip(names, a):
+        print(f"  {nm:18s} {v:8.2f}")
+    print("tail (us): final rmsnorm %.2f, lm_head %.2f, final barrier %.2f" % tuple(tail / n / 1e3))
+    print(f"consumer warp0 waited on weights: {np.mean(cw) / clk * 1e3:.3f} ms/step; producer waited on free slots: {np.mean(pw) / clk * 1e3:.3f} ms/step")
+    print("gate/up phase end across CTAs (layer 1): max-min %.2f us, max-median %.2f us; release after last arrival: mean %.2f us, max %.2f us" % tuple(sk))
+    lt = np.array(late) / 1e3  # [steps, 148] us relative to the median CTA
+    m, sdv = lt.mean(0), lt.std(0)
+    order = np.argsort(-m)
+    print("slowest CTAs (mean lateness us +- std over steps):", ", ".join(f"{i}:{m[i]:.2f}+-{sdv[i]:.2f}" for i in order[:12]))
+    print("systematic part: std of per-CTA means %.2f us; mean of per-CTA stds %.2f us" % (m.std(), sdv.mean()))
