@@ -84,21 +84,24 @@ __device__ __forceinline__ void red_release_add(uint32_t* p, uint32_t v) {
 }
 
 // ticket barrier over all CTAs (consumer threads only; the producer warps never synchronise with the grid).
-// Arrival: one red.release.gpu after the CTA-local barrier (cumulativity publishes every consumer thread's writes).
-// Wait: lane 0 of EVERY consumer warp polls on its own — eight naturally staggered pollers per CTA cut the detection
-// delay of a single 0.6 us (loaded-L2 round trip) poll loop, and no second CTA barrier is needed after the release.
+// One red.release.gpu per CTA after the CTA-local barrier (cumulativity publishes every consumer thread's writes), ONE poller
+// per CTA (relaxed loads, a single acquire fence at the end). Measured on B200 (profiles/r01_skeleton_probe.txt): ~1.9 us per
+// barrier even on an idle memory system; multi-counter, tree, flag-per-CTA and 8-pollers-per-CTA protocols are all slower.
 __device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t& target, bool skip = false) {
   target += gridDim.x;
   cbar();
-  if (threadIdx.x == 0) red_release_add(counter, 1u);
-  if (skip) return;  // profiling mode: keep the ticket arithmetic consistent, do not wait
-  if ((threadIdx.x & 31) == 0) {
-    uint32_t spins = 0;
-    while (static_cast<int32_t>(ld_acquire_u32(counter) - target) < 0) {
-      if (++spins > EMX_SPIN_LIMIT) __trap();
+  if (threadIdx.x == 0) {
+    red_release_add(counter, 1u);
+    if (!skip) {  // (profiling mode: keep the ticket arithmetic consistent, do not wait)
+      uint32_t spins = 0, v;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (++spins > EMX_SPIN_LIMIT) __trap();
+      } while (static_cast<int32_t>(v - target) < 0);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
   }
-  __syncwarp();
+  cbar();
 }
 
 __device__ __forceinline__ float cblock_sum(float v, float* red) {
@@ -251,69 +254,82 @@ __device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_
         if (lane < nrows)
           bulk_g2s(ring + slot * DEC_STAGE_BYTES + lane * DEC_ROWSTRIDE, cur.d.W + static_cast<long>(cur.r + lane) * cur.d.K + k0,
                    klen * 2, &full[slot], policy);
+        if (lane == 0) s_groups_issued[pidx] = it + 1;  // ring stages issued by this producer (for the L2 prefetch warp)
       }
       ++it;
     }
     ++groups;
-    if (pidx == 0 && lane == 0) *s_groups_issued = groups;  // progress for the L2 prefetch warp
     cur.advance(p);
   }
   if (dbg && lane == 0) dbg[15 * p.layers + 9 + pidx] = waited;
 }
 
 // ---- L2 prefetch warp ---------------------------------------------------------------------------------------------------
-// Runs `l2_lookahead_kb` ahead of the ring in the same static schedule and pulls the weights HBM -> L2, so that HBM keeps
-// streaming into the 126 MB L2 while the consumers sit in a grid barrier or in the attention phase and the 192 KB ring
-// is full; the ring loads then hit in L2 and the consumers catch up at L2 speed. The prefetches are issued from the LSU
-// (prefetch.global.L2, one 128-B line per lane) and NOT as cp.async.bulk.prefetch: bulk prefetches queue in the same
-// per-SM TMA engine as the ring copies and were measured to slow the kernel down (profiles/r01_decode_l2_prefetch_sweep.txt).
-__device__ void prefetch_loop(const emx_decode_params& p, int lane, volatile uint32_t* s_groups_issued) {
+// The 192 KB ring only just covers the bandwidth-delay product of a saturated HBM (~45 KB/us per SM x ~4 us loaded latency),
+// so whenever the consumers stall (grid barrier, attention) the ring fills, no new copy can be issued and HBM idles
+// (tools/skeleton_probe.py: stalls are 100 % exposed without prefetch). This warp watches for exactly that condition — the
+// newest ring copy of this CTA has LANDED, i.e. nothing of ours is in flight — and then pulls the next groups of the static
+// schedule HBM -> L2 with cp.async.bulk.prefetch.L2, paced at about twice the SM's fair share, at most `l2_lookahead_kb`
+// ahead of the ring. In the HBM-bound steady state it never triggers, so it costs nothing there.
+__device__ void prefetch_loop(const emx_decode_params& p, int lane, volatile uint32_t* s_issued, uint64_t* full) {
   const long lookahead = static_cast<long>(p.l2_lookahead_kb) * 1024;
   if (lookahead <= 0) return;
-  const int mode = (p.debug_flags >> 4) & 3;  // 0: LSU prefetch per line, 1: bulk (TMA) prefetch, 2: ld with L2::256B hint
-  constexpr long CHUNK = 32 * 1024;
+  const long long pace_ns = (p.debug_flags >> 8) ? (p.debug_flags >> 8) * 10 : 700;  // per 64 KB
   SchedIter cur, pf;
   cur.init(p);
   pf.init(p);
-  uint32_t cur_groups = 0;
-  long ahead = 0;   // bytes prefetched (or skipped) but not yet requested by the ring
-  long pf_off = 0;  // progress inside the group `pf` points at
+  uint32_t cur_stage = 0;  // first ring-stage index of the group `cur` points at
+  long ahead = 0;          // bytes between the start of `cur` and the start of `pf`
+  long pf_off = 0;         // progress inside the group `pf` points at
+  long pf_total = 0;
   while (!pf.done()) {
-    // retire groups the producers have already pulled into the ring
-    const uint32_t issued = *s_groups_issued;
-    while (cur_groups < issued) {
+    // follow the producers: s_issued = number of ring stages issued so far
+    const uint32_t issued = max(s_issued[0], s_issued[1]);
+    while (!cur.done()) {
+      const uint32_t st = (cur.d.K + DEC_KC - 1) / DEC_KC;
+      if (cur_stage + st > issued) break;
+      cur_stage += st;
       ahead -= cur.group_bytes();
       cur.advance(p);
-      ++cur_groups;
     }
-    if (ahead >= lookahead) {
-      __nanosleep(100);
+    if (cur.done()) break;  // everything is in the ring already
+    if (ahead <= 0) {  // at (or behind) the group the ring is loading right now: start with the one after it
+      pf = cur, pf_off = 0;
+      ahead = pf.group_bytes();
+      pf.advance(p);
+      if (pf.done()) break;
+    }
+    bool idle = false;
+    // lead of the prefetch point over the ring's issue point, in bytes
+    const uint32_t st_cur = (cur.d.K + DEC_KC - 1) / DEC_KC;
+    const long lead = ahead + pf_off - static_cast<long>(issued - cur_stage) * (cur.group_bytes() / st_cur);
+    if (issued > 0 && lead < lookahead) {
+      const uint32_t last = issued - 1;
+      idle = mbar_try_wait(&full[last % DEC_STAGES], (last / DEC_STAGES) & 1);
+    }
+    if (!idle) {
+      __nanosleep(200);
       continue;
     }
+    const long long t0 = global_ns();
     const long gb = pf.group_bytes();
-    const long n = min(CHUNK, gb - pf_off);
-    if (ahead + pf_off >= 0) {  // (if the ring overtook us, skip ahead without prefetching what is already being loaded)
+    const long n = min(static_cast<long>(64 * 1024), gb - pf_off);
+    {
       const char* src = reinterpret_cast<const char*>(pf.d.W + static_cast<long>(pf.r) * pf.d.K) + pf_off;
-      if (mode == 1) {
-        const long per_lane = ((n + 31) / 32 + 15) & ~15L;
-        const long off = per_lane * lane;
-        if (off < n) prefetch_l2(src + off, static_cast<uint32_t>(min(per_lane, n - off)));
-      } else if (mode == 2) {
-        for (long off = lane * 256L; off < n; off += 32 * 256L) {
-          uint32_t sink;
-          asm volatile("ld.global.L1::no_allocate.L2::256B.u32 %0, [%1];" : "=r"(sink) : "l"(src + off));
-        }
-      } else {
-        for (long off = lane * 128L; off < n; off += 32 * 128L) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
-      }
+      const long per_lane = ((n + 31) / 32 + 15) & ~15L;
+      const long off = per_lane * lane;
+      if (off < n) prefetch_l2(src + off, static_cast<uint32_t>(min(per_lane, n - off)));
     }
+    pf_total += n;
     pf_off += n;
     if (pf_off >= gb) {
       ahead += gb;
       pf_off = 0;
       pf.advance(p);
     }
+    while (global_ns() - t0 < pace_ns * n / (64 * 1024)) __nanosleep(100);
   }
+  if (p.dbg && blockIdx.x == 0 && lane == 0) reinterpret_cast<long long*>(p.dbg)[15 * p.layers + 13] = pf_total;
 }
 
 // ---- consumer: tensor-core dot products of one phase ---------------------------------------------------------------------
@@ -329,7 +345,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 struct ConsumerState {
   uint32_t it;
   uint32_t group;  // selects the partial-sum buffer / named barrier
-  long long waited;
+  long long waited;        // cycles in mbar_wait(full) (thread 0: warp 0)
+  long long t_sync, t_epi;  // cycles warp 0 spent waiting for the other warps' partial sums / in the epilogue
 };
 
 // Hand-off of per-warp partial row sums to warp 0: warps 1..7 arrive and run on, warp 0 waits. One named barrier per
@@ -341,7 +358,7 @@ __device__ __forceinline__ void part_sync(uint32_t buf) { asm volatile("bar.sync
 // epi(row, v0, v1) is called for row pairs (row even) by threads 0..7 of warp 0, rows ascending per thread
 template <typename Epi>
 __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t* ring, uint64_t* full, uint64_t* empty, ConsumerState& cs,
-                                              const __nv_bfloat16* xs, float* part, int warp, int lane, Epi&& epi) {
+                                              const __nv_bfloat16* xs, float* part, int warp, int lane, int debug_flags, Epi&& epi) {
   int r_begin, r_end;
   cta_rows(d.N, r_begin, r_end);
   // ldmatrix.x4 row address of this lane: matrices (rows 0-7 | 8-15) x (cols 0-7 | 8-15) of a 16x16 A tile
@@ -362,7 +379,7 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
       const long long t0 = clock64();
       mbar_wait(&full[slot], ph);
       cs.waited += clock64() - t0;
-      if (ksteps > 0) {
+      if (ksteps > 0 && !(debug_flags & 64)) {
         const uint32_t a_base = smem_u32(ring + slot * DEC_STAGE_BYTES) + a_lane_off + kbeg * 2;
         if (ksteps == DEC_KW / 16) {
 #pragma unroll
@@ -401,13 +418,17 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
       pb[warp * DEC_GROUP + (lane >> 2) + 8] = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]);
     }
     if (warp == 0) {
+      const long long t1 = clock64();
       part_sync(buf);
+      const long long t2 = clock64();
       if (lane < 8 && 2 * lane < nrows) {
         float v0 = 0.f, v1 = 0.f;
 #pragma unroll
         for (int w = 0; w < DEC_CWARPS; ++w) v0 += pb[w * DEC_GROUP + 2 * lane], v1 += pb[w * DEC_GROUP + 2 * lane + 1];
         epi(r0 + 2 * lane, v0, v1);
       }
+      __syncwarp();
+      cs.t_sync += t2 - t1, cs.t_epi += clock64() - t2;
     } else {
       part_arrive(buf);
     }
@@ -610,6 +631,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     s_state[2] = static_cast<int>(ldg_cg_u32(&st->n_generated));
     s_state[3] = static_cast<int>(ldg_cg_u32(&st->finished));
     *reinterpret_cast<volatile uint32_t*>(misc + 24) = 0;
+    *reinterpret_cast<volatile uint32_t*>(misc + 25) = 0;
     for (int s = 0; s < DEC_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], DEC_CWARPS);
@@ -624,7 +646,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   long long* dbg = (blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
   if (warp >= DEC_CWARPS + DEC_PWARPS) {
-    prefetch_loop(p, lane, s_groups_issued);
+    prefetch_loop(p, lane, s_groups_issued, full);
     return;
   }
   if (warp >= DEC_CWARPS) {
@@ -638,7 +660,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     if (dbg && tid == 0) dbg[dbg_i] = global_ns();
     ++dbg_i;
   };
-  ConsumerState cs{0, 0, 0};
+  ConsumerState cs{0, 0, 0, 0, 0};
   // barrier tickets: every non-finished launch performs exactly (5 L + 1) grid syncs
   const uint32_t n_sync = 5u * L + 1u;
   uint32_t target = ldg_cg_u32(&st->epoch) * n_sync * gridDim.x;
@@ -654,7 +676,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     mark();
     load_rmsnorm(resid_src, static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
     prefetch_kv(p, layer, pos);
-    consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, xs, part, warp, lane,
+    consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags,
                   [&](int row, float a0, float a1) { *reinterpret_cast<uint32_t*>(qkv + row) = pack_bf16(a0, a1); });
     mark();
     grid_sync(&st->barrier, target, p.debug_flags & 1);
@@ -671,7 +693,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     if (tid < (re - rb) / 2) s_resid[tid] = ldg_cg_u32(resid_src + rb + 2 * tid);  // lands while the weights stream
     load_vec(static_cast<const __nv_bfloat16*>(p.attn), xs, H);
     mark();
-    consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float a0, float a1) {
+    consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags, [&](int row, float a0, float a1) {
       const uint32_t r = s_resid[(row - rb) >> 1];
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
@@ -681,7 +703,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     // ---- P4: RMSNorm + gate/up + SwiGLU ----
     load_rmsnorm(x, static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
     mark();
-    consume_phase(phase_desc(p, layer, PH_GATEUP), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float g, float u) {
+    consume_phase(phase_desc(p, layer, PH_GATEUP), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags, [&](int row, float g, float u) {
       hbuf[row >> 1] = __float2bfloat16_rn(bf16_round(silu(bf16_round(g))) * bf16_round(u));
     });
     mark();
@@ -693,7 +715,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     if (tid < (re - rb) / 2) s_resid[tid] = ldg_cg_u32(x + rb + 2 * tid);
     load_vec(hbuf, xs, p.inter);
     mark();
-    consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float a0, float a1) {
+    consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags, [&](int row, float a0, float a1) {
       const uint32_t r = s_resid[(row - rb) >> 1];
       *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
     });
@@ -707,14 +729,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   mark();
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  consume_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, cs, xs, part, warp, lane, [&](int row, float a0, float a1) {
+  consume_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags, [&](int row, float a0, float a1) {
     const float v0 = bf16_round(a0), v1 = bf16_round(a1);
     if (p.logits_out) p.logits_out[row] = v0, p.logits_out[row + 1] = v1;
     if (v0 > best) best = v0, best_i = row;  // rows ascend per thread: strict '>' keeps the lowest index
     if (v1 > best) best = v1, best_i = row + 1;
   });
   mark();
-  if (dbg && tid == 0) dbg[15 * L + 8] = cs.waited;
+  if (dbg && tid == 0) dbg[15 * L + 8] = cs.waited, dbg[15 * L + 11] = cs.t_sync, dbg[15 * L + 12] = cs.t_epi;
   if (warp == 0 && lane < 8) s_best[lane] = best, reinterpret_cast<int*>(s_best + 8)[lane] = best_i;
   cbar();
   if (tid == 0) {

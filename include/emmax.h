@@ -161,6 +161,15 @@ int emx_detokenize_actions(const int32_t* ids, int n, int vocab_size, int n_bins
 int emx_debug_stream(const void* src, long bytes, int rows, int seg, long row_stride, int stages, int evict_first, int grid,
                      int npairs, emx_stream_t stream);
 
+/* Dataflow skeleton of emx_decode_step (profiling aid): per CTA a static byte schedule of `n_phases` phases
+ * (`phase_stages[i]` ring stages of rows x seg bytes each) streamed `reps` times through a `stages`-deep ring, a grid barrier
+ * of protocol `barrier_variant` after every phase followed by a consumer stall of `stall_ns[i]`. `sync`: >= 32 * (2*148 + 1)
+ * zeroed uint32; `out`: 32 + 2*148 int64 (CTA 0: per-phase ns, per-barrier ns, total ns; per-CTA total ns and %smid). */
+int emx_debug_skeleton(const void* src, long region_bytes, int n_phases, const int* phase_stages, const int* stall_ns, int reps,
+                       int rows, int seg, long row_stride, int stages, int consume_cycles, int barrier_variant, int n_prod, int n_cons,
+                       const float* weight, int timers, int pf_stages, int pf_mode, int pf_pace_ns, void* sync, void* out,
+                       emx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

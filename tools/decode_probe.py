@@ -40,7 +40,7 @@ for conf in args.configs.split(","):
     p = eng._decode_params(0)
     p.l2_lookahead_kb, p.debug_flags = la, flags
     dbg = torch.zeros(15 * L + 16 + 2 * 148 + 8, dtype=torch.int64, device="cuda")
-    skews, late, tot, cw, pw = [], [], [], [], []
+    skews, late, tot, cw, pw, ts, te = [], [], [], [], [], [], []
     acc, tail = np.zeros(13), np.zeros(3)
     for s in range(args.warm + args.steps):
         p.dbg = dbg.data_ptr() if s >= args.warm else None
@@ -63,13 +63,16 @@ for conf in args.configs.split(","):
             late.append(arr[:, 0] - np.median(arr[:, 0]))
             cw.append(t[15 * L + 8])
             pw.append(t[15 * L + 9])
+            ts.append(t[15 * L + 11])
+            te.append(t[15 * L + 12])
+            pfb = t[15 * L + 13]
     n = args.steps
     a = acc / n / 1e3
     sk = np.array(skews).mean(0) / 1e3
     print(f"== lookahead {la} KiB, debug_flags {flags}: kernel {np.mean(tot):.3f} ms (min {np.min(tot):.3f}) | per layer {a.sum():.2f} us: "
           f"weights {a[0] + a[5] + a[8] + a[11]:.2f} (qkv {a[0]:.2f} o {a[5]:.2f} gateup {a[8]:.2f} down {a[11]:.2f}) barriers "
           f"{a[1] + a[3] + a[6] + a[9] + a[12]:.2f} attention {a[2]:.2f} loads {a[4] + a[7] + a[10]:.2f} | lm_head {tail[1] / n / 1e3:.1f} us | "
-          f"consumer wait {np.mean(cw) / clk * 1e3:.3f} ms | gate/up skew max-min {sk[0]:.2f} us, release {sk[2]:.2f} us", flush=True)  # fmt: skip
+          f"consumer wait {np.mean(cw) / clk * 1e3:.3f} ms, warp0 partial-sync {np.mean(ts) / clk * 1e3:.3f} ms, epilogue {np.mean(te) / clk * 1e3:.3f} ms, CTA0 prefetched {pfb / 1e6:.1f} MB of 89.3 | gate/up skew max-min {sk[0]:.2f} us, release {sk[2]:.2f} us", flush=True)  # fmt: skip
     if args.brief:
         continue
     print("per-layer phase means (us), CTA 0:")
