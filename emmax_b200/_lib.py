@@ -40,7 +40,7 @@ class DecodeParams(C.Structure):
         ("lm_head", C.c_void_p), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
         ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("block_table", C.c_void_p),
         ("page_size", C.c_int32), ("n_pages", C.c_int32), ("max_pages", C.c_int32),
-        ("x", C.c_void_p), ("qkv", C.c_void_p), ("attn", C.c_void_p), ("h", C.c_void_p),
+        ("x", C.c_void_p), ("xo", C.c_void_p), ("qkv", C.c_void_p), ("attn", C.c_void_p), ("h", C.c_void_p),
         ("part", C.c_void_p), ("argmax_part", C.c_void_p),
         ("out_tokens", C.c_void_p), ("logits_out", C.c_void_p),
         ("eos_token", C.c_int32), ("kv_splits", C.c_int32), ("state", C.c_void_p), ("dbg", C.c_void_p),

@@ -6,22 +6,27 @@
 // ~10^3 kernel launches per token, a full re-copy of the KV cache (DynamicCache torch.cat) and a host sync.
 //
 // B200 design (HBM-bound: 13.2 GB of bf16 weights per token):
-//   * grid = one CTA per SM (148), 8 consumer warps + 1 producer warp, launched cooperatively (co-residency guaranteed);
-//   * the producer warp walks the STATIC weight schedule of its CTA (layer -> qkv, o, gate/up, down -> 16-row group ->
-//     2048-column chunk) and two producer warps (alternating stages) keep a 3 x 64 KB shared-memory ring full with
-//     cp.async.bulk (TMA engine) copies, 16 x 4 KB per instruction, L2 evict-first. Measured on B200
-//     (profiles/r01_stream_probe.txt): bulk-copy instructions of one warp do not overlap each other (~1.3 us each
-//     regardless of size), so bytes per instruction x producer warps sets the streaming ceiling: 16 x 2 KB from one warp
-//     tops out at 3.8 TB/s, 16 x 4 KB reaches the 7.4 TB/s HBM read limit. Producers never wait for a grid barrier;
-//   * consumers: the 16 rows x 1024 columns of a stage are one A operand of mma.sync.m16n8k16 (bf16, fp32 accumulate);
-//     each warp owns a 128-column slice (ldmatrix from a 16-B padded, conflict-free row stride), the activation vector is
-//     the B operand straight from shared memory; per-warp partial row sums are combined once per row group. ~10x fewer
-//     issue slots per byte than a SIMT dot product, so the drain rate is far above the HBM feed rate;
-//   * RMSNorm is recomputed per CTA from the 8 KB residual vector (cheaper than a launch + barrier);
-//   * attention: (head, kv-split) items across CTAs, RoPE + KV append fused in, lane-per-key scores with all row loads in
-//     flight at once, last-arriving split combines;
-//   * phases are separated by a ticket grid barrier (release/acquire at gpu scope); cross-CTA activations are read
-//     with ld.global.cg (L1 bypass).
+//   * grid = one CTA per SM (148), 8 consumer warps + 2 producer warps + 1 L2-prefetch warp, launched cooperatively
+//     (co-residency is what makes the spin-waits below safe);
+//   * the producer warps walk the STATIC weight schedule of their CTA (layer -> qkv, o, gate/up, down -> 16-row group ->
+//     2048-column chunk) and keep a 3 x 64 KB shared-memory ring full with cp.async.bulk (TMA engine) copies, 16 x 4 KB per
+//     instruction, L2 evict-first. Producers never wait for anything but a free ring slot;
+//   * consumers: the 16 rows x 2048 columns of a stage are A operands of mma.sync.m16n8k16 (bf16, fp32 accumulate); each warp
+//     owns a 256-column slice (ldmatrix from a 16-B padded, conflict-free row stride), the activation vector is the B operand
+//     (one 16-B shared load per two k-steps thanks to a permuted layout), four independent accumulator chains; per-warp partial
+//     row sums are handed to warp 0 through named barriers. Measured: skipping the MMAs altogether changes the kernel time by
+//     3 % — the consumer is far from being the limit;
+//   * NO GRID BARRIERS. A 148-CTA barrier costs ~1.9 us on B200 even on an idle memory system (tools/skeleton_probe.py) and a
+//     decode step needs 160 of them. Instead every cross-CTA vector (qkv, attention output, residual stream, SwiGLU output,
+//     split-KV partials, argmax candidates) travels as 8-byte "LL" units {2 x bf16 | 32-bit tag} written with one 64-bit
+//     store and read with polling 64-bit loads: data and flag arrive atomically, so no fence, no atomic and no barrier is
+//     needed; a consumer waits exactly for the words it needs, ~one L2 round trip after they were produced. The tag encodes
+//     (launch epoch, layer), so stale words of the previous layer / token never match. Reuse of a buffer is safe without
+//     further synchronisation because every phase gathers a COMPLETE vector before it produces anything (see ll_gather);
+//   * RMSNorm is recomputed per CTA from the 8 KB residual vector (cheaper than an extra exchange);
+//   * attention: (head, kv-split) items across CTAs start as soon as THEIR q/k/v rows have arrived (no global wait), RoPE + KV
+//     append fused in, lane-per-key scores with all row loads in flight at once, split 0 of each head combines;
+//   * an L2-prefetch warp keeps HBM busy while the consumers stall (attention, exchanges) and the ring is full.
 // Rounding points mirror the torch-eager reference (bf16 after every Linear / norm / residual add / activation).
 #include "common.cuh"
 #include "emmax.h"
@@ -49,12 +54,13 @@ enum PhaseKind { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4
 
 struct PhaseDesc {
   const __nv_bfloat16* W;
-  int N, K;
+  int N, K, kind;
 };
 
 __device__ __forceinline__ PhaseDesc phase_desc(const emx_decode_params& p, int layer, int kind) {
   const long H = p.hidden, I = p.inter;
   PhaseDesc d;
+  d.kind = kind;
   switch (kind) {
     case PH_QKV: d.W = static_cast<const __nv_bfloat16*>(p.w_qkv) + layer * 3 * H * H, d.N = 3 * H, d.K = H; break;
     case PH_O: d.W = static_cast<const __nv_bfloat16*>(p.w_o) + layer * H * H, d.N = H, d.K = H; break;
@@ -65,43 +71,78 @@ __device__ __forceinline__ PhaseDesc phase_desc(const emx_decode_params& p, int 
   return d;
 }
 
-// rows of a phase owned by this CTA (row pairs are never split: gate/up interleave, packed bf16x2 stores)
-__device__ __forceinline__ void cta_rows(int N, int& r_begin, int& r_end) {
-  const long U = N / 2;
-  r_begin = static_cast<int>(U * blockIdx.x / gridDim.x) * 2;
-  r_end = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x) * 2;
+// rows of a phase owned by this CTA. Row pairs are never split (one LL unit = one row pair); gate/up rows come in groups of
+// four (two SwiGLU outputs = one LL unit).
+__device__ __forceinline__ void cta_rows(int N, int kind, int& r_begin, int& r_end) {
+  const int g = (kind == PH_GATEUP) ? 4 : 2;
+  const long U = N / g;
+  r_begin = static_cast<int>(U * blockIdx.x / gridDim.x) * g;
+  r_end = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x) * g;
 }
 
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(DEC_CTHREADS) : "memory"); }
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// ---- LL units: {32-bit payload | 32-bit tag} in one naturally aligned 64-bit word ---------------------------------------
+// A 64-bit scalar store / load is single-copy atomic, so a reader that sees the expected tag also sees the payload.
+__device__ __forceinline__ void ll_store(uint64_t* unit, uint32_t data, uint32_t tag) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(unit), "l"((static_cast<uint64_t>(tag) << 32) | data) : "memory");
+}
+__device__ __forceinline__ uint64_t ll_load(const uint64_t* unit) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(unit) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_add(uint32_t* p, uint32_t v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void ll_load2(const uint64_t* unit, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(unit) : "memory");
+}
+// spin until `unit` carries `tag` (check == false: profiling modes whose results are garbage anyway)
+__device__ __forceinline__ uint32_t ll_wait(const uint64_t* unit, uint32_t tag, bool check) {
+  uint64_t v = ll_load(unit);
+  uint32_t spins = 0;
+  while (check && static_cast<uint32_t>(v >> 32) != tag) {
+    v = ll_load(unit);
+    if (++spins > EMX_SPIN_LIMIT) __trap();
+  }
+  return static_cast<uint32_t>(v);
 }
 
-// ticket barrier over all CTAs (consumer threads only; the producer warps never synchronise with the grid).
-// One red.release.gpu per CTA after the CTA-local barrier (cumulativity publishes every consumer thread's writes), ONE poller
-// per CTA (relaxed loads, a single acquire fence at the end). Measured on B200 (profiles/r01_skeleton_probe.txt): ~1.9 us per
-// barrier even on an idle memory system; multi-counter, tree, flag-per-CTA and 8-pollers-per-CTA protocols are all slower.
-__device__ __forceinline__ void grid_sync(uint32_t* counter, uint32_t& target, bool skip = false) {
-  target += gridDim.x;
-  cbar();
-  if (threadIdx.x == 0) {
-    red_release_add(counter, 1u);
-    if (!skip) {  // (profiling mode: keep the ticket arithmetic consistent, do not wait)
-      uint32_t spins = 0, v;
-      do {
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        if (++spins > EMX_SPIN_LIMIT) __trap();
-      } while (static_cast<int32_t>(v - target) < 0);
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+// Gather a whole vector of `n_units` (even) LL units tagged `tag`: thread t takes the unit pairs t, t + 256, ...; all loads of a
+// chunk of MAXP pairs are in flight before the first tag is checked, pairs that are not there yet are re-polled.
+// sink(u, word) is called exactly once per unit (by the thread that fetched it).
+// WHY BUFFER REUSE IS SAFE: a CTA produces outputs of phase n+1 only after gathering ALL of phase n's vector, so when any
+// word of phase n+2 (or of the same phase one layer later) is overwritten, every CTA has long finished reading phase n.
+template <int MAXP, typename Sink>
+__device__ __forceinline__ void ll_gather(const uint64_t* buf, int n_units, uint32_t tag, bool check, Sink&& sink) {
+  const int n_pairs = n_units >> 1;
+  for (int base = 0; base < n_pairs; base += MAXP * DEC_CTHREADS) {
+    uint64_t a[MAXP], b[MAXP];
+    uint32_t pending = 0;
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int pr = base + i * DEC_CTHREADS + static_cast<int>(threadIdx.x);
+      if (pr < n_pairs) {
+        ll_load2(buf + 2 * pr, a[i], b[i]);
+        pending |= 1u << i;
+      }
+    }
+    uint32_t spins = 0;
+    while (pending) {
+#pragma unroll
+      for (int i = 0; i < MAXP; ++i) {
+        if (pending & (1u << i)) {
+          const int pr = base + i * DEC_CTHREADS + static_cast<int>(threadIdx.x);
+          if (!check || (static_cast<uint32_t>(a[i] >> 32) == tag && static_cast<uint32_t>(b[i] >> 32) == tag)) {
+            pending &= ~(1u << i);
+            sink(2 * pr, static_cast<uint32_t>(a[i]));
+            sink(2 * pr + 1, static_cast<uint32_t>(b[i]));
+          } else {
+            ll_load2(buf + 2 * pr, a[i], b[i]);
+          }
+        }
+      }
+      if (++spins > EMX_SPIN_LIMIT) __trap();
     }
   }
-  cbar();
 }
 
 __device__ __forceinline__ float cblock_sum(float v, float* red) {
@@ -125,58 +166,24 @@ __device__ __forceinline__ float cblock_max(float v, float* red) {
   return t;
 }
 
-__device__ __forceinline__ uint4 rms_apply(uint4 v, uint4 ww, float rs) {
-  const uint32_t u[4] = {v.x, v.y, v.z, v.w}, uw[4] = {ww.x, ww.y, ww.z, ww.w};
-  uint32_t r[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    r[j] = pack_bf16(bf16_lo(uw[j]) * bf16_round(bf16_lo(u[j]) * rs), bf16_hi(uw[j]) * bf16_round(bf16_hi(u[j]) * rs));
-  return make_uint4(r[0], r[1], r[2], r[3]);
+// Activation vector layout in shared memory: inside every block of 16 words (32 bf16) the 4 x 4 word matrix is transposed.
+// The two B fragments a lane needs for TWO consecutive k-steps of mma.m16n8k16 (words 8j+t, 8j+4+t, 8j+8+t, 8j+12+t,
+// t = lane%4) are then one 16-byte shared load. xs_pos maps a word index of the vector to its position.
+__device__ __forceinline__ int xs_pos(int w) { return (w & ~15) + 4 * (w & 3) + 2 * ((w >> 3) & 1) + ((w >> 2) & 1); }
+
+__device__ __forceinline__ float sumsq2(uint32_t w) {
+  const float a = bf16_lo(w), c = bf16_hi(w);
+  return a * a + c * c;
 }
-__device__ __forceinline__ float sumsq8(uint4 v) {
-  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-  float ss = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float a = bf16_lo(u[j]), c = bf16_hi(u[j]);
-    ss += a * a + c * c;
+
+// second half of LlamaRMSNorm over the raw vector already sitting in xs: xs = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))
+__device__ __forceinline__ void rmsnorm_finish(uint32_t* xs, const __nv_bfloat16* w, int H, float eps, float ss, float* red) {
+  const float rs = 1.0f / sqrtf(cblock_sum(ss, red) / H + eps);  // (its barriers also publish the raw words)
+  const uint32_t* ww = reinterpret_cast<const uint32_t*>(w);
+  for (int i = threadIdx.x; i < (H >> 1); i += DEC_CTHREADS) {
+    const uint32_t v = xs[xs_pos(i)], g = __ldg(ww + i);
+    xs[xs_pos(i)] = pack_bf16(bf16_lo(g) * bf16_round(bf16_lo(v) * rs), bf16_hi(g) * bf16_round(bf16_hi(v) * rs));
   }
-  return ss;
-}
-
-// Activation vector layout in shared memory: inside every block of 16 words (32 bf16) the 4 x 4 word matrix is transposed
-// (word q of 16-byte vector i lands at word (i/4)*16 + 4q + i%4). The two B fragments a lane needs for TWO consecutive
-// k-steps of mma.m16n8k16 (words 8j+t, 8j+4+t, 8j+8+t, 8j+12+t, t = lane%4) are then one 16-byte shared load.
-__device__ __forceinline__ void xs_store8(__nv_bfloat16* xs, int i, uint4 v) {
-  uint32_t* w = reinterpret_cast<uint32_t*>(xs) + (i >> 2) * 16 + (i & 3);
-  w[0] = v.x, w[4] = v.y, w[8] = v.z, w[12] = v.w;
-}
-
-// xs = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))  — LlamaRMSNorm, computed redundantly by every CTA.
-// x and w loads are issued together (one L2/HBM round trip on the critical path instead of two).
-__device__ __forceinline__ void load_rmsnorm(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* xs, int H, float eps,
-                                             float* red) {
-  const int nv = H >> 3;
-  if (nv <= 2 * DEC_CTHREADS) {
-    const int i0 = threadIdx.x, i1 = threadIdx.x + DEC_CTHREADS;
-    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, w0 = v0, w1 = v0;
-    if (i0 < nv) v0 = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i0), w0 = reinterpret_cast<const uint4*>(w)[i0];
-    if (i1 < nv) v1 = ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i1), w1 = reinterpret_cast<const uint4*>(w)[i1];
-    const float rs = 1.0f / sqrtf(cblock_sum(sumsq8(v0) + sumsq8(v1), red) / H + eps);
-    if (i0 < nv) xs_store8(xs, i0, rms_apply(v0, w0, rs));
-    if (i1 < nv) xs_store8(xs, i1, rms_apply(v1, w1, rs));
-  } else {
-    float ss = 0.f;
-    for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS) ss += sumsq8(ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i));
-    const float rs = 1.0f / sqrtf(cblock_sum(ss, red) / H + eps);
-    for (int i = threadIdx.x; i < nv; i += DEC_CTHREADS)
-      xs_store8(xs, i, rms_apply(ldg_cg_v4(reinterpret_cast<const uint4*>(x) + i), reinterpret_cast<const uint4*>(w)[i], rs));
-  }
-  cbar();
-}
-
-__device__ __forceinline__ void load_vec(const __nv_bfloat16* v, __nv_bfloat16* xs, int n) {
-  for (int i = threadIdx.x; i < (n >> 3); i += DEC_CTHREADS) xs_store8(xs, i, ldg_cg_v4(reinterpret_cast<const uint4*>(v) + i));
   cbar();
 }
 
@@ -192,7 +199,7 @@ struct SchedIter {
   PhaseDesc d;
   __device__ __forceinline__ void load_phase(const emx_decode_params& p) {
     d = phase_desc(p, layer, kind);
-    cta_rows(d.N, r, r_end);
+    cta_rows(d.N, kind, r, r_end);
   }
   __device__ __forceinline__ bool done() const { return kind == PH_END; }
   __device__ __forceinline__ void next_phase(const emx_decode_params& p) {
@@ -355,12 +362,13 @@ struct ConsumerState {
 __device__ __forceinline__ void part_arrive(uint32_t buf) { asm volatile("bar.arrive %0, %1;" ::"r"(2u + buf), "n"(DEC_CTHREADS) : "memory"); }
 __device__ __forceinline__ void part_sync(uint32_t buf) { asm volatile("bar.sync %0, %1;" ::"r"(2u + buf), "n"(DEC_CTHREADS) : "memory"); }
 
-// epi(row, v0, v1) is called for row pairs (row even) by threads 0..7 of warp 0, rows ascending per thread
+// epi(row, v0, v1, valid) is called for row pairs (row even) by lanes 0..7 of warp 0 (all eight, converged), rows ascending
+// per lane; valid == false marks lanes beyond the last row of a short group
 template <typename Epi>
 __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t* ring, uint64_t* full, uint64_t* empty, ConsumerState& cs,
                                               const __nv_bfloat16* xs, float* part, int warp, int lane, int debug_flags, Epi&& epi) {
   int r_begin, r_end;
-  cta_rows(d.N, r_begin, r_end);
+  cta_rows(d.N, d.kind, r_begin, r_end);
   // ldmatrix.x4 row address of this lane: matrices (rows 0-7 | 8-15) x (cols 0-7 | 8-15) of a 16x16 A tile
   const uint32_t a_lane_off = ((lane & 7) + ((lane >> 3) & 1) * 8) * DEC_ROWSTRIDE + (lane >> 4) * 16;
   const int kbeg = warp * DEC_KW;
@@ -421,11 +429,11 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
       const long long t1 = clock64();
       part_sync(buf);
       const long long t2 = clock64();
-      if (lane < 8 && 2 * lane < nrows) {
+      if (lane < 8) {
         float v0 = 0.f, v1 = 0.f;
 #pragma unroll
         for (int w = 0; w < DEC_CWARPS; ++w) v0 += pb[w * DEC_GROUP + 2 * lane], v1 += pb[w * DEC_GROUP + 2 * lane + 1];
-        epi(r0 + 2 * lane, v0, v1);
+        epi(r0 + 2 * lane, v0, v1, 2 * lane < nrows);
       }
       __syncwarp();
       cs.t_sync += t2 - t1, cs.t_epi += clock64() - t2;
@@ -462,41 +470,47 @@ __device__ __forceinline__ void prefetch_kv(const emx_decode_params& p, int laye
 // shared-memory carve-up of the (idle) activation area during attention, in floats
 constexpr int ATT_SQ = 0, ATT_SKNEW = 128, ATT_SVNEW = 256, ATT_SACC = 384 /*[8][128]*/, ATT_SSCORE = 384 + 1024;
 
-__device__ void attention_item(const emx_decode_params& p, int layer, int head, int split, int pos, float* sm, float* red) {
+__device__ void attention_item(const emx_decode_params& p, int layer, int head, int split, int pos, uint32_t tag, bool check, float* sm,
+                               float* red) {
   constexpr int HALF = DEC_HD / 2;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = pos + 1, S = p.kv_splits;
   const int k_begin = static_cast<int>(static_cast<long>(n) * split / S), k_end = static_cast<int>(static_cast<long>(n) * (split + 1) / S);
   const int nk = k_end - k_begin;
   float* sq = sm + ATT_SQ;          // [128] rotated q
   float* sknew = sm + ATT_SKNEW;    // [128] rotated new k
   float* svnew = sm + ATT_SVNEW;    // [128] new v
-  float* sacc = sm + ATT_SACC;      // [8][128] PV partials
+  float* sacc = sm + ATT_SACC;      // [8][128] PV partials, then [128] the reduced partial of this split
   float* sscore = sm + ATT_SSCORE;  // [nk] scores -> probabilities (host guarantees capacity)
   __nv_bfloat16* kc = static_cast<__nv_bfloat16*>(p.k_cache);
   __nv_bfloat16* vc = static_cast<__nv_bfloat16*>(p.v_cache);
-  const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(p.qkv);
+  const uint64_t* qkv = static_cast<const uint64_t*>(p.qkv);
   const int H = p.hidden;
   const bool owns_new = (k_end == n);  // the split that contains the token being decoded
 
-  if (tid < HALF) {
-    const int j = tid;
-    const float c = ld_bf16(static_cast<const __nv_bfloat16*>(p.cos_tab) + static_cast<long>(pos) * HALF + j);
-    const float s = ld_bf16(static_cast<const __nv_bfloat16*>(p.sin_tab) + static_cast<long>(pos) * HALF + j);
-    const float q1 = ldg_cg_bf16(qkv + head * DEC_HD + j), q2 = ldg_cg_bf16(qkv + head * DEC_HD + j + HALF);
-    float k1 = 0.f, k2 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (owns_new) {
-      k1 = ldg_cg_bf16(qkv + H + head * DEC_HD + j), k2 = ldg_cg_bf16(qkv + H + head * DEC_HD + j + HALF);
-      v1 = ldg_cg_bf16(qkv + 2 * H + head * DEC_HD + j), v2 = ldg_cg_bf16(qkv + 2 * H + head * DEC_HD + j + HALF);
-    }
-    sq[j] = bf16_round(bf16_round(q1 * c) + bf16_round(-q2 * s));
-    sq[j + HALF] = bf16_round(bf16_round(q2 * c) + bf16_round(q1 * s));
-    if (owns_new) {
-      const float r1 = bf16_round(bf16_round(k1 * c) + bf16_round(-k2 * s)), r2 = bf16_round(bf16_round(k2 * c) + bf16_round(k1 * s));
-      sknew[j] = r1, sknew[j + HALF] = r2, svnew[j] = v1, svnew[j + HALF] = v2;
+  // q / k / v rows of this head arrive as LL units (unit = 2 consecutive elements): warp 0 takes q, warp 1 k, warp 2 v.
+  // Lane t owns units t and t + 32, i.e. elements (2t, 2t+1) and their rotate_half partners (2t+64, 2t+65).
+  if (warp < 3 && (warp == 0 || owns_new)) {
+    const uint64_t* src = qkv + warp * (H / 2) + head * HALF;
+    const uint32_t lo = ll_wait(src + lane, tag, check), hi = ll_wait(src + lane + 32, tag, check);
+    const float x1a = bf16_lo(lo), x1b = bf16_hi(lo), x2a = bf16_lo(hi), x2b = bf16_hi(hi);
+    if (warp == 2) {
+      svnew[2 * lane] = x1a, svnew[2 * lane + 1] = x1b, svnew[2 * lane + HALF] = x2a, svnew[2 * lane + 1 + HALF] = x2b;
       const long dst = kv_row(p, layer, head, pos);
-      kc[dst + j] = __float2bfloat16_rn(r1), kc[dst + j + HALF] = __float2bfloat16_rn(r2);
-      vc[dst + j] = __float2bfloat16_rn(v1), vc[dst + j + HALF] = __float2bfloat16_rn(v2);
+      reinterpret_cast<uint32_t*>(vc + dst)[lane] = lo, reinterpret_cast<uint32_t*>(vc + dst + HALF)[lane] = hi;
+    } else {
+      const uint32_t cw = *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(p.cos_tab) + static_cast<long>(pos) * HALF + 2 * lane);
+      const uint32_t sw = *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(p.sin_tab) + static_cast<long>(pos) * HALF + 2 * lane);
+      const float ca = bf16_lo(cw), cb = bf16_hi(cw), sa = bf16_lo(sw), sb = bf16_hi(sw);
+      // x_embed = bf16(bf16(x*cos) + bf16(rotate_half(x)*sin)), rotate_half(x) = [-x2, x1]
+      const float r1a = bf16_round(bf16_round(x1a * ca) + bf16_round(-x2a * sa)), r1b = bf16_round(bf16_round(x1b * cb) + bf16_round(-x2b * sb));
+      const float r2a = bf16_round(bf16_round(x2a * ca) + bf16_round(x1a * sa)), r2b = bf16_round(bf16_round(x2b * cb) + bf16_round(x1b * sb));
+      float* dstv = (warp == 0) ? sq : sknew;
+      dstv[2 * lane] = r1a, dstv[2 * lane + 1] = r1b, dstv[2 * lane + HALF] = r2a, dstv[2 * lane + 1 + HALF] = r2b;
+      if (warp == 1) {
+        const long dst = kv_row(p, layer, head, pos);
+        reinterpret_cast<uint32_t*>(kc + dst)[lane] = pack_bf16(r1a, r1b), reinterpret_cast<uint32_t*>(kc + dst + HALF)[lane] = pack_bf16(r2a, r2b);
+      }
     }
   }
   cbar();
@@ -564,46 +578,46 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
   }
   *reinterpret_cast<float4*>(sacc + slice * 128 + 4 * quad) = make_float4(a[0], a[1], a[2], a[3]);
   cbar();
-  float* part = p.part + (static_cast<long>(head) * S + split) * (DEC_HD + 2);
+  float acc = 0.f;
   if (tid < DEC_HD) {
-    float t = 0.f;
 #pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2) t += sacc[s2 * 128 + tid];
-    part[2 + tid] = t;
+    for (int s2 = 0; s2 < 8; ++s2) acc += sacc[s2 * 128 + tid];
   }
-  if (tid == 0) part[0] = m, part[1] = l;
-
-  // last-arriving split of this head combines the partials
-  __shared__ uint32_t s_ticket;
-  __threadfence();
+  uint64_t* part = static_cast<uint64_t*>(p.part) + (static_cast<long>(head) * S + split) * (DEC_HD + 2);
+  if (split != 0) {
+    // hand the partial (m, l, acc[128]) to the combining CTA of this head as LL units
+    if (tid < DEC_HD) ll_store(part + 2 + tid, __float_as_uint(acc), tag);
+    if (tid == 0) ll_store(part, __float_as_uint(m), tag), ll_store(part + 1, __float_as_uint(l), tag);
+    cbar();
+    return;
+  }
+  // split 0 combines: own partial from shared memory, the others as they arrive
+  cbar();  // everyone has read sacc
+  if (tid < DEC_HD) sacc[tid] = acc;
   cbar();
-  if (tid == 0) s_ticket = atomicAdd(&p.state->head_ticket[head], 1u);
-  cbar();
-  if ((s_ticket + 1) % S == 0) {
-    __threadfence();
-    if (tid < DEC_HD) {
-      const float* ph = p.part + static_cast<long>(head) * S * (DEC_HD + 2);
-      float ms[8], ls[8], as[8];  // S <= 8
-      float M = -INFINITY;
+  if (tid < HALF) {
+    float ms[8], ls[8], a0[8], a1[8];  // S <= 8
+    ms[0] = m, ls[0] = l, a0[0] = sacc[2 * tid], a1[0] = sacc[2 * tid + 1];
+    float M = (l > 0.f) ? m : -INFINITY;
 #pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) {
-        ms[s2] = -INFINITY, ls[s2] = 0.f, as[s2] = 0.f;
-        if (s2 < S) {
-          ms[s2] = ldg_cg_f32(ph + s2 * (DEC_HD + 2)), ls[s2] = ldg_cg_f32(ph + s2 * (DEC_HD + 2) + 1);
-          as[s2] = ldg_cg_f32(ph + s2 * (DEC_HD + 2) + 2 + tid);
-          if (ls[s2] > 0.f) M = fmaxf(M, ms[s2]);
-        }
+    for (int s2 = 1; s2 < 8; ++s2) {
+      ms[s2] = -INFINITY, ls[s2] = 0.f, a0[s2] = a1[s2] = 0.f;
+      if (s2 < S) {
+        const uint64_t* ph = part + s2 * (DEC_HD + 2);
+        ms[s2] = __uint_as_float(ll_wait(ph, tag, check)), ls[s2] = __uint_as_float(ll_wait(ph + 1, tag, check));
+        a0[s2] = __uint_as_float(ll_wait(ph + 2 + 2 * tid, tag, check)), a1[s2] = __uint_as_float(ll_wait(ph + 3 + 2 * tid, tag, check));
+        if (ls[s2] > 0.f) M = fmaxf(M, ms[s2]);
       }
-      float num = 0.f, den = 0.f;
-#pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) {
-        if (s2 < S && ls[s2] > 0.f) {
-          const float w = __expf(ms[s2] - M);
-          num = fmaf(w, as[s2], num), den = fmaf(w, ls[s2], den);
-        }
-      }
-      static_cast<__nv_bfloat16*>(p.attn)[head * DEC_HD + tid] = __float2bfloat16_rn(num / den);
     }
+    float n0 = 0.f, n1 = 0.f, den = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2) {
+      if (s2 < S && ls[s2] > 0.f) {
+        const float w = __expf(ms[s2] - M);
+        n0 = fmaf(w, a0[s2], n0), n1 = fmaf(w, a1[s2], n1), den = fmaf(w, ls[s2], den);
+      }
+    }
+    ll_store(static_cast<uint64_t*>(p.attn) + head * HALF + tid, pack_bf16(n0 / den, n1 / den), tag);
   }
   cbar();
 }
@@ -612,16 +626,16 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
 __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_decode_params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ring = smem;
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + DEC_STAGES * DEC_STAGE_BYTES);
+  uint32_t* xs = reinterpret_cast<uint32_t*>(smem + DEC_STAGES * DEC_STAGE_BYTES);  // activation vector, bf16 pairs, xs_pos order
   float* misc = reinterpret_cast<float*>(smem + DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES);
   uint64_t* empty = full + DEC_STAGES;
   float* red = misc;                                 // [8]
-  int* s_state = reinterpret_cast<int*>(misc + 16);  // [4]
+  int* s_state = reinterpret_cast<int*>(misc + 16);  // [5]
   float* s_best = misc + 32;                         // [8] values + [8] indices
   float* part = misc + 64;                           // [DEC_PARTBUFS][8 warps][16 rows] partial row sums
   uint32_t* s_resid = reinterpret_cast<uint32_t*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP);  // [DEC_MAX_RESID] residual bf16 pairs of this CTA's rows
-  volatile uint32_t* s_groups_issued = reinterpret_cast<volatile uint32_t*>(misc + 24);  // producer 0 -> prefetch warp
+  volatile uint32_t* s_issued = reinterpret_cast<volatile uint32_t*>(misc + 24);  // [2] producers -> prefetch warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   emx_decode_state* st = p.state;
@@ -630,8 +644,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     s_state[1] = static_cast<int>(ldg_cg_u32(&st->pos));
     s_state[2] = static_cast<int>(ldg_cg_u32(&st->n_generated));
     s_state[3] = static_cast<int>(ldg_cg_u32(&st->finished));
-    *reinterpret_cast<volatile uint32_t*>(misc + 24) = 0;
-    *reinterpret_cast<volatile uint32_t*>(misc + 25) = 0;
+    s_state[4] = static_cast<int>(ldg_cg_u32(&st->epoch));
+    s_issued[0] = 0, s_issued[1] = 0;
     for (int s = 0; s < DEC_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], DEC_CWARPS);
@@ -646,11 +660,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   long long* dbg = (blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
   if (warp >= DEC_CWARPS + DEC_PWARPS) {
-    prefetch_loop(p, lane, s_groups_issued, full);
+    prefetch_loop(p, lane, s_issued, full);
     return;
   }
   if (warp >= DEC_CWARPS) {
-    producer_loop(p, ring, full, empty, lane, warp - DEC_CWARPS, s_groups_issued, dbg);
+    producer_loop(p, ring, full, empty, lane, warp - DEC_CWARPS, s_issued, dbg);
     return;
   }
 
@@ -661,101 +675,125 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     ++dbg_i;
   };
   ConsumerState cs{0, 0, 0, 0, 0};
-  // barrier tickets: every non-finished launch performs exactly (5 L + 1) grid syncs
-  const uint32_t n_sync = 5u * L + 1u;
-  uint32_t target = ldg_cg_u32(&st->epoch) * n_sync * gridDim.x;
+  // LL tags of this launch: tag0 + l for everything exchanged inside layer l (and for the residual stream ENTERING layer l);
+  // tag0 + L enters the final norm, tag0 + L + 1 carries the argmax candidates. Never 0, unique across launches.
+  const uint32_t tag0 = static_cast<uint32_t>(s_state[4]) * static_cast<uint32_t>(L + 2) + 1u;
+  const bool check = !(p.debug_flags & 1);
 
-  __nv_bfloat16* x = static_cast<__nv_bfloat16*>(p.x);
-  __nv_bfloat16* qkv = static_cast<__nv_bfloat16*>(p.qkv);
-  __nv_bfloat16* hbuf = static_cast<__nv_bfloat16*>(p.h);
-  const __nv_bfloat16* emb_row = static_cast<const __nv_bfloat16*>(p.embed) + static_cast<long>(token) * H;
+  uint64_t* xd = static_cast<uint64_t*>(p.x);      // residual stream after down_proj   [H/2] units
+  uint64_t* xo = static_cast<uint64_t*>(p.xo);     // residual stream after o_proj      [H/2]
+  uint64_t* qkv = static_cast<uint64_t*>(p.qkv);   // [3H/2]
+  uint64_t* attn = static_cast<uint64_t*>(p.attn); // [H/2]
+  uint64_t* hbuf = static_cast<uint64_t*>(p.h);    // [inter/2]
+  const uint32_t* emb_row = reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(p.embed) + static_cast<long>(token) * H);
+  int rb, re;
+  cta_rows(H, PH_O, rb, re);  // this CTA's rows of the two residual-producing phases (o_proj, down_proj)
+  const int rb2 = rb >> 1, re2 = re >> 1;
+
+  // raw residual vector -> xs (+ sum of squares, + this CTA's own rows kept for the residual add of the next epilogue)
+  float ss = 0.f;
+  auto take = [&](int u, uint32_t w) {
+    xs[xs_pos(u)] = w;
+    ss += sumsq2(w);
+    if (u >= rb2 && u < re2) s_resid[u - rb2] = w;
+  };
 
   for (int layer = 0; layer < L; ++layer) {
-    const __nv_bfloat16* resid_src = (layer == 0) ? emb_row : x;
-    // ---- P1: RMSNorm + QKV ----
+    const uint32_t tag = tag0 + layer;
+    // ---- P1: residual in, RMSNorm, QKV ----
     mark();
-    load_rmsnorm(resid_src, static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
+    ss = 0.f;
+    if (layer == 0) {
+      for (int u = tid; u < (H >> 1); u += DEC_CTHREADS) take(u, __ldg(emb_row + u));
+    } else {
+      ll_gather<4>(xd, H >> 1, tag, check, take);
+    }
+    rmsnorm_finish(xs, static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer) * H, H, p.rms_eps, ss, red);
     prefetch_kv(p, layer, pos);
-    consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags,
-                  [&](int row, float a0, float a1) { *reinterpret_cast<uint32_t*>(qkv + row) = pack_bf16(a0, a1); });
     mark();
-    grid_sync(&st->barrier, target, p.debug_flags & 1);
+    consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
+                  p.debug_flags, [&](int row, float a0, float a1, bool valid) {
+                    if (valid) ll_store(qkv + (row >> 1), pack_bf16(a0, a1), tag);
+                  });
     mark();
-    // ---- P2: RoPE + KV append + split-KV attention ----
+    // ---- P2: RoPE + KV append + split-KV attention (starts as soon as THIS head's q/k/v have arrived) ----
     for (int item = blockIdx.x; item < p.heads * p.kv_splits && !(p.debug_flags & 2); item += gridDim.x)
-      attention_item(p, layer, item / p.kv_splits, item % p.kv_splits, pos, reinterpret_cast<float*>(xs), red);
+      attention_item(p, layer, item / p.kv_splits, item % p.kv_splits, pos, tag, check, reinterpret_cast<float*>(xs), red);
     mark();
-    grid_sync(&st->barrier, target, p.debug_flags & 1);
+    // ---- P3: attention output in, o_proj + residual ----
+    ll_gather<4>(attn, H >> 1, tag, check, [&](int u, uint32_t w) { xs[xs_pos(u)] = w; });
+    cbar();
     mark();
-    // ---- P3: o_proj + residual ----
-    int rb, re;
-    cta_rows(H, rb, re);
-    if (tid < (re - rb) / 2) s_resid[tid] = ldg_cg_u32(resid_src + rb + 2 * tid);  // lands while the weights stream
-    load_vec(static_cast<const __nv_bfloat16*>(p.attn), xs, H);
+    consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
+                  p.debug_flags, [&](int row, float a0, float a1, bool valid) {
+                    if (!valid) return;
+                    const uint32_t r = s_resid[(row - rb) >> 1];
+                    ll_store(xo + (row >> 1), pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1)), tag);
+                  });
     mark();
-    consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags, [&](int row, float a0, float a1) {
-      const uint32_t r = s_resid[(row - rb) >> 1];
-      *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
-    });
+    // ---- P4: residual in, RMSNorm, gate/up + SwiGLU ----
+    ss = 0.f;
+    ll_gather<4>(xo, H >> 1, tag, check, take);
+    rmsnorm_finish(xs, static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H, H, p.rms_eps, ss, red);
     mark();
-    grid_sync(&st->barrier, target, p.debug_flags & 1);
+    consume_phase(phase_desc(p, layer, PH_GATEUP), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
+                  p.debug_flags, [&](int row, float g, float u, bool valid) {
+                    // lanes 0..7 (converged): lane i holds (gate, up) of output row/2; two outputs make one LL unit
+                    const float hv = bf16_round(bf16_round(silu(bf16_round(g))) * bf16_round(u));
+                    const float hn = __shfl_down_sync(0xffu, hv, 1);
+                    if (valid && !(lane & 1)) ll_store(hbuf + (row >> 2), pack_bf16(hv, hn), tag);
+                  });
     mark();
-    // ---- P4: RMSNorm + gate/up + SwiGLU ----
-    load_rmsnorm(x, static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H, xs, H, p.rms_eps, red);
+    // ---- P5: SwiGLU output in, down_proj + residual ----
+    ll_gather<11>(hbuf, p.inter >> 1, tag, check, [&](int u, uint32_t w) { xs[xs_pos(u)] = w; });
+    cbar();
     mark();
-    consume_phase(phase_desc(p, layer, PH_GATEUP), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags, [&](int row, float g, float u) {
-      hbuf[row >> 1] = __float2bfloat16_rn(bf16_round(silu(bf16_round(g))) * bf16_round(u));
-    });
+    consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
+                  p.debug_flags, [&](int row, float a0, float a1, bool valid) {
+                    if (!valid) return;
+                    const uint32_t r = s_resid[(row - rb) >> 1];
+                    ll_store(xd + (row >> 1), pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1)), tag + 1);
+                  });
     mark();
-    if (p.dbg && layer == 1 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 16 + 2 * blockIdx.x] = global_ns();
-    grid_sync(&st->barrier, target, p.debug_flags & 1);
-    if (p.dbg && layer == 1 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 17 + 2 * blockIdx.x] = global_ns();
-    mark();
-    // ---- P5: down_proj + residual ----
-    if (tid < (re - rb) / 2) s_resid[tid] = ldg_cg_u32(x + rb + 2 * tid);
-    load_vec(hbuf, xs, p.inter);
-    mark();
-    consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags, [&](int row, float a0, float a1) {
-      const uint32_t r = s_resid[(row - rb) >> 1];
-      *reinterpret_cast<uint32_t*>(x + row) = pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1));
-    });
-    mark();
-    grid_sync(&st->barrier, target, p.debug_flags & 1);
+    if (p.dbg && layer == 1 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 16 + blockIdx.x] = global_ns();
   }
-  mark();
 
   // ---- final norm + lm_head + greedy argmax ----
-  load_rmsnorm(x, static_cast<const __nv_bfloat16*>(p.final_norm), xs, H, p.rms_eps, red);
+  mark();
+  ss = 0.f;
+  ll_gather<4>(xd, H >> 1, tag0 + L, check, take);
+  rmsnorm_finish(xs, static_cast<const __nv_bfloat16*>(p.final_norm), H, p.rms_eps, ss, red);
   mark();
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  consume_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, cs, xs, part, warp, lane, p.debug_flags, [&](int row, float a0, float a1) {
-    const float v0 = bf16_round(a0), v1 = bf16_round(a1);
-    if (p.logits_out) p.logits_out[row] = v0, p.logits_out[row + 1] = v1;
-    if (v0 > best) best = v0, best_i = row;  // rows ascend per thread: strict '>' keeps the lowest index
-    if (v1 > best) best = v1, best_i = row + 1;
-  });
+  consume_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane, p.debug_flags,
+                [&](int row, float a0, float a1, bool valid) {
+                  if (!valid) return;
+                  const float v0 = bf16_round(a0), v1 = bf16_round(a1);
+                  if (p.logits_out) p.logits_out[row] = v0, p.logits_out[row + 1] = v1;
+                  if (v0 > best) best = v0, best_i = row;  // rows ascend per thread: strict '>' keeps the lowest index
+                  if (v1 > best) best = v1, best_i = row + 1;
+                });
   mark();
   if (dbg && tid == 0) dbg[15 * L + 8] = cs.waited, dbg[15 * L + 11] = cs.t_sync, dbg[15 * L + 12] = cs.t_epi;
   if (warp == 0 && lane < 8) s_best[lane] = best, reinterpret_cast<int*>(s_best + 8)[lane] = best_i;
   cbar();
+  uint64_t* cand = static_cast<uint64_t*>(p.argmax_part);  // [grid][2] LL units: value bits, index
   if (tid == 0) {
     for (int w = 1; w < 8; ++w) {
       const float v = s_best[w];
       const int i = reinterpret_cast<int*>(s_best + 8)[w];
       if (v > best || (v == best && i < best_i)) best = v, best_i = i;
     }
-    p.argmax_part[2 * blockIdx.x] = best;
-    reinterpret_cast<int*>(p.argmax_part)[2 * blockIdx.x + 1] = best_i;
+    ll_store(cand + 2 * blockIdx.x, __float_as_uint(best), tag0 + L + 1);
+    ll_store(cand + 2 * blockIdx.x + 1, static_cast<uint32_t>(best_i), tag0 + L + 1);
   }
-  grid_sync(&st->barrier, target, p.debug_flags & 1);
-  mark();
   if (blockIdx.x == 0 && warp == 0) {
     float b = -INFINITY;
     int bi = 0x7fffffff;
     for (int c = lane; c < static_cast<int>(gridDim.x); c += 32) {
-      const float v = ldg_cg_f32(p.argmax_part + 2 * c);
-      const int i = static_cast<int>(ldg_cg_u32(p.argmax_part + 2 * c + 1));
+      const float v = __uint_as_float(ll_wait(cand + 2 * c, tag0 + L + 1, check));
+      const int i = static_cast<int>(ll_wait(cand + 2 * c + 1, tag0 + L + 1, check));
       if (v > b || (v == b && i < bi)) b = v, bi = i;
     }
 #pragma unroll
@@ -770,8 +808,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
       st->pos = pos + 1;
       st->n_generated = n_gen + 1;
       if (p.eos_token >= 0 && bi == p.eos_token) st->finished = 1;
-      st->epoch = st->epoch + 1;
+      st->epoch = static_cast<uint32_t>(s_state[4]) + 1u;
     }
+    mark();
   }
 }
 
@@ -784,9 +823,10 @@ extern "C" int emx_decode_step(const emx_decode_params* params, cudaStream_t str
   const emx_decode_params& p = *params;
   EMX_REQUIRE(p.head_dim == DEC_HD, "emx_decode_step: head_dim %d not supported (128)", p.head_dim);
   EMX_REQUIRE(p.hidden % 16 == 0 && p.inter % 16 == 0 && p.vocab % 2 == 0, "emx_decode_step: hidden/inter must be multiples of 16, vocab even");
+  EMX_REQUIRE(p.x && p.xo && p.qkv && p.attn && p.h && p.part && p.argmax_part && p.state, "emx_decode_step: null scratch pointer");
   EMX_REQUIRE(p.inter * 2 <= DEC_XS_BYTES && p.hidden * 2 <= DEC_XS_BYTES, "emx_decode_step: activation vector exceeds %d bytes", DEC_XS_BYTES);
   EMX_REQUIRE(p.kv_splits >= 1 && p.kv_splits <= 8 && (p.kv_splits & (p.kv_splits - 1)) == 0, "emx_decode_step: kv_splits must be 1, 2, 4 or 8");
-  EMX_REQUIRE(p.heads <= 64, "emx_decode_step: at most 64 heads");
+  EMX_REQUIRE(p.heads * p.kv_splits <= kNumSMs, "emx_decode_step: heads x kv_splits must not exceed the grid (one attention item per CTA)");
   EMX_REQUIRE(p.hidden / 2 / kNumSMs + 2 <= DEC_MAX_RESID, "emx_decode_step: hidden too large for the residual staging buffer");
   const int max_keys_per_split = DEC_XS_BYTES / 4 - ATT_SSCORE;
   EMX_REQUIRE((static_cast<long>(p.max_pages) * p.page_size + p.kv_splits - 1) / p.kv_splits + 1 <= max_keys_per_split,

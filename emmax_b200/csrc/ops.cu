@@ -290,7 +290,7 @@ __global__ void detok_kernel(const int32_t* __restrict__ ids, int n, int vocab, 
 using namespace emx;
 
 extern "C" const char* emx_last_error(void) { return g_err; }
-extern "C" int emx_abi_version(void) { return 1; }
+extern "C" int emx_abi_version(void) { return 2; }
 extern "C" const char* emx_arch(void) { return "sm_100a"; }
 
 #define BF(p) static_cast<const __nv_bfloat16*>(p)

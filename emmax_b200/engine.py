@@ -133,12 +133,12 @@ class Engine:
         self.layer_cache_bytes = self.k_cache[0].numel() * 2
         # decode scratch
         grid = _lib.load().emx_decode_grid()
-        self.d_x = torch.zeros(H, dtype=BF16, device=dev)
-        self.d_qkv = torch.zeros(3 * H, dtype=BF16, device=dev)
-        self.d_attn = torch.zeros(H, dtype=BF16, device=dev)
-        self.d_h = torch.zeros(I, dtype=BF16, device=dev)
-        self.d_part = torch.zeros(t.num_attention_heads * self.kv_splits * (t.head_dim + 2), dtype=torch.float32, device=dev)
-        self.d_argmax = torch.zeros(2 * grid, dtype=torch.float32, device=dev)
+        # LL exchange buffers of the decode kernel: 8-byte units {payload | tag}, zeroed once (tag 0 is never valid)
+        ll = lambda n: torch.zeros(n, dtype=torch.int64, device=dev)  # noqa: E731
+        self.d_x, self.d_xo, self.d_attn = ll(H // 2), ll(H // 2), ll(H // 2)
+        self.d_qkv, self.d_h = ll(3 * H // 2), ll(I // 2)
+        self.d_part = ll(t.num_attention_heads * self.kv_splits * (t.head_dim + 2))
+        self.d_argmax = ll(2 * grid)
         self.d_state = torch.zeros(C.sizeof(DecodeState) // 4, dtype=torch.int32, device=dev)
         self.max_new = self.max_context
         self.d_out_tokens = torch.zeros(self.max_new, dtype=torch.int32, device=dev)
@@ -285,7 +285,7 @@ class Engine:
         p.k_cache, p.v_cache = ptr(self.k_cache), ptr(self.v_cache)
         p.block_table = self.block_table[b].data_ptr()
         p.page_size, p.n_pages, p.max_pages = self.PAGE, self.n_pages, self.pages_per_seq
-        p.x, p.qkv, p.attn, p.h = ptr(self.d_x), ptr(self.d_qkv), ptr(self.d_attn), ptr(self.d_h)
+        p.x, p.xo, p.qkv, p.attn, p.h = ptr(self.d_x), ptr(self.d_xo), ptr(self.d_qkv), ptr(self.d_attn), ptr(self.d_h)
         p.part, p.argmax_part = ptr(self.d_part), ptr(self.d_argmax)
         p.out_tokens, p.logits_out = ptr(self.d_out_tokens), None
         p.eos_token, p.kv_splits, p.state = -1, self.kv_splits, ptr(self.d_state)

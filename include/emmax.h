@@ -86,7 +86,8 @@ int emx_lmhead_argmax(const void* W, int ldw, const void* x, int N, int K, float
  * ONE launch = one new token for one sequence: embedding gather, 32 x (RMSNorm + QKV GEMV + RoPE + paged-KV append +
  * split-KV attention + o_proj + residual + RMSNorm + gate/up GEMV + SwiGLU + down GEMV + residual), final norm,
  * lm_head GEMV + greedy argmax, all inside one persistent kernel (1 CTA/SM) that streams the 13.2 GB of weights through
- * a bulk-async (TMA) shared-memory ring and separates phases with grid barriers.
+ * a bulk-async (TMA) shared-memory ring. There are no grid barriers: CTAs exchange activation vectors as 8-byte
+ * "LL units" {2 x bf16 payload | 32-bit tag} (single 64-bit stores, polling 64-bit loads; tag = launch epoch x layer).
  * Replaces the cached branch of PrismaticForConditionalGeneration.forward (modeling_prismatic.py:325-341) + one
  * iteration of GenerationMixin's greedy loop (called at modeling_prismatic.py:519). */
 typedef struct emx_decode_state {
@@ -95,10 +96,10 @@ typedef struct emx_decode_state {
   int32_t n_generated;
   int32_t finished;  /* set when EOS was produced; later launches return immediately */
   /* kernel-private, zero once at allocation and never touched by the host afterwards: */
-  uint32_t barrier;  /* grid-barrier ticket counter (monotonic) */
-  uint32_t epoch;    /* completed launches (monotonic); barrier tickets are derived from it */
+  uint32_t barrier;  /* unused since ABI 2 (was: grid-barrier ticket counter) */
+  uint32_t epoch;    /* completed launches (monotonic); the LL tags are derived from it */
   uint32_t pad0_[2];
-  uint32_t head_ticket[64]; /* per-head split-KV arrival counters */
+  uint32_t head_ticket[64]; /* unused since ABI 2 */
 } emx_decode_state;
 
 typedef struct emx_decode_params {
@@ -121,26 +122,28 @@ typedef struct emx_decode_params {
   void* v_cache;
   const int32_t* block_table; /* [max_pages] page ids of this sequence */
   int32_t page_size, n_pages, max_pages;
-  /* scratch (device) */
-  void* x;        /* [hidden] bf16 residual stream */
-  void* qkv;      /* [3*hidden] bf16 */
-  void* attn;     /* [hidden] bf16 */
-  void* h;        /* [inter] bf16 */
-  float* part;    /* [heads][kv_splits][head_dim + 2] fp32 split-KV partials */
-  float* argmax_part; /* [grid][2] */
+  /* exchange buffers (device, 8-byte aligned, zeroed once at allocation, then owned by the kernel). One LL unit = 8 bytes. */
+  void* x;        /* [hidden/2] units: residual stream after down_proj */
+  void* xo;       /* [hidden/2] units: residual stream after o_proj */
+  void* qkv;      /* [3*hidden/2] units */
+  void* attn;     /* [hidden/2] units */
+  void* h;        /* [inter/2] units: SwiGLU output */
+  void* part;     /* [heads][kv_splits][head_dim + 2] units (fp32 payload): split-KV partials */
+  void* argmax_part; /* [grid][2] units: per-CTA argmax candidate (value bits, index) */
   /* outputs */
   int32_t* out_tokens;  /* out_tokens[n_generated] = new token */
   float* logits_out;    /* optional [vocab] fp32 (bf16-rounded values), for parity tests */
   int32_t eos_token;    /* -1 disables EOS handling */
   int32_t kv_splits;
   emx_decode_state* state;
-  /* optional profiling buffer (device, >= 15*layers + 16 + 2*grid int64): CTA 0 stores %globaltimer at every phase boundary,
+  /* optional profiling buffer (device, >= 15*layers + 16 + grid int64): CTA 0 stores %globaltimer at every phase boundary,
    * then [15*layers + 8 ..] = cycles warp 0 waited for weights / cycles the producer waited for a free ring slot */
   int64_t* dbg;
   /* per-CTA look-ahead (KiB) of cp.async.bulk.prefetch.L2 beyond the shared-memory ring; 0 disables (148 CTAs x 256 KiB
    * = 37 MB of the 126 MB L2 keeps HBM streaming through grid barriers and the attention phase) */
   int32_t l2_lookahead_kb;
-  /* profiling only (results become garbage): 1 = skip grid barriers, 2 = skip attention, 4 = no L2 evict-first hint */
+  /* profiling only (results become garbage): 1 = do not wait for LL tags, 2 = skip attention (needs 1), 4 = no L2 evict-first
+   * hint, 64 = skip the MMAs, bits 8.. = prefetch pace in 10 ns per 64 KB (default 700 ns) */
   int32_t debug_flags;
 } emx_decode_params;
 

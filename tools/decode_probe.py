@@ -1,7 +1,7 @@
 """Phase-level timing of the persistent decode kernel (CTA 0's view, %globaltimer) + ring wait counters, swept over
 (L2 look-ahead KiB, debug_flags) configurations with ONE model build.
 Usage (GPU box): python tools/decode_probe.py [--steps 16] [--configs 0:0,256:0,256:16] [--ctx 296] [--brief]
-debug_flags: 1 skip grid barriers, 2 skip attention, 4 no evict-first hint, 16 bulk (TMA) L2 prefetch, 32 ld.L2::256B prefetch."""
+debug_flags: 1 do not wait for LL tags, 2 skip attention (with 1), 4 no evict-first hint, 64 skip MMAs, bits 8.. prefetch pace (10 ns / 64 KB)."""
 import argparse
 import ctypes as C
 import os
@@ -31,8 +31,7 @@ ids = torch.tensor([[1] + np.random.default_rng(1234).integers(3, 31744, 39).tol
 pv = torch.randn(1, 6, 224, 224, device="cuda").to(torch.bfloat16)
 eng.generate(ids, pv, 2 + args.advance, eos_token_id=None)
 lib = _lib.load()
-names = ["P1 rmsnorm+qkv", "barrier", "attention", "barrier", "load attn", "o_proj", "barrier", "rmsnorm2", "gate/up", "barrier",
-         "load h", "down", "barrier"]  # fmt: skip
+names = ["x in + rmsnorm1", "qkv", "attention", "attn in", "o_proj", "x in + rmsnorm2", "gate/up", "h in", "down"]
 clk = 1.965e9
 
 for conf in args.configs.split(","):
@@ -41,7 +40,7 @@ for conf in args.configs.split(","):
     p.l2_lookahead_kb, p.debug_flags = la, flags
     dbg = torch.zeros(15 * L + 16 + 2 * 148 + 8, dtype=torch.int64, device="cuda")
     skews, late, tot, cw, pw, ts, te = [], [], [], [], [], [], []
-    acc, tail = np.zeros(13), np.zeros(3)
+    acc, tail = np.zeros(9), np.zeros(3)
     for s in range(args.warm + args.steps):
         p.dbg = dbg.data_ptr() if s >= args.warm else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -51,16 +50,15 @@ for conf in args.configs.split(","):
         torch.cuda.synchronize()
         if s >= args.warm:
             t = dbg.cpu().numpy()
-            marks = t[: 13 * L + 4].astype(np.float64)
-            iv = np.array([[marks[13 * l + k + 1] - marks[13 * l + k] for k in range(13)] for l in range(L)])
+            marks = t[: 10 * L + 4].astype(np.float64)
+            iv = np.array([[marks[10 * l + k + 1] - marks[10 * l + k] for k in range(9)] for l in range(L)])
             acc += iv.mean(0)
-            base = 13 * L
+            base = 10 * L
             tail += np.array([marks[base + 1] - marks[base], marks[base + 2] - marks[base + 1], marks[base + 3] - marks[base + 2]])
             tot.append(e0.elapsed_time(e1))
-            arr = t[15 * L + 16 : 15 * L + 16 + 296].reshape(148, 2).astype(np.float64)
-            skews.append((arr[:, 0].max() - arr[:, 0].min(), arr[:, 0].max() - np.median(arr[:, 0]), (arr[:, 1] - arr[:, 0].max()).mean(),
-                          (arr[:, 1] - arr[:, 0].max()).max()))  # fmt: skip
-            late.append(arr[:, 0] - np.median(arr[:, 0]))
+            arr = t[15 * L + 16 : 15 * L + 16 + 148].astype(np.float64)  # end of layer 1 on every CTA
+            skews.append((arr.max() - arr.min(), arr.max() - np.median(arr)))
+            late.append(arr - np.median(arr))
             cw.append(t[15 * L + 8])
             pw.append(t[15 * L + 9])
             ts.append(t[15 * L + 11])
@@ -70,9 +68,9 @@ for conf in args.configs.split(","):
     a = acc / n / 1e3
     sk = np.array(skews).mean(0) / 1e3
     print(f"== lookahead {la} KiB, debug_flags {flags}: kernel {np.mean(tot):.3f} ms (min {np.min(tot):.3f}) | per layer {a.sum():.2f} us: "
-          f"weights {a[0] + a[5] + a[8] + a[11]:.2f} (qkv {a[0]:.2f} o {a[5]:.2f} gateup {a[8]:.2f} down {a[11]:.2f}) barriers "
-          f"{a[1] + a[3] + a[6] + a[9] + a[12]:.2f} attention {a[2]:.2f} loads {a[4] + a[7] + a[10]:.2f} | lm_head {tail[1] / n / 1e3:.1f} us | "
-          f"consumer wait {np.mean(cw) / clk * 1e3:.3f} ms, warp0 partial-sync {np.mean(ts) / clk * 1e3:.3f} ms, epilogue {np.mean(te) / clk * 1e3:.3f} ms, CTA0 prefetched {pfb / 1e6:.1f} MB of 89.3 | gate/up skew max-min {sk[0]:.2f} us, release {sk[2]:.2f} us", flush=True)  # fmt: skip
+          f"weights {a[1] + a[4] + a[6] + a[8]:.2f} (qkv {a[1]:.2f} o {a[4]:.2f} gateup {a[6]:.2f} down {a[8]:.2f}) exchanges "
+          f"{a[0] + a[3] + a[5] + a[7]:.2f} (x {a[0]:.2f} attn {a[3]:.2f} xo {a[5]:.2f} h {a[7]:.2f}) attention {a[2]:.2f} | lm_head {tail[1] / n / 1e3:.1f} us | "
+          f"consumer wait {np.mean(cw) / clk * 1e3:.3f} ms, warp0 partial-sync {np.mean(ts) / clk * 1e3:.3f} ms, epilogue {np.mean(te) / clk * 1e3:.3f} ms, CTA0 prefetched {pfb / 1e6:.1f} MB of 89.3 | layer-1 end skew max-min {sk[0]:.2f} us", flush=True)  # fmt: skip
     if args.brief:
         continue
     print("per-layer phase means (us), CTA 0:")
@@ -80,7 +78,7 @@ for conf in args.configs.split(","):
         print(f"  {nm:18s} {v:8.2f}")
     print("tail (us): final rmsnorm %.2f, lm_head %.2f, final barrier %.2f" % tuple(tail / n / 1e3))
     print(f"consumer warp0 waited on weights: {np.mean(cw) / clk * 1e3:.3f} ms/step; producer waited on free slots: {np.mean(pw) / clk * 1e3:.3f} ms/step")
-    print("gate/up phase end across CTAs (layer 1): max-min %.2f us, max-median %.2f us; release after last arrival: mean %.2f us, max %.2f us" % tuple(sk))
+    print("end of layer 1 across CTAs: max-min %.2f us, max-median %.2f us" % tuple(sk))
     lt = np.array(late) / 1e3  # [steps, 148] us relative to the median CTA
     m, sdv = lt.mean(0), lt.std(0)
     order = np.argsort(-m)
