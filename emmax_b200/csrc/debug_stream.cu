@@ -11,16 +11,18 @@ __global__ void __launch_bounds__(512, 1) stream_probe_kernel(const uint8_t* __r
   extern __shared__ __align__(128) uint8_t smem_all[];
   const int stage_bytes = rows * seg;
   const int pair = threadIdx.x >> 6;
+  const bool extra = pair >= npairs;  // padding warps (thread-count experiments): take part in the barrier, then leave
   const long ring_bytes = static_cast<long>(stages) * stage_bytes;
   uint8_t* smem = smem_all + pair * ring_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_all + npairs * ring_bytes) + pair * 2 * stages;
   uint64_t* empty = full + stages;
   const int warp = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
-  if ((threadIdx.x & 63) == 0) {
+  if ((threadIdx.x & 63) == 0 && !extra) {
     for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
+  if (extra) return;
   // a "block" = rows x row_stride bytes of source, streamed as row_stride/seg stages of rows x seg
   const uint8_t* base = src + (static_cast<long>(blockIdx.x) * npairs + pair) * bytes_per_pair;
   const long block_bytes = static_cast<long>(rows) * row_stride;
@@ -55,14 +57,15 @@ __global__ void __launch_bounds__(512, 1) stream_probe_kernel(const uint8_t* __r
 }  // namespace emx
 
 extern "C" int emx_debug_stream(const void* src, long bytes, int rows, int seg, long row_stride, int stages, int evict_first, int grid,
-                                int npairs, cudaStream_t stream) {
+                                int npairs_and_pad, cudaStream_t stream) {
   using namespace emx;
+  const int npairs = npairs_and_pad & 15, pad_warps = npairs_and_pad >> 4;
   const int smem = npairs * (stages * rows * seg + 2 * stages * 8) + 128;
   EMX_REQUIRE(smem <= 227 * 1024 && seg % 16 == 0 && row_stride % seg == 0 && npairs >= 1 && npairs <= 8, "emx_debug_stream: bad geometry");
   EMX_CHECK_CUDA(cudaFuncSetAttribute(stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long block = static_cast<long>(rows) * row_stride;
   const long per_pair = bytes / grid / npairs / block * block;
-  stream_probe_kernel<<<grid, 64 * npairs, smem, stream>>>(static_cast<const uint8_t*>(src), per_pair, rows, seg, row_stride, stages,
+  stream_probe_kernel<<<grid, 64 * npairs + 32 * pad_warps, smem, stream>>>(static_cast<const uint8_t*>(src), per_pair, rows, seg, row_stride, stages,
                                                            evict_first, npairs);
   EMX_CHECK_CUDA(cudaGetLastError());
   return static_cast<int>(per_pair / block);  // blocks per producer/consumer pair actually streamed (>= 0)
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(352, 1) skeleton_kernel(const SkelParams p) {
 
 extern "C" int emx_debug_skeleton(const void* src, long region_bytes, int n_phases, const int* phase_stages, const int* stall_ns, int reps,
                                   int rows, int seg, long row_stride, int stages, int consume_cycles, int barrier_variant, int n_prod,
-                                  int n_cons, const float* weight, int timers, int pf_stages, int pf_mode, int pf_pace_ns, void* sync, void* out, cudaStream_t stream) {
+                                  int n_cons, const float* weight, int timers, int pf_stages, int pf_mode, int pf_pace_ns, int launch_mode, void* sync, void* out, cudaStream_t stream) {
   using namespace emx;
   EMX_REQUIRE(n_phases >= 1 && n_phases <= 8 && seg % 16 == 0 && row_stride % seg == 0, "emx_debug_skeleton: bad arguments");
   SkelParams p;
@@ -388,6 +391,11 @@ extern "C" int emx_debug_skeleton(const void* src, long region_bytes, int n_phas
   EMX_REQUIRE(smem <= 227 * 1024, "emx_debug_skeleton: ring of %d bytes does not fit", smem);
   EMX_CHECK_CUDA(cudaFuncSetAttribute(skeleton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   void* args[] = {&p};
-  EMX_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(skeleton_kernel), dim3(kNumSMs), dim3(352), args, smem, stream));
+  if (launch_mode & 1) {  // plain launch (only safe for barrier_variant 0 ... the grid is co-resident anyway at 1 CTA/SM)
+    skeleton_kernel<<<kNumSMs, 352, smem, stream>>>(p);
+    EMX_CHECK_CUDA(cudaGetLastError());
+  } else {
+    EMX_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(skeleton_kernel), dim3(kNumSMs), dim3(352), args, smem, stream));
+  }
   return 0;
 }

@@ -47,7 +47,8 @@ constexpr int DEC_MAX_RESID = 192;               // residual pairs of one CTA st
 constexpr int DEC_XS_BYTES = 22528;                         // activation vector (bf16), up to 11264 elements
 constexpr int DEC_MISC_BYTES = 4096;
 constexpr int DEC_PARTBUFS = 4;                  // partial-sum buffers (a warp is never more than 3 ring stages ahead of warp 0)
-constexpr int DEC_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128;
+constexpr int DEC_LN_BYTES = 8192;              // norm weights of the NEXT RMSNorm, fetched asynchronously a phase ahead (hidden <= 4096)
+constexpr int DEC_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128 + DEC_LN_BYTES;
 constexpr int DEC_HD = 128;  // head_dim supported by the decode kernel (Llama-2)
 
 enum PhaseKind { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4, PH_END = 5 };
@@ -176,13 +177,75 @@ __device__ __forceinline__ float sumsq2(uint32_t w) {
   return a * a + c * c;
 }
 
-// second half of LlamaRMSNorm over the raw vector already sitting in xs: xs = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))
-__device__ __forceinline__ void rmsnorm_finish(uint32_t* xs, const __nv_bfloat16* w, int H, float eps, float ss, float* red) {
-  const float rs = 1.0f / sqrtf(cblock_sum(ss, red) / H + eps);  // (its barriers also publish the raw words)
-  const uint32_t* ww = reinterpret_cast<const uint32_t*>(w);
-  for (int i = threadIdx.x; i < (H >> 1); i += DEC_CTHREADS) {
-    const uint32_t v = xs[xs_pos(i)], g = __ldg(ww + i);
-    xs[xs_pos(i)] = pack_bf16(bf16_lo(g) * bf16_round(bf16_lo(v) * rs), bf16_hi(g) * bf16_round(bf16_hi(v) * rs));
+// The 8 KB norm-weight vectors are streamed once per token, so they are never L2-resident when they are needed, and an
+// L2 prefetch hint is dropped while HBM is saturated. Each thread therefore copies exactly the words IT will need for the
+// next RMSNorm into shared memory with cp.async a whole phase ahead (no cross-thread hand-off: the thread that copied a word
+// is the thread that reads it after cp.async.wait_group).
+__device__ __forceinline__ void ln_fetch_async(const __nv_bfloat16* w, uint2* ln_s, int H) {
+  const int n_pairs = H >> 2;
+  for (int pr = threadIdx.x; pr < n_pairs; pr += DEC_CTHREADS)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(ln_s + pr)), "l"(reinterpret_cast<const uint2*>(w) + pr) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Residual vector in (LL units, or a plain bf16 row for layer 0) -> LlamaRMSNorm -> xs, in ONE pass over registers:
+//   xs = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))
+// Thread t owns the unit pairs t, t + 256, ... (<= 4 pairs: hidden <= 4096, the host checks). The norm weights were copied to
+// `ln_s` by ln_fetch_async; own(u, word) sees every raw word once.
+template <typename Own>
+__device__ __forceinline__ void gather_rmsnorm(const uint64_t* ll, const uint32_t* plain, int H, uint32_t tag, bool check,
+                                               const uint2* ln_s, float eps, uint32_t* xs, float* red, Own&& own) {
+  constexpr int MAXP = 4;
+  const int n_pairs = H >> 2;
+  uint2 g[MAXP];
+  uint64_t a[MAXP], b[MAXP];
+  uint32_t pending = 0;
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int pr = i * DEC_CTHREADS + static_cast<int>(threadIdx.x);
+    g[i] = make_uint2(0, 0), a[i] = b[i] = 0;
+    if (pr < n_pairs) {
+      if (plain) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(plain) + pr);
+        a[i] = v.x, b[i] = v.y;
+      } else {
+        ll_load2(ll + 2 * pr, a[i], b[i]);
+        pending |= 1u << i;
+      }
+    }
+  }
+  uint32_t spins = 0;
+  while (pending) {
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      if (pending & (1u << i)) {
+        if (!check || (static_cast<uint32_t>(a[i] >> 32) == tag && static_cast<uint32_t>(b[i] >> 32) == tag))
+          pending &= ~(1u << i);
+        else
+          ll_load2(ll + 2 * (i * DEC_CTHREADS + static_cast<int>(threadIdx.x)), a[i], b[i]);
+      }
+    }
+    if (++spins > EMX_SPIN_LIMIT) __trap();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int pr = i * DEC_CTHREADS + static_cast<int>(threadIdx.x);
+    if (pr < n_pairs) g[i] = ln_s[pr];
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) ss += sumsq2(static_cast<uint32_t>(a[i])) + sumsq2(static_cast<uint32_t>(b[i]));  // absent pairs are 0
+  const float rs = 1.0f / sqrtf(cblock_sum(ss, red) / H + eps);
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int pr = i * DEC_CTHREADS + static_cast<int>(threadIdx.x);
+    if (pr < n_pairs) {
+      const uint32_t v0 = static_cast<uint32_t>(a[i]), v1 = static_cast<uint32_t>(b[i]);
+      own(2 * pr, v0), own(2 * pr + 1, v1);
+      xs[xs_pos(2 * pr)] = pack_bf16(bf16_lo(g[i].x) * bf16_round(bf16_lo(v0) * rs), bf16_hi(g[i].x) * bf16_round(bf16_hi(v0) * rs));
+      xs[xs_pos(2 * pr + 1)] = pack_bf16(bf16_lo(g[i].y) * bf16_round(bf16_lo(v1) * rs), bf16_hi(g[i].y) * bf16_round(bf16_hi(v1) * rs));
+    }
   }
   cbar();
 }
@@ -252,9 +315,9 @@ __device__ void producer_loop(const emx_decode_params& p, uint8_t* ring, uint64_
       const uint32_t ph = (it / DEC_STAGES) & 1;
       if ((it % DEC_PWARPS) == static_cast<uint32_t>(pidx)) {
         if (lane == 0) {
-          const long long t0 = clock64();
+          const long long t0 = dbg ? clock64() : 0;
           mbar_wait(&empty[slot], ph ^ 1);
-          waited += clock64() - t0;
+          if (dbg) waited += clock64() - t0;
           mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(nrows) * klen * 2);
         }
         __syncwarp();
@@ -364,7 +427,7 @@ __device__ __forceinline__ void part_sync(uint32_t buf) { asm volatile("bar.sync
 
 // epi(row, v0, v1, valid) is called for row pairs (row even) by lanes 0..7 of warp 0 (all eight, converged), rows ascending
 // per lane; valid == false marks lanes beyond the last row of a short group
-template <typename Epi>
+template <bool PROF, typename Epi>
 __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t* ring, uint64_t* full, uint64_t* empty, ConsumerState& cs,
                                               const __nv_bfloat16* xs, float* part, int warp, int lane, int debug_flags, Epi&& epi) {
   int r_begin, r_end;
@@ -384,9 +447,9 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
       const uint32_t ph = (cs.it / DEC_STAGES) & 1;
       const int ksteps = min(DEC_KW / 16, (klen - kbeg) / 16);  // <= 0: this warp's slice is past the K tail
       const uint4* xw = reinterpret_cast<const uint4*>(xs + k0 + kbeg) + (lane & 3);
-      const long long t0 = clock64();
+      const long long t0 = PROF ? clock64() : 0;
       mbar_wait(&full[slot], ph);
-      cs.waited += clock64() - t0;
+      if (PROF) cs.waited += clock64() - t0;
       if (ksteps > 0 && !(debug_flags & 64)) {
         const uint32_t a_base = smem_u32(ring + slot * DEC_STAGE_BYTES) + a_lane_off + kbeg * 2;
         if (ksteps == DEC_KW / 16) {
@@ -426,9 +489,9 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
       pb[warp * DEC_GROUP + (lane >> 2) + 8] = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]);
     }
     if (warp == 0) {
-      const long long t1 = clock64();
+      const long long t1 = PROF ? clock64() : 0;
       part_sync(buf);
-      const long long t2 = clock64();
+      const long long t2 = PROF ? clock64() : 0;
       if (lane < 8) {
         float v0 = 0.f, v1 = 0.f;
 #pragma unroll
@@ -436,7 +499,7 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
         epi(r0 + 2 * lane, v0, v1, 2 * lane < nrows);
       }
       __syncwarp();
-      cs.t_sync += t2 - t1, cs.t_epi += clock64() - t2;
+      if (PROF) cs.t_sync += t2 - t1, cs.t_epi += clock64() - t2;
     } else {
       part_arrive(buf);
     }
@@ -445,10 +508,12 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
 }
 
 // ---- attention for one (head, split) item ------------------------------------------------------------------------------
+// element offset of (layer, head, key) in the paged cache; page_size is a power of two (checked by the host)
 __device__ __forceinline__ long kv_row(const emx_decode_params& p, int layer, int head, int key) {
-  const int page = p.block_table[key / p.page_size];
-  const long layer_off = static_cast<long>(layer) * p.n_pages * p.heads * p.page_size * DEC_HD;
-  return layer_off + ((static_cast<long>(page) * p.heads + head) * p.page_size + key % p.page_size) * DEC_HD;
+  const int shift = 31 - __clz(p.page_size);
+  const int page = __ldg(p.block_table + (key >> shift));
+  const long layer_off = static_cast<long>(layer) * p.n_pages * p.heads;
+  return (((layer_off + static_cast<long>(page) * p.heads + head) << shift) + (key & (p.page_size - 1))) * DEC_HD;
 }
 
 // Pull the K/V rows this CTA will read in the attention phase into L2 ahead of time (they do not depend on the token
@@ -488,6 +553,17 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
   const int H = p.hidden;
   const bool owns_new = (k_end == n);  // the split that contains the token being decoded
 
+  // K rows do not depend on the token being decoded: one LANE per key, the 16 x 16-B loads of its 256-B row are issued before
+  // q is even waited for (nk <= 256 is guaranteed by the host: one key per thread)
+  const int mykey = k_begin + tid;
+  const bool has_key = tid < nk && mykey != pos;
+  uint4 kreg[16];
+  if (has_key) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kc + kv_row(p, layer, head, mykey));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) kreg[j] = ldg_nc_v4(kr + j);
+  }
+
   // q / k / v rows of this head arrive as LL units (unit = 2 consecutive elements): warp 0 takes q, warp 1 k, warp 2 v.
   // Lane t owns units t and t + 32, i.e. elements (2t, 2t+1) and their rotate_half partners (2t+64, 2t+65).
   if (warp < 3 && (warp == 0 || owns_new)) {
@@ -515,65 +591,71 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
   }
   cbar();
 
-  // scores: one LANE per key — the 16 x 16-B loads of a 256-B K row are all in flight at once (one memory round trip)
+  // scores
   const float scale = rsqrtf(static_cast<float>(DEC_HD));
-  float lmax = -INFINITY;
-  for (int kk = tid; kk < nk; kk += DEC_CTHREADS) {
-    const int key = k_begin + kk;
+  float sc = -INFINITY;
+  if (tid < nk) {
     float d = 0.f;
-    if (key == pos) {
+    if (mykey == pos) {
 #pragma unroll 8
       for (int j = 0; j < DEC_HD; ++j) d = fmaf(sq[j], sknew[j], d);
     } else {
-      const uint4* kr = reinterpret_cast<const uint4*>(kc + kv_row(p, layer, head, key));
-      uint4 r[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) r[j] = ldg_nc_v4(kr + j);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float4 qa = *reinterpret_cast<const float4*>(sq + 8 * j), qb = *reinterpret_cast<const float4*>(sq + 8 * j + 4);
-        d = fmaf(qa.x, bf16_lo(r[j].x), d), d = fmaf(qa.y, bf16_hi(r[j].x), d);
-        d = fmaf(qa.z, bf16_lo(r[j].y), d), d = fmaf(qa.w, bf16_hi(r[j].y), d);
-        d = fmaf(qb.x, bf16_lo(r[j].z), d), d = fmaf(qb.y, bf16_hi(r[j].z), d);
-        d = fmaf(qb.z, bf16_lo(r[j].w), d), d = fmaf(qb.w, bf16_hi(r[j].w), d);
+        d = fmaf(qa.x, bf16_lo(kreg[j].x), d), d = fmaf(qa.y, bf16_hi(kreg[j].x), d);
+        d = fmaf(qa.z, bf16_lo(kreg[j].y), d), d = fmaf(qa.w, bf16_hi(kreg[j].y), d);
+        d = fmaf(qb.x, bf16_lo(kreg[j].z), d), d = fmaf(qb.y, bf16_hi(kreg[j].z), d);
+        d = fmaf(qb.z, bf16_lo(kreg[j].w), d), d = fmaf(qb.w, bf16_hi(kreg[j].w), d);
       }
     }
-    d *= scale;
-    sscore[kk] = d;
-    lmax = fmaxf(lmax, d);
+    sc = d * scale;
   }
-  const float m = cblock_max(lmax, red);
-  float lsum = 0.f;
-  for (int kk = tid; kk < nk; kk += DEC_CTHREADS) {
-    const float pr = __expf(sscore[kk] - m);
-    lsum += pr;
-    sscore[kk] = bf16_round(pr);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
-  }
-  const float l = cblock_sum(lsum, red);  // its barriers also publish the probabilities
 
-  // PV: thread = (key slice of 8, 4 output dims); 32 threads read one 256-B V row coalesced; loads unrolled x4
+  // V: thread = (key slice of 8, 4 output dims); 32 threads read one 256-B V row coalesced. The loads of the first 128 keys
+  // go out NOW, before the softmax reductions, so their latency overlaps them.
   const int quad = tid & 31, slice = tid >> 5;
-  float a[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int kk0 = slice; kk0 < nk; kk0 += 8 * 4) {
-    uint2 vv[4];
-    float pw[4];
+  constexpr int VU = 16;
+  uint2 vv[VU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < VU; ++u) {
+    const int kk = slice + 8 * u;
+    vv[u] = make_uint2(0, 0);
+    if (kk < nk && k_begin + kk != pos) vv[u] = ldg_cg_v2(vc + kv_row(p, layer, head, k_begin + kk) + 4 * quad);
+  }
+
+  const float m = cblock_max(sc, red);
+  const float pr = (tid < nk) ? __expf(sc - m) : 0.f;
+  if (tid < nk) sscore[tid] = bf16_round(pr);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
+  const float l = cblock_sum(pr, red);         // its barriers also publish the probabilities
+
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (owns_new && slice == (pos - k_begin) % 8) {  // the token being decoded: V comes from shared memory
+    const float pw = sscore[pos - k_begin];
+    a[0] = pw * bf16_round(svnew[4 * quad]), a[1] = pw * bf16_round(svnew[4 * quad + 1]);
+    a[2] = pw * bf16_round(svnew[4 * quad + 2]), a[3] = pw * bf16_round(svnew[4 * quad + 3]);
+  }
+#pragma unroll
+  for (int u = 0; u < VU; ++u) {
+    const int kk = slice + 8 * u;
+    const float pw = (kk < nk) ? sscore[kk] : 0.f;
+    a[0] = fmaf(pw, bf16_lo(vv[u].x), a[0]), a[1] = fmaf(pw, bf16_hi(vv[u].x), a[1]);
+    a[2] = fmaf(pw, bf16_lo(vv[u].y), a[2]), a[3] = fmaf(pw, bf16_hi(vv[u].y), a[3]);
+  }
+  for (int kk0 = slice + 8 * VU; kk0 < nk; kk0 += 8 * VU) {  // contexts beyond 128 keys per split
+    uint2 v2[VU];
+#pragma unroll
+    for (int u = 0; u < VU; ++u) {
       const int kk = kk0 + 8 * u;
-      pw[u] = 0.f, vv[u] = make_uint2(0, 0);
-      if (kk < nk) {
-        pw[u] = sscore[kk];
-        const int key = k_begin + kk;
-        if (key == pos)
-          vv[u] = make_uint2(pack_bf16(svnew[4 * quad], svnew[4 * quad + 1]), pack_bf16(svnew[4 * quad + 2], svnew[4 * quad + 3]));
-        else
-          vv[u] = ldg_cg_v2(vc + kv_row(p, layer, head, key) + 4 * quad);
-      }
+      v2[u] = make_uint2(0, 0);
+      if (kk < nk && k_begin + kk != pos) v2[u] = ldg_cg_v2(vc + kv_row(p, layer, head, k_begin + kk) + 4 * quad);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      a[0] = fmaf(pw[u], bf16_lo(vv[u].x), a[0]), a[1] = fmaf(pw[u], bf16_hi(vv[u].x), a[1]);
-      a[2] = fmaf(pw[u], bf16_lo(vv[u].y), a[2]), a[3] = fmaf(pw[u], bf16_hi(vv[u].y), a[3]);
+    for (int u = 0; u < VU; ++u) {
+      const int kk = kk0 + 8 * u;
+      const float pw = (kk < nk) ? sscore[kk] : 0.f;
+      a[0] = fmaf(pw, bf16_lo(v2[u].x), a[0]), a[1] = fmaf(pw, bf16_hi(v2[u].x), a[1]);
+      a[2] = fmaf(pw, bf16_lo(v2[u].y), a[2]), a[3] = fmaf(pw, bf16_hi(v2[u].y), a[3]);
     }
   }
   *reinterpret_cast<float4*>(sacc + slice * 128 + 4 * quad) = make_float4(a[0], a[1], a[2], a[3]);
@@ -623,6 +705,9 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
+// PROF = true: the instrumented twin used when `dbg` is given (phase timestamps, wait counters); it costs registers, so the
+// product launch uses PROF = false.
+template <bool PROF>
 __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_decode_params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ring = smem;
@@ -630,6 +715,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   float* misc = reinterpret_cast<float*>(smem + DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES);
   uint64_t* empty = full + DEC_STAGES;
+  uint2* ln_s = reinterpret_cast<uint2*>(smem + DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128);
   float* red = misc;                                 // [8]
   int* s_state = reinterpret_cast<int*>(misc + 16);  // [5]
   float* s_best = misc + 32;                         // [8] values + [8] indices
@@ -657,7 +743,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   if (s_state[3]) return;  // sequence already hit EOS: nothing to do (uniform across the grid)
 
   const int L = p.layers, H = p.hidden;
-  long long* dbg = (blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
+  long long* dbg = (PROF && blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
   if (warp >= DEC_CWARPS + DEC_PWARPS) {
     prefetch_loop(p, lane, s_issued, full);
@@ -671,8 +757,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   // ===================== consumer warps =====================
   int dbg_i = 0;
   auto mark = [&]() {
-    if (dbg && tid == 0) dbg[dbg_i] = global_ns();
-    ++dbg_i;
+    if (PROF) {
+      if (dbg && tid == 0) dbg[dbg_i] = global_ns();
+      ++dbg_i;
+    }
   };
   ConsumerState cs{0, 0, 0, 0, 0};
   // LL tags of this launch: tag0 + l for everything exchanged inside layer l (and for the residual stream ENTERING layer l);
@@ -690,28 +778,21 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   cta_rows(H, PH_O, rb, re);  // this CTA's rows of the two residual-producing phases (o_proj, down_proj)
   const int rb2 = rb >> 1, re2 = re >> 1;
 
-  // raw residual vector -> xs (+ sum of squares, + this CTA's own rows kept for the residual add of the next epilogue)
-  float ss = 0.f;
-  auto take = [&](int u, uint32_t w) {
-    xs[xs_pos(u)] = w;
-    ss += sumsq2(w);
+  // this CTA's own rows of the residual stream are kept for the residual add of the next epilogue
+  auto own = [&](int u, uint32_t w) {
     if (u >= rb2 && u < re2) s_resid[u - rb2] = w;
   };
 
+  ln_fetch_async(static_cast<const __nv_bfloat16*>(p.ln1), ln_s, H);
   for (int layer = 0; layer < L; ++layer) {
     const uint32_t tag = tag0 + layer;
     // ---- P1: residual in, RMSNorm, QKV ----
     mark();
-    ss = 0.f;
-    if (layer == 0) {
-      for (int u = tid; u < (H >> 1); u += DEC_CTHREADS) take(u, __ldg(emb_row + u));
-    } else {
-      ll_gather<4>(xd, H >> 1, tag, check, take);
-    }
-    rmsnorm_finish(xs, static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer) * H, H, p.rms_eps, ss, red);
+    gather_rmsnorm(xd, layer == 0 ? emb_row : nullptr, H, tag, check, ln_s, p.rms_eps, xs, red, own);
+    ln_fetch_async(static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H, ln_s, H);  // for P4
     prefetch_kv(p, layer, pos);
     mark();
-    consume_phase(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
+    consume_phase<PROF>(phase_desc(p, layer, PH_QKV), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
                   p.debug_flags, [&](int row, float a0, float a1, bool valid) {
                     if (valid) ll_store(qkv + (row >> 1), pack_bf16(a0, a1), tag);
                   });
@@ -724,7 +805,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     ll_gather<4>(attn, H >> 1, tag, check, [&](int u, uint32_t w) { xs[xs_pos(u)] = w; });
     cbar();
     mark();
-    consume_phase(phase_desc(p, layer, PH_O), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
+    consume_phase<PROF>(phase_desc(p, layer, PH_O), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
                   p.debug_flags, [&](int row, float a0, float a1, bool valid) {
                     if (!valid) return;
                     const uint32_t r = s_resid[(row - rb) >> 1];
@@ -732,11 +813,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
                   });
     mark();
     // ---- P4: residual in, RMSNorm, gate/up + SwiGLU ----
-    ss = 0.f;
-    ll_gather<4>(xo, H >> 1, tag, check, take);
-    rmsnorm_finish(xs, static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H, H, p.rms_eps, ss, red);
+    gather_rmsnorm(xo, nullptr, H, tag, check, ln_s, p.rms_eps, xs, red, own);
+    ln_fetch_async(layer + 1 < L ? static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer + 1) * H
+                                 : static_cast<const __nv_bfloat16*>(p.final_norm), ln_s, H);  // for the next P1 / the final norm
     mark();
-    consume_phase(phase_desc(p, layer, PH_GATEUP), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
+    consume_phase<PROF>(phase_desc(p, layer, PH_GATEUP), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
                   p.debug_flags, [&](int row, float g, float u, bool valid) {
                     // lanes 0..7 (converged): lane i holds (gate, up) of output row/2; two outputs make one LL unit
                     const float hv = bf16_round(bf16_round(silu(bf16_round(g))) * bf16_round(u));
@@ -748,25 +829,23 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     ll_gather<11>(hbuf, p.inter >> 1, tag, check, [&](int u, uint32_t w) { xs[xs_pos(u)] = w; });
     cbar();
     mark();
-    consume_phase(phase_desc(p, layer, PH_DOWN), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
+    consume_phase<PROF>(phase_desc(p, layer, PH_DOWN), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
                   p.debug_flags, [&](int row, float a0, float a1, bool valid) {
                     if (!valid) return;
                     const uint32_t r = s_resid[(row - rb) >> 1];
                     ll_store(xd + (row >> 1), pack_bf16(bf16_lo(r) + bf16_round(a0), bf16_hi(r) + bf16_round(a1)), tag + 1);
                   });
     mark();
-    if (p.dbg && layer == 1 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 16 + blockIdx.x] = global_ns();
+    if (PROF && p.dbg && layer == 1 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 16 + blockIdx.x] = global_ns();
   }
 
   // ---- final norm + lm_head + greedy argmax ----
   mark();
-  ss = 0.f;
-  ll_gather<4>(xd, H >> 1, tag0 + L, check, take);
-  rmsnorm_finish(xs, static_cast<const __nv_bfloat16*>(p.final_norm), H, p.rms_eps, ss, red);
+  gather_rmsnorm(xd, nullptr, H, tag0 + L, check, ln_s, p.rms_eps, xs, red, own);
   mark();
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  consume_phase(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane, p.debug_flags,
+  consume_phase<PROF>(phase_desc(p, 0, PH_LMHEAD), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane, p.debug_flags,
                 [&](int row, float a0, float a1, bool valid) {
                   if (!valid) return;
                   const float v0 = bf16_round(a0), v1 = bf16_round(a1);
@@ -775,7 +854,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
                   if (v1 > best) best = v1, best_i = row + 1;
                 });
   mark();
-  if (dbg && tid == 0) dbg[15 * L + 8] = cs.waited, dbg[15 * L + 11] = cs.t_sync, dbg[15 * L + 12] = cs.t_epi;
+  if (PROF && dbg && tid == 0) dbg[15 * L + 8] = cs.waited, dbg[15 * L + 11] = cs.t_sync, dbg[15 * L + 12] = cs.t_epi;
   if (warp == 0 && lane < 8) s_best[lane] = best, reinterpret_cast<int*>(s_best + 8)[lane] = best_i;
   cbar();
   uint64_t* cand = static_cast<uint64_t*>(p.argmax_part);  // [grid][2] LL units: value bits, index
@@ -825,26 +904,30 @@ extern "C" int emx_decode_step(const emx_decode_params* params, cudaStream_t str
   EMX_REQUIRE(p.hidden % 16 == 0 && p.inter % 16 == 0 && p.vocab % 2 == 0, "emx_decode_step: hidden/inter must be multiples of 16, vocab even");
   EMX_REQUIRE(p.x && p.xo && p.qkv && p.attn && p.h && p.part && p.argmax_part && p.state, "emx_decode_step: null scratch pointer");
   EMX_REQUIRE(p.inter * 2 <= DEC_XS_BYTES && p.hidden * 2 <= DEC_XS_BYTES, "emx_decode_step: activation vector exceeds %d bytes", DEC_XS_BYTES);
+  EMX_REQUIRE(p.page_size > 0 && (p.page_size & (p.page_size - 1)) == 0, "emx_decode_step: page_size must be a power of two");
   EMX_REQUIRE(p.kv_splits >= 1 && p.kv_splits <= 8 && (p.kv_splits & (p.kv_splits - 1)) == 0, "emx_decode_step: kv_splits must be 1, 2, 4 or 8");
+  EMX_REQUIRE(p.hidden <= 16 * DEC_CTHREADS && p.hidden * 2 <= DEC_LN_BYTES, "emx_decode_step: hidden > %d not supported by the fused gather + RMSNorm", DEC_LN_BYTES / 2);
   EMX_REQUIRE(p.heads * p.kv_splits <= kNumSMs, "emx_decode_step: heads x kv_splits must not exceed the grid (one attention item per CTA)");
   EMX_REQUIRE(p.hidden / 2 / kNumSMs + 2 <= DEC_MAX_RESID, "emx_decode_step: hidden too large for the residual staging buffer");
-  const int max_keys_per_split = DEC_XS_BYTES / 4 - ATT_SSCORE;
-  EMX_REQUIRE((static_cast<long>(p.max_pages) * p.page_size + p.kv_splits - 1) / p.kv_splits + 1 <= max_keys_per_split,
+  const int max_keys_per_split = min(DEC_XS_BYTES / 4 - ATT_SSCORE, DEC_CTHREADS);
+  EMX_REQUIRE((static_cast<long>(p.max_pages) * p.page_size + p.kv_splits - 1) / p.kv_splits <= max_keys_per_split,
               "emx_decode_step: context capacity %d x %d exceeds the per-split score buffer (%d keys)", p.max_pages, p.page_size,
               max_keys_per_split);
   static bool attr_set = false;
   static int grid = 0;
   if (!attr_set) {
-    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
     int dev = 0, sms = 0, per_sm = 0;
     EMX_CHECK_CUDA(cudaGetDevice(&dev));
     EMX_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    EMX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel, DEC_THREADS, DEC_SMEM));
+    EMX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<true>, DEC_THREADS, DEC_SMEM));
     EMX_REQUIRE(per_sm >= 1, "emx_decode_step: kernel does not fit on an SM (smem %d)", DEC_SMEM);
     grid = sms;
     attr_set = true;
   }
   void* args[] = {const_cast<emx_decode_params*>(params)};
-  EMX_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_step_kernel), dim3(grid), dim3(DEC_THREADS), args, DEC_SMEM, stream));
+  void* fn = p.dbg ? reinterpret_cast<void*>(decode_step_kernel<true>) : reinterpret_cast<void*>(decode_step_kernel<false>);
+  EMX_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(DEC_THREADS), args, DEC_SMEM, stream));
   return 0;
 }

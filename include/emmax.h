@@ -170,7 +170,7 @@ int emx_debug_stream(const void* src, long bytes, int rows, int seg, long row_st
  * zeroed uint32; `out`: 32 + 2*148 int64 (CTA 0: per-phase ns, per-barrier ns, total ns; per-CTA total ns and %smid). */
 int emx_debug_skeleton(const void* src, long region_bytes, int n_phases, const int* phase_stages, const int* stall_ns, int reps,
                        int rows, int seg, long row_stride, int stages, int consume_cycles, int barrier_variant, int n_prod, int n_cons,
-                       const float* weight, int timers, int pf_stages, int pf_mode, int pf_pace_ns, void* sync, void* out,
+                       const float* weight, int timers, int pf_stages, int pf_mode, int pf_pace_ns, int launch_mode, void* sync, void* out,
                        emx_stream_t stream);
 
 #ifdef __cplusplus

@@ -19,7 +19,7 @@ out = torch.zeros(32 + 2 * GRID, dtype=torch.int64, device="cuda")
 st = _lib.stream()
 
 
-def run(label, phases, stalls, reps=32, rows=16, seg=4096, stride=8192, stages=3, consume=0, variant=1, n=5, n_prod=2, n_cons=8, dist=False, weight=None, timers=1, quiet=False, pf=0, pf_mode=0, pace=1400):
+def run(label, phases, stalls, reps=32, rows=16, seg=4096, stride=8192, stages=3, consume=0, variant=1, n=5, n_prod=2, n_cons=8, dist=False, weight=None, timers=1, quiet=False, pf=0, pf_mode=0, pace=1400, launch=0):
     ph = (C.c_int * len(phases))(*phases)
     sl = (C.c_int * len(stalls))(*stalls)
     region = nbytes // GRID // (rows * stride) * (rows * stride)
@@ -29,7 +29,7 @@ def run(label, phases, stalls, reps=32, rows=16, seg=4096, stride=8192, stages=3
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.check(lib.emx_debug_skeleton(buf.data_ptr(), region, len(phases), ph, sl, reps, rows, seg, stride, stages, consume, variant,
-                                          n_prod, n_cons, None if weight is None else weight.data_ptr(), timers, pf, pf_mode, pace, sync.data_ptr(),
+                                          n_prod, n_cons, None if weight is None else weight.data_ptr(), timers, pf, pf_mode, pace, launch, sync.data_ptr(),
                                           out.data_ptr(), st))
         e1.record()
         torch.cuda.synchronize()
@@ -58,13 +58,10 @@ NOST = [0, 0, 0, 0, 0]
 
 import numpy as np
 
-print("--- idle-triggered L2 prefetch (barrier variant 2, stalls 8/0.7/1/1/1 us)")
-run("barriers+stalls, no prefetch", LAYER, STALL, variant=2)
-run("barriers+stalls, window prefetch 8 stages, LSU", LAYER, STALL, variant=2, pf=8, pf_mode=1)
-for mode in (3, 2):
-    for pace in (1400, 1000, 700):
-        for pf in (8, 12):
-            run(f"idle-triggered mode {mode}, max {pf} stages, pace {pace} ns", LAYER, STALL, variant=2, pf=pf, pf_mode=mode, pace=pace)
-run("free run, idle-triggered mode 3, max 8, pace 1400", LAYER, NOST, variant=0, pf=8, pf_mode=3)
-run("barriers only, idle-triggered mode 3, max 8, pace 1000", LAYER, NOST, variant=2, pf=8, pf_mode=3, pace=1000)
-run("barriers only, no prefetch", LAYER, NOST, variant=2)
+print("--- free-run streaming: cooperative vs plain launch")
+run("1 producer, 1 consumer, single phase, cooperative", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0)
+run("1 producer, 1 consumer, single phase, plain launch", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0, launch=1)
+run("2 producers, 8 consumers, single phase, cooperative", [43], [0], variant=0, timers=0)
+run("2 producers, 8 consumers, single phase, plain launch", [43], [0], variant=0, timers=0, launch=1)
+run("2 producers, 8 consumers, single phase, plain, 24 reps (no wrap)", [43], [0], variant=0, timers=0, launch=1, reps=24)
+run("1 producer, 1 consumer, single phase, plain, 24 reps (no wrap)", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0, launch=1, reps=24)

@@ -18,23 +18,12 @@ def run(rows, seg, stride, stages, ef=1, grid=148, npairs=1, reps=5):
     for _ in range(reps):
         lib.emx_debug_stream(buf.data_ptr(), nbytes, rows, seg, stride, stages, ef, grid, npairs, st)
     e1.record(); torch.cuda.synchronize()
-    moved = blocks * rows * stride * grid * npairs
+    moved = blocks * rows * stride * grid * (npairs & 15)
     ms = e0.elapsed_time(e1) / reps
     its = blocks * (stride // seg)
     print(f"rows={rows:3d} seg={seg:6d} stride={stride:6d} stages={stages:2d} pairs={npairs} grid={grid}: {moved/ms/1e6:8.1f} GB/s  ({ms:.3f} ms, {ms*1e3/its:.3f} us/iter)")
-run(16, 2048, 8192, 6)
-run(16, 2048, 8192, 3, npairs=2)
-run(16, 2048, 8192, 2, npairs=3)
-run(16, 2048, 8192, 1, npairs=6)
 run(16, 4096, 8192, 3)
+run(16, 4096, 8192, 3, npairs=1 + 16 * 9)   # + 9 padding warps that exit immediately (352 threads like the decode kernel)
+run(16, 4096, 8192, 3, npairs=1 + 16 * 2)
 run(16, 4096, 8192, 2)
-run(16, 4096, 8192, 1, npairs=3)
-run(16, 8192, 8192, 1)
-run(8, 8192, 8192, 3)
-run(8, 8192, 8192, 2)
-run(16, 1024, 8192, 3, npairs=4)
-run(16, 2048, 22016 // 2048 * 2048, 6)
-run(16, 4096, 8192, 3, grid=74)
-run(16, 4096, 8192, 3, grid=120)
-run(1, 65536, 65536, 3)
-run(2, 32768, 32768, 3)
+run(16, 4096, 8192, 2, npairs=1 + 16 * 9)
