@@ -95,6 +95,7 @@ struct SkelParams {
   int barrier_variant;    // 0 none, 1 fence+red.release / ld.acquire poll (v3 kernel), 2 red.release / relaxed poll + fence,
                           // 3 last arriver (atom) releases per-CTA flags, 4 like 2 with nanosleep back-off
   int pf_pace_ns;
+  int prod_warp0;          // first producer warp (8 = like the decode kernel; 1 with n_cons == 1 = like the plain stream probe)
   int pf_stages, pf_mode;  // L2 prefetch warp: look-ahead in ring stages (0 = off); mode 0 bulk prefetch, 1 LSU prefetch per 128-B line,
                            // 2/3: the same two but issued only while the SM has no ring copy in flight, one stage per pf_pace_ns
   const float* weight;    // optional per-CTA work multiplier (mean 1): stages of a phase = round(phase_stages * weight), error carried
@@ -307,8 +308,8 @@ __global__ void __launch_bounds__(352, 1) skeleton_kernel(const SkelParams p) {
     }
     return;
   }
-  if (warp >= 8) {  // producer warps, alternating stages
-    const int pidx = warp - 8;
+  if (warp >= p.prod_warp0 && warp < p.prod_warp0 + 2) {  // producer warps, alternating stages
+    const int pidx = warp - p.prod_warp0;
     if (pidx >= p.n_prod) return;
     volatile uint32_t* issued = reinterpret_cast<volatile uint32_t*>(empty + p.stages);
     const uint64_t policy = l2_policy_evict_first();
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(352, 1) skeleton_kernel(const SkelParams p) {
     }
     return;
   }
-  if (warp >= p.n_cons) return;
+  if (warp >= p.n_cons) return;  // (also the unused warps 8..9 when the producers sit at warp 1)
   uint32_t epoch = 0;
   long it = 0;
   long long t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_bar[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -384,6 +385,7 @@ extern "C" int emx_debug_skeleton(const void* src, long region_bytes, int n_phas
   p.src = static_cast<const uint8_t*>(src), p.region_bytes = region_bytes, p.n_phases = n_phases;
   for (int i = 0; i < 8; ++i) p.phase_stages[i] = i < n_phases ? phase_stages[i] : 0, p.stall_ns[i] = i < n_phases ? stall_ns[i] : 0;
   p.reps = reps, p.rows = rows, p.seg = seg, p.row_stride = row_stride, p.stages = stages, p.consume_cycles = consume_cycles;
+  p.prod_warp0 = (launch_mode & 2) ? 1 : 8;
   p.n_prod = n_prod, p.n_cons = n_cons, p.weight = weight, p.timers = timers, p.pf_stages = pf_stages, p.pf_mode = pf_mode, p.pf_pace_ns = pf_pace_ns;
   EMX_REQUIRE(n_prod >= 1 && n_prod <= 2 && n_cons >= 1 && n_cons <= 8, "emx_debug_skeleton: 1..2 producer and 1..8 consumer warps");
   p.barrier_variant = barrier_variant, p.sync = static_cast<uint32_t*>(sync), p.out = static_cast<long long*>(out);

@@ -43,13 +43,14 @@ class Engine:
 
     def __init__(self, config: OpenVLAConfig, state_dict: Dict[str, torch.Tensor], device: torch.device,
                  max_batch: int = 1, max_context: int = 1024, kv_splits: int = 4) -> None:  # fmt: skip
+        kv_splits = int(os.environ.get("EMX_KV_SPLITS", kv_splits))
         _lib.load()  # raises if libemmax.so is missing: there is no fallback path
         if device.type != "cuda":
             raise _lib.EmxError("emmax_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         self.config, self.device = config, device
         self.t = config.text_config
         self.max_batch, self.kv_splits = max_batch, kv_splits
-        self.l2_lookahead_kb = int(os.environ.get("EMX_L2_LOOKAHEAD_KB", "0"))
+        self.l2_lookahead_kb = int(os.environ.get("EMX_L2_LOOKAHEAD_KB", "256"))  # idle-triggered L2 prefetch window per CTA
         self.max_context = _ceil_to(max_context, self.PAGE)
         self._graphs: Dict[Tuple[int, int], Tuple[torch.cuda.CUDAGraph, int]] = {}
         self.last_decode = None

@@ -50,10 +50,10 @@ for conf in args.configs.split(","):
         torch.cuda.synchronize()
         if s >= args.warm:
             t = dbg.cpu().numpy()
-            marks = t[: 10 * L + 4].astype(np.float64)
-            iv = np.array([[marks[10 * l + k + 1] - marks[10 * l + k] for k in range(9)] for l in range(L)])
+            marks = t[: 9 * L + 4].astype(np.float64)
+            iv = np.array([[marks[9 * l + k + 1] - marks[9 * l + k] for k in range(9)] for l in range(L)])
             acc += iv.mean(0)
-            base = 10 * L
+            base = 9 * L
             tail += np.array([marks[base + 1] - marks[base], marks[base + 2] - marks[base + 1], marks[base + 3] - marks[base + 2]])
             tot.append(e0.elapsed_time(e1))
             arr = t[15 * L + 16 : 15 * L + 16 + 148].astype(np.float64)  # end of layer 1 on every CTA
@@ -64,13 +64,14 @@ for conf in args.configs.split(","):
             ts.append(t[15 * L + 11])
             te.append(t[15 * L + 12])
             pfb = t[15 * L + 13]
+            gp = t[15 * L + 4 : 15 * L + 8] / clk * 1e6 / (2 * L + 1)
     n = args.steps
     a = acc / n / 1e3
     sk = np.array(skews).mean(0) / 1e3
     print(f"== lookahead {la} KiB, debug_flags {flags}: kernel {np.mean(tot):.3f} ms (min {np.min(tot):.3f}) | per layer {a.sum():.2f} us: "
           f"weights {a[1] + a[4] + a[6] + a[8]:.2f} (qkv {a[1]:.2f} o {a[4]:.2f} gateup {a[6]:.2f} down {a[8]:.2f}) exchanges "
           f"{a[0] + a[3] + a[5] + a[7]:.2f} (x {a[0]:.2f} attn {a[3]:.2f} xo {a[5]:.2f} h {a[7]:.2f}) attention {a[2]:.2f} | lm_head {tail[1] / n / 1e3:.1f} us | "
-          f"consumer wait {np.mean(cw) / clk * 1e3:.3f} ms, warp0 partial-sync {np.mean(ts) / clk * 1e3:.3f} ms, epilogue {np.mean(te) / clk * 1e3:.3f} ms, CTA0 prefetched {pfb / 1e6:.1f} MB of 89.3 | layer-1 end skew max-min {sk[0]:.2f} us", flush=True)  # fmt: skip
+          f"consumer wait {np.mean(cw) / clk * 1e3:.3f} ms, warp0 partial-sync {np.mean(ts) / clk * 1e3:.3f} ms, epilogue {np.mean(te) / clk * 1e3:.3f} ms, CTA0 prefetched {pfb / 1e6:.1f} MB of 89.3 | layer-1 end skew max-min {sk[0]:.2f} us | gather+norm us/call: loads {gp[0]:.2f} ln-wait {gp[1]:.2f} sum {gp[2]:.2f} norm+bar {gp[3]:.2f}", flush=True)  # fmt: skip
     if args.brief:
         continue
     print("per-layer phase means (us), CTA 0:")

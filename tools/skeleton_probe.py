@@ -58,10 +58,9 @@ NOST = [0, 0, 0, 0, 0]
 
 import numpy as np
 
-print("--- free-run streaming: cooperative vs plain launch")
-run("1 producer, 1 consumer, single phase, cooperative", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0)
-run("1 producer, 1 consumer, single phase, plain launch", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0, launch=1)
-run("2 producers, 8 consumers, single phase, cooperative", [43], [0], variant=0, timers=0)
-run("2 producers, 8 consumers, single phase, plain launch", [43], [0], variant=0, timers=0, launch=1)
-run("2 producers, 8 consumers, single phase, plain, 24 reps (no wrap)", [43], [0], variant=0, timers=0, launch=1, reps=24)
-run("1 producer, 1 consumer, single phase, plain, 24 reps (no wrap)", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0, launch=1, reps=24)
+print("--- free-run streaming: producer warp placement (launch bit 1: producers are warps 1,2 instead of 8,9)")
+run("1 producer (warp 8), 1 consumer", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0)
+run("1 producer (warp 1), 1 consumer", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0, launch=2)
+run("2 producers (warps 1,2), 1 consumer", [43], [0], variant=0, n_prod=2, n_cons=1, timers=0, launch=2)
+run("2 producers (warps 8,9), 1 consumer", [43], [0], variant=0, n_prod=2, n_cons=1, timers=0)
+run("1 producer (warp 1), 1 consumer, 2 x 64 KB", [43], [0], variant=0, n_prod=1, n_cons=1, timers=0, launch=2, stages=2)
