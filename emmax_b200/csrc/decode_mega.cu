@@ -50,6 +50,7 @@ constexpr int DEC_PARTBUFS = 4;                  // partial-sum buffers (a warp 
 constexpr int DEC_LN_BYTES = 8192;              // norm weights of the NEXT RMSNorm, fetched asynchronously a phase ahead (hidden <= 4096)
 constexpr int DEC_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128 + DEC_LN_BYTES;
 constexpr int DEC_HD = 128;  // head_dim supported by the decode kernel (Llama-2)
+constexpr int DEC_MAX_PAGES = 64;  // block-table entries staged in shared memory
 
 enum PhaseKind { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4, PH_END = 5 };
 
@@ -362,7 +363,9 @@ __device__ void producer_loop(const emx_decode_params& p, const PhaseTab& tab, u
 __device__ void prefetch_loop(const emx_decode_params& p, const PhaseTab& tab, int lane, volatile uint32_t* s_issued, uint64_t* full) {
   const long lookahead = static_cast<long>(p.l2_lookahead_kb) * 1024;
   if (lookahead <= 0) return;
-  const long long pace_ns = (p.debug_flags >> 8) ? (p.debug_flags >> 8) * 10 : 700;  // per 64 KB
+  const long long pace_ns = ((p.debug_flags >> 8) & 0xfff) ? ((p.debug_flags >> 8) & 0xfff) * 10 : 700;  // per 64 KB while the ring is idle
+  const long long pace_catchup_ns = (p.debug_flags >> 20) ? (p.debug_flags >> 20) * 10 : 1300;            // per 64 KB while the ring drains L2
+  const bool catchup = p.debug_flags & 8;  // measured neutral-to-slightly-negative on B200 (profiles/r01_decode_v5_prefetch_modes.txt): off by default
   SchedIter cur, pf;
   cur.init(tab, p.layers);
   pf.init(tab, p.layers);
@@ -370,6 +373,7 @@ __device__ void prefetch_loop(const emx_decode_params& p, const PhaseTab& tab, i
   long ahead = 0;          // bytes between the start of `cur` and the start of `pf`
   long pf_off = 0;         // progress inside the group `pf` points at
   long pf_total = 0;
+  bool live = false;       // data prefetched after the last idle period is still ahead of the ring
   while (!pf.done()) {
     // follow the producers: s_issued = number of ring stages issued so far
     const uint32_t issued = max(s_issued[0], s_issued[1]);
@@ -381,21 +385,33 @@ __device__ void prefetch_loop(const emx_decode_params& p, const PhaseTab& tab, i
       cur.advance(tab);
     }
     if (cur.done()) break;  // everything is in the ring already
-    if (ahead <= 0) {  // at (or behind) the group the ring is loading right now: start with the one after it
+    // lead of the prefetch point over the ring's issue point, in bytes
+    const uint32_t st_cur = (cur.d.K + DEC_KC - 1) / DEC_KC;
+    const long ring_off = static_cast<long>(issued - cur_stage) * (cur.group_bytes() / st_cur);
+    long lead = ahead + pf_off - ring_off;
+    if (ahead <= 0 || lead <= 0) {  // the ring has caught up with (or passed) the prefetch point: restart after the group it is loading
       pf = cur, pf_off = 0;
       ahead = pf.group_bytes();
       pf.advance(tab);
       if (pf.done()) break;
+      live = false;
+      lead = ahead - ring_off;
     }
-    bool idle = false;
-    // lead of the prefetch point over the ring's issue point, in bytes
-    const uint32_t st_cur = (cur.d.K + DEC_KC - 1) / DEC_KC;
-    const long lead = ahead + pf_off - static_cast<long>(issued - cur_stage) * (cur.group_bytes() / st_cur);
+    // Two triggers. IDLE: the newest ring copy of this CTA has landed, nothing of ours is in flight (consumers are stalled and the
+    // ring is full). CATCH-UP: the consumers are running again and the ring is refilling out of the L2 lines prefetched during the
+    // stall (lead > 0) — those copies cost no HBM time, so HBM would idle until the ring reaches the end of the prefetched
+    // region; keep streaming ahead at about the SM's fair share of HBM until the ring overtakes the prefetch point, which is
+    // the HBM-bound steady state where this warp stays out of the way.
+    bool go = false, idle = false;
     if (issued > 0 && lead < lookahead) {
-      const uint32_t last = issued - 1;
-      idle = mbar_try_wait(&full[last % DEC_STAGES], (last / DEC_STAGES) & 1);
+      if (catchup && live) {
+        go = true;
+      } else {
+        const uint32_t last = issued - 1;
+        go = idle = mbar_try_wait(&full[last % DEC_STAGES], (last / DEC_STAGES) & 1);
+      }
     }
-    if (!idle) {
+    if (!go) {
       __nanosleep(200);
       continue;
     }
@@ -408,6 +424,7 @@ __device__ void prefetch_loop(const emx_decode_params& p, const PhaseTab& tab, i
       const long off = per_lane * lane;
       if (off < n) prefetch_l2(src + off, static_cast<uint32_t>(min(per_lane, n - off)));
     }
+    live = true;
     pf_total += n;
     pf_off += n;
     if (pf_off >= gb) {
@@ -415,7 +432,8 @@ __device__ void prefetch_loop(const emx_decode_params& p, const PhaseTab& tab, i
       pf_off = 0;
       pf.advance(tab);
     }
-    while (global_ns() - t0 < pace_ns * n / (64 * 1024)) __nanosleep(100);
+    const long long wait_ns = (idle ? pace_ns : pace_catchup_ns) * n / (64 * 1024);
+    while (global_ns() - t0 < wait_ns) __nanosleep(100);
   }
   if (p.dbg && blockIdx.x == 0 && lane == 0) reinterpret_cast<long long*>(p.dbg)[15 * p.layers + 13] = pf_total;
 }
@@ -531,14 +549,14 @@ struct KvAddr {
   long base;         // element offset of (layer, page 0, head, slot 0)
   int page_stride;   // elements between consecutive pages: heads * page_size * head_dim
   int shift, mask;
-  const int32_t* table;
+  const int32_t* table;  // block table of the sequence, staged in SHARED memory at kernel start (no dependent global load per row)
   __device__ __forceinline__ long row(int key) const {
-    return base + static_cast<long>(__ldg(table + (key >> shift))) * page_stride + ((key & mask) << 7);  // << 7: * DEC_HD
+    return base + static_cast<long>(table[key >> shift]) * page_stride + ((key & mask) << 7);  // << 7: * DEC_HD
   }
 };
-__device__ __forceinline__ KvAddr kv_addr(const emx_decode_params& p, int layer, int head) {
+__device__ __forceinline__ KvAddr kv_addr(const emx_decode_params& p, const int32_t* s_table, int layer, int head) {
   KvAddr a;
-  a.shift = 31 - __clz(p.page_size), a.mask = p.page_size - 1, a.table = p.block_table;
+  a.shift = 31 - __clz(p.page_size), a.mask = p.page_size - 1, a.table = s_table;
   a.page_stride = (p.heads << a.shift) * DEC_HD;
   a.base = (static_cast<long>(layer) * p.n_pages * p.heads + head) * (static_cast<long>(DEC_HD) << a.shift);
   return a;
@@ -546,13 +564,13 @@ __device__ __forceinline__ KvAddr kv_addr(const emx_decode_params& p, int layer,
 
 // Pull the K/V rows this CTA will read in the attention phase into L2 ahead of time (they do not depend on the token
 // being decoded), so the phase pays L2 latency instead of loaded-HBM latency on its critical path.
-__device__ __forceinline__ void prefetch_kv(const emx_decode_params& p, int layer, int pos) {
+__device__ __forceinline__ void prefetch_kv(const emx_decode_params& p, const int32_t* s_table, int layer, int pos) {
   const int n = pos + 1, S = p.kv_splits;
   const int item = blockIdx.x;  // one attention item per CTA (host-checked: heads * kv_splits <= grid)
   if (item >= p.heads * S) return;
   const int head = item / S, split = item % S;
   const int k_begin = static_cast<int>(static_cast<long>(n) * split / S), k_end = static_cast<int>(static_cast<long>(n) * (split + 1) / S);
-  const KvAddr ka = kv_addr(p, layer, head);
+  const KvAddr ka = kv_addr(p, s_table, layer, head);
   for (int i = threadIdx.x; i < (k_end - k_begin) * 4; i += DEC_CTHREADS) {
     const int key = k_begin + (i >> 2);
     if (key == pos) continue;
@@ -564,8 +582,8 @@ __device__ __forceinline__ void prefetch_kv(const emx_decode_params& p, int laye
 // shared-memory carve-up of the (idle) activation area during attention, in floats
 constexpr int ATT_SQ = 0, ATT_SKNEW = 128, ATT_SVNEW = 256, ATT_SACC = 384 /*[8][128]*/, ATT_SSCORE = 384 + 1024;
 
-__device__ void attention_item(const emx_decode_params& p, int layer, int head, int split, int pos, uint32_t tag, bool check, float* sm,
-                               float* red) {
+__device__ void attention_item(const emx_decode_params& p, const int32_t* s_table, const uint32_t* s_rope, int layer, int head, int split, int pos,
+                               uint32_t tag, bool check, float* sm, float* red) {
   constexpr int HALF = DEC_HD / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = pos + 1, S = p.kv_splits;
@@ -574,17 +592,20 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
   float* sq = sm + ATT_SQ;          // [128] rotated q
   float* sknew = sm + ATT_SKNEW;    // [128] rotated new k
   float* svnew = sm + ATT_SVNEW;    // [128] new v
-  float* sacc = sm + ATT_SACC;      // [8][128] PV partials, then [128] the reduced partial of this split
+  float* sacc = sm + ATT_SACC;      // [8][128] PV partials
   float* sscore = sm + ATT_SSCORE;  // [nk] scores -> probabilities (host guarantees capacity)
   __nv_bfloat16* kc = static_cast<__nv_bfloat16*>(p.k_cache);
   __nv_bfloat16* vc = static_cast<__nv_bfloat16*>(p.v_cache);
   const uint64_t* qkv = static_cast<const uint64_t*>(p.qkv);
   const int H = p.hidden;
   const bool owns_new = (k_end == n);  // the split that contains the token being decoded
-  const KvAddr ka = kv_addr(p, layer, head);
+  const KvAddr ka = kv_addr(p, s_table, layer, head);
 
-  // K rows do not depend on the token being decoded: one LANE per key, the 16 x 16-B loads of its 256-B row are issued before
-  // q is even waited for (nk <= 256 is guaranteed by the host: one key per thread)
+  // Neither the cached K rows nor the cached V rows depend on the token being decoded, and every dependent global access costs
+  // 2-3 us while the weight stream saturates HBM. So ALL cache loads of the item are issued up front, in one batch, before q is
+  // even waited for (addresses come from the shared-memory block table):
+  //  K: one LANE per key, the 16 x 16-B loads of its 256-B row (nk <= 256 is guaranteed by the host: one key per thread);
+  //  V: thread = (key slice of 8, 4 output dims), 32 threads read one 256-B V row coalesced; the first 128 keys of the split.
   const int mykey = k_begin + tid;
   const bool has_key = tid < nk && mykey != pos;
   uint4 kreg[16];
@@ -592,6 +613,15 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
     const uint4* kr = reinterpret_cast<const uint4*>(kc + ka.row(mykey));
 #pragma unroll
     for (int j = 0; j < 16; ++j) kreg[j] = ldg_nc_v4(kr + j);
+  }
+  const int quad = tid & 31, slice = tid >> 5;
+  constexpr int VU = 16;
+  uint2 vv[VU];
+#pragma unroll
+  for (int u = 0; u < VU; ++u) {
+    const int kk = slice + 8 * u;
+    vv[u] = make_uint2(0, 0);
+    if (kk < nk && k_begin + kk != pos) vv[u] = ldg_cg_v2(vc + ka.row(k_begin + kk) + 4 * quad);
   }
 
   // q / k / v rows of this head arrive as LL units (unit = 2 consecutive elements): warp 0 takes q, warp 1 k, warp 2 v.
@@ -605,8 +635,7 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
       const long dst = ka.row(pos);
       reinterpret_cast<uint32_t*>(vc + dst)[lane] = lo, reinterpret_cast<uint32_t*>(vc + dst + HALF)[lane] = hi;
     } else {
-      const uint32_t cw = *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(p.cos_tab) + static_cast<long>(pos) * HALF + 2 * lane);
-      const uint32_t sw = *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(p.sin_tab) + static_cast<long>(pos) * HALF + 2 * lane);
+      const uint32_t cw = s_rope[lane], sw = s_rope[32 + lane];  // bf16 cos / sin of this position (staged at kernel start)
       const float ca = bf16_lo(cw), cb = bf16_hi(cw), sa = bf16_lo(sw), sb = bf16_hi(sw);
       // x_embed = bf16(bf16(x*cos) + bf16(rotate_half(x)*sin)), rotate_half(x) = [-x2, x1]
       const float r1a = bf16_round(bf16_round(x1a * ca) + bf16_round(-x2a * sa)), r1b = bf16_round(bf16_round(x1b * cb) + bf16_round(-x2b * sb));
@@ -642,22 +671,21 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
     sc = d * scale;
   }
 
-  // V: thread = (key slice of 8, 4 output dims); 32 threads read one 256-B V row coalesced. The loads of the first 128 keys
-  // go out NOW, before the softmax reductions, so their latency overlaps them.
-  const int quad = tid & 31, slice = tid >> 5;
-  constexpr int VU = 16;
-  uint2 vv[VU];
+  // softmax over the split with two block barriers: per-warp maxima -> everyone reduces the 8 values; same for the row sum
+  const float wm = warp_max(sc);
+  if (lane == 0) red[warp] = wm;
+  cbar();
+  float m = red[0];
 #pragma unroll
-  for (int u = 0; u < VU; ++u) {
-    const int kk = slice + 8 * u;
-    vv[u] = make_uint2(0, 0);
-    if (kk < nk && k_begin + kk != pos) vv[u] = ldg_cg_v2(vc + ka.row(k_begin + kk) + 4 * quad);
-  }
-
-  const float m = cblock_max(sc, red);
+  for (int w = 1; w < DEC_CWARPS; ++w) m = fmaxf(m, red[w]);
   const float pr = (tid < nk) ? __expf(sc - m) : 0.f;
   if (tid < nk) sscore[tid] = bf16_round(pr);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
-  const float l = cblock_sum(pr, red);         // its barriers also publish the probabilities
+  const float wl = warp_sum(pr);
+  if (lane == 0) red[DEC_CWARPS + warp] = wl;
+  cbar();  // also publishes the probabilities
+  float l = 0.f;
+#pragma unroll
+  for (int w = 0; w < DEC_CWARPS; ++w) l += red[DEC_CWARPS + w];
 
   float a[4] = {0.f, 0.f, 0.f, 0.f};
   if (owns_new && slice == (pos - k_begin) % 8) {  // the token being decoded: V comes from shared memory
@@ -690,26 +718,27 @@ __device__ void attention_item(const emx_decode_params& p, int layer, int head, 
   }
   *reinterpret_cast<float4*>(sacc + slice * 128 + 4 * quad) = make_float4(a[0], a[1], a[2], a[3]);
   cbar();
-  float acc = 0.f;
-  if (tid < DEC_HD) {
+  // threads 0..63 reduce the 8 key slices for output elements (2 tid, 2 tid + 1)
+  float n0 = 0.f, n1 = 0.f;
+  if (tid < HALF) {
 #pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2) acc += sacc[s2 * 128 + tid];
+    for (int s2 = 0; s2 < 8; ++s2) {
+      const float2 v = *reinterpret_cast<const float2*>(sacc + s2 * 128 + 2 * tid);
+      n0 += v.x, n1 += v.y;
+    }
   }
   uint64_t* part = static_cast<uint64_t*>(p.part) + (static_cast<long>(head) * S + split) * (DEC_HD + 2);
   if (split != 0) {
     // hand the partial (m, l, acc[128]) to the combining CTA of this head as LL units
-    if (tid < DEC_HD) ll_store(part + 2 + tid, __float_as_uint(acc), tag);
+    if (tid < HALF) ll_store(part + 2 + 2 * tid, __float_as_uint(n0), tag), ll_store(part + 3 + 2 * tid, __float_as_uint(n1), tag);
     if (tid == 0) ll_store(part, __float_as_uint(m), tag), ll_store(part + 1, __float_as_uint(l), tag);
-    cbar();
+    cbar();  // the caller reuses `sm` (the activation vector) right away
     return;
   }
-  // split 0 combines: own partial from shared memory, the others as they arrive
-  cbar();  // everyone has read sacc
-  if (tid < DEC_HD) sacc[tid] = acc;
-  cbar();
+  // split 0 combines: own partial from registers, the others as they arrive
   if (tid < HALF) {
-    // online merge of the splits (own partial first, the others as they arrive); a split with l == 0 is empty
-    float M = (l > 0.f) ? m : -INFINITY, den = l, n0 = sacc[2 * tid], n1 = sacc[2 * tid + 1];
+    // online merge of the splits; a split with l == 0 is empty
+    float M = (l > 0.f) ? m : -INFINITY, den = l;
 #pragma unroll 1
     for (int s2 = 1; s2 < S; ++s2) {
       const uint64_t* ph = part + s2 * (DEC_HD + 2);
@@ -746,10 +775,21 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   uint32_t* s_resid = reinterpret_cast<uint32_t*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP);  // [DEC_MAX_RESID] residual bf16 pairs of this CTA's rows
   volatile uint32_t* s_issued = reinterpret_cast<volatile uint32_t*>(misc + 24);  // [2] producers -> prefetch warp
   PhaseTab& tab = *reinterpret_cast<PhaseTab*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID);  // 8-byte aligned
+  static_assert(sizeof(PhaseTab) == 160, "PhaseTab layout");
+  int32_t* s_table = reinterpret_cast<int32_t*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID + 40);  // [DEC_MAX_PAGES] block table
+  uint32_t* s_rope = reinterpret_cast<uint32_t*>(s_table + DEC_MAX_PAGES);  // [32] cos pairs | [32] sin pairs of this position (bf16)
+  static_assert((64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID + 40 + DEC_MAX_PAGES + 64) * 4 <= DEC_MISC_BYTES, "misc area overflow");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   emx_decode_state* st = p.state;
   if (tid >= 32 && tid < 37) build_phase_tab(p, tab, tid - 32);
+  if (tid >= 64 && tid < 64 + p.max_pages) s_table[tid - 64] = __ldg(p.block_table + (tid - 64));
+  if (tid >= 128 && tid < 192) {  // RoPE row of the position being decoded: the same for all layers
+    const int i = tid - 128;
+    const long ppos = static_cast<long>(ldg_cg_u32(&st->pos)) * (DEC_HD / 2);
+    const __nv_bfloat16* tabp = static_cast<const __nv_bfloat16*>(i < 32 ? p.cos_tab : p.sin_tab);
+    s_rope[i] = __ldg(reinterpret_cast<const uint32_t*>(tabp + ppos) + (i & 31));
+  }
   if (tid == 0) {
     s_state[0] = static_cast<int>(ldg_cg_u32(&st->cur_token));
     s_state[1] = static_cast<int>(ldg_cg_u32(&st->pos));
@@ -831,14 +871,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
                                                         : static_cast<const __nv_bfloat16*>(p.final_norm);
         ln_fetch_async(next_w, ln_s, H);
       }
-      if (kind == PH_QKV) prefetch_kv(p, layer, pos);
+      if (kind == PH_QKV) prefetch_kv(p, s_table, layer, pos);
     } else {
       // ---- (attention,) then a plain vector in: attention output for o_proj, SwiGLU output for down_proj ----
       if (kind == PH_O) {
         // RoPE + KV append + split-KV attention: starts as soon as THIS head's q/k/v have arrived
         const int item = blockIdx.x;
         if (item < p.heads * p.kv_splits && !(p.debug_flags & 2))
-          attention_item(p, layer, item / p.kv_splits, item % p.kv_splits, pos, tag, check, reinterpret_cast<float*>(xs), red);
+          attention_item(p, s_table, s_rope, layer, item / p.kv_splits, item % p.kv_splits, pos, tag, check, reinterpret_cast<float*>(xs), red);
         mark();
       }
       ll_gather<11>(kind == PH_O ? attn : hbuf, (kind == PH_O ? H : p.inter) >> 1, tag, check, [&](int u, uint32_t w) { xs[xs_pos(u)] = w; });
@@ -925,6 +965,7 @@ extern "C" int emx_decode_step(const emx_decode_params* params, cudaStream_t str
   EMX_REQUIRE(p.page_size > 0 && (p.page_size & (p.page_size - 1)) == 0, "emx_decode_step: page_size must be a power of two");
   EMX_REQUIRE(p.kv_splits >= 1 && p.kv_splits <= 8 && (p.kv_splits & (p.kv_splits - 1)) == 0, "emx_decode_step: kv_splits must be 1, 2, 4 or 8");
   EMX_REQUIRE(p.hidden <= 16 * DEC_CTHREADS && p.hidden * 2 <= DEC_LN_BYTES, "emx_decode_step: hidden > %d not supported by the fused gather + RMSNorm", DEC_LN_BYTES / 2);
+  EMX_REQUIRE(p.max_pages <= DEC_MAX_PAGES, "emx_decode_step: block table of %d pages exceeds %d", p.max_pages, DEC_MAX_PAGES);
   EMX_REQUIRE(p.heads * p.kv_splits <= kNumSMs, "emx_decode_step: heads x kv_splits must not exceed the grid (one attention item per CTA)");
   EMX_REQUIRE(p.hidden / 2 / kNumSMs + 2 <= DEC_MAX_RESID, "emx_decode_step: hidden too large for the residual staging buffer");
   const int max_keys_per_split = min(DEC_XS_BYTES / 4 - ATT_SSCORE, DEC_CTHREADS);

@@ -1,7 +1,7 @@
 """Phase-level timing of the persistent decode kernel (CTA 0's view, %globaltimer) + ring wait counters, swept over
 (L2 look-ahead KiB, debug_flags) configurations with ONE model build.
 Usage (GPU box): python tools/decode_probe.py [--steps 16] [--configs 0:0,256:0,256:16] [--ctx 296] [--brief]
-debug_flags: 1 do not wait for LL tags, 2 skip attention (with 1), 4 no evict-first hint, 64 skip MMAs, bits 8.. prefetch pace (10 ns / 64 KB)."""
+debug_flags: 1 do not wait for LL tags, 2 skip attention (with 1), 4 no evict-first hint, 8 L2 prefetch also in catch-up mode, 16 drop LL stores, 64 skip MMAs, bits 8..19 idle prefetch pace, bits 20.. catch-up prefetch pace (10 ns / 64 KB)."""
 import argparse
 import ctypes as C
 import os
