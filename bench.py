@@ -129,6 +129,8 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm is ONE process that may use every host core
+    torch.set_num_threads(os.cpu_count() or 1)
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     cfg, tok, sd, _ = build_weights(dev)
     sd = {k: v.cpu() for k, v in sd.items()}
@@ -197,6 +199,8 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # keeps the version banner off stdout (one JSON line only)
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
 
