@@ -36,7 +36,9 @@ namespace emx {
 constexpr int DEC_CWARPS = 8;                    // consumer warps
 constexpr int DEC_CTHREADS = DEC_CWARPS * 32;    // 256
 constexpr int DEC_PWARPS = 2;                    // producer warps (alternate ring stages)
-constexpr int DEC_THREADS = DEC_CTHREADS + 32 * DEC_PWARPS + 32;  // + L2 prefetch warp
+constexpr int DEC_AWARPS = 4;                    // attention warps (their own dataflow, concurrent with the consumers)
+constexpr int DEC_ATHREADS = DEC_AWARPS * 32;    // 128
+constexpr int DEC_THREADS = 512;                 // 8 consumer + 4 attention + 2 producer + 1 L2-prefetch warp (+ 1 idle): 128 registers / thread
 constexpr int DEC_GROUP = 16;                    // rows per ring stage == M of the MMA atom
 constexpr int DEC_KC = 2048;                     // K elements per ring stage (4 KB per row segment)
 constexpr int DEC_KW = DEC_KC / DEC_CWARPS;      // 256 columns per consumer warp per stage
@@ -52,7 +54,11 @@ constexpr int DEC_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_
 constexpr int DEC_HD = 128;  // head_dim supported by the decode kernel (Llama-2)
 constexpr int DEC_MAX_PAGES = 64;  // block-table entries staged in shared memory
 
-enum PhaseKind { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4, PH_END = 5 };
+// q, k and v rows are three phases of their own, q FIRST: every CTA finishes its share of the q rows a third of the way into the
+// fused projection, so the attention warps get q ~7 us before k/v of the new token exist and do all the cached-key work in the shadow
+// of the k/v weight stream.
+constexpr int PH_STEPS = 6;  // weight phases per layer
+enum PhaseKind { PH_Q = 0, PH_K = 1, PH_V = 2, PH_O = 3, PH_GATEUP = 4, PH_DOWN = 5, PH_LMHEAD = 6, PH_END = 7 };
 
 struct PhaseDesc {
   const __nv_bfloat16* W;
@@ -62,9 +68,9 @@ struct PhaseDesc {
 // Per-CTA table of the five weight phases, built once per launch in shared memory (keeps 64-bit multiplies / divisions and a
 // switch out of every phase transition: the kernel's instruction footprint matters, see the note at decode_step_kernel).
 struct PhaseTab {
-  const __nv_bfloat16* W[5];
-  long layer_stride[5];  // elements between consecutive layers
-  int N[5], K[5], r_begin[5], r_end[5];
+  const __nv_bfloat16* W[7];
+  long layer_stride[7];  // elements between consecutive layers
+  int N[7], K[7], r_begin[7], r_end[7];
 };
 
 // Rows of a phase owned by this CTA. Row pairs are never split (one LL unit = one row pair); gate/up rows come in groups of
@@ -72,7 +78,9 @@ struct PhaseTab {
 __device__ __forceinline__ void build_phase_tab(const emx_decode_params& p, PhaseTab& t, int kind) {
   const long H = p.hidden, I = p.inter;
   switch (kind) {
-    case PH_QKV: t.W[kind] = static_cast<const __nv_bfloat16*>(p.w_qkv), t.layer_stride[kind] = 3 * H * H, t.N[kind] = 3 * H, t.K[kind] = H; break;
+    case PH_Q:
+    case PH_K:
+    case PH_V: t.W[kind] = static_cast<const __nv_bfloat16*>(p.w_qkv) + kind * H * H, t.layer_stride[kind] = 3 * H * H, t.N[kind] = H, t.K[kind] = H; break;
     case PH_O: t.W[kind] = static_cast<const __nv_bfloat16*>(p.w_o), t.layer_stride[kind] = H * H, t.N[kind] = H, t.K[kind] = H; break;
     case PH_GATEUP: t.W[kind] = static_cast<const __nv_bfloat16*>(p.w_gateup), t.layer_stride[kind] = 2 * I * H, t.N[kind] = 2 * I, t.K[kind] = H; break;
     case PH_DOWN: t.W[kind] = static_cast<const __nv_bfloat16*>(p.w_down), t.layer_stride[kind] = H * I, t.N[kind] = H, t.K[kind] = I; break;
@@ -290,7 +298,7 @@ struct SchedIter {
       return;
     }
     if (kind == PH_DOWN) {
-      kind = PH_QKV;
+      kind = PH_Q;
       if (++layer == layers) kind = PH_LMHEAD;
     } else {
       ++kind;
@@ -301,7 +309,7 @@ struct SchedIter {
     while (!done() && r >= r_end) next_phase(t);
   }
   __device__ __forceinline__ void init(const PhaseTab& t, int n_layers) {
-    layer = 0, kind = PH_QKV, layers = n_layers;
+    layer = 0, kind = PH_Q, layers = n_layers;
     load_phase(t);
     skip_empty(t);
   }
@@ -562,198 +570,252 @@ __device__ __forceinline__ KvAddr kv_addr(const emx_decode_params& p, const int3
   return a;
 }
 
-// Pull the K/V rows this CTA will read in the attention phase into L2 ahead of time (they do not depend on the token
-// being decoded), so the phase pays L2 latency instead of loaded-HBM latency on its critical path.
-__device__ __forceinline__ void prefetch_kv(const emx_decode_params& p, const int32_t* s_table, int layer, int pos) {
-  const int n = pos + 1, S = p.kv_splits;
-  const int item = blockIdx.x;  // one attention item per CTA (host-checked: heads * kv_splits <= grid)
-  if (item >= p.heads * S) return;
-  const int head = item / S, split = item % S;
-  const int k_begin = static_cast<int>(static_cast<long>(n) * split / S), k_end = static_cast<int>(static_cast<long>(n) * (split + 1) / S);
-  const KvAddr ka = kv_addr(p, s_table, layer, head);
-  for (int i = threadIdx.x; i < (k_end - k_begin) * 4; i += DEC_CTHREADS) {
-    const int key = k_begin + (i >> 2);
-    if (key == pos) continue;
-    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>((i & 2) ? p.v_cache : p.k_cache);
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ka.row(key) + (i & 1) * 64));
+// ---- attention warps -------------------------------------------------------------------------------------------------------
+// One (head, kv-split) item per CTA and layer, run by 4 dedicated warps CONCURRENTLY with the consumer warps. Per layer:
+//   1. (long before q exists: the cached rows do not depend on the token being decoded) every cached K / V row of the item is
+//      pulled HBM -> registers -> TENSOR MEMORY. The kernel's GEMVs run on mma.sync, so the SM's 256 KB of TMEM is free; each
+//      attention thread uses its own TMEM lane as 1 KB of extra register file (tcgen05.st / tcgen05.ld, 32 lanes x 32 columns
+//      per pass). All loaded-HBM latency (2-3 us per dependent access while the weight stream saturates the memory system) is paid
+//      here, in the ~45 us these warps would otherwise idle;
+//   2. q arrives as LL units a third of the way into the q|k|v projection -> RoPE -> scores of all cached keys, softmax
+//      statistics, P·V out of TMEM — while the consumers of every CTA are still streaming the k and v rows;
+//   3. the splits that do not contain the new token publish their partial (m, l, acc) right away; the LAST split (which does)
+//      waits for k, v of the new token (RoPE, KV append, one online-softmax step), merges the other splits' partials — long
+//      there by then — and publishes the head's output.
+// The consumers only ever see the finished attention vector (ll_gather before o_proj).
+constexpr int ATT_PASS = 64;                     // keys per pass: 2 threads per key (K), 4 key slices x 32 quads (V)
+constexpr int ATT_MAX_PASSES = 4;                // <= 256 cached keys per split (host-checked)
+constexpr int ATT_SQ = 0, ATT_SQ2 = 68 /* second half of q, skewed by 4 banks */, ATT_SVNEW = 136, ATT_SACC = 264 /*[4][128]*/, ATT_SSCORE = 776;
+constexpr int ATT_SM_FLOATS = ATT_SSCORE + ATT_PASS * ATT_MAX_PASSES;  // 1032 floats
+constexpr int ATT_SM_OFFSET = 16384;             // inside the activation area: bytes [16 K, 22 K) are only used by the down_proj input
+constexpr int ATT_TMEM_COLS = 2 * 32 * ATT_MAX_PASSES;  // K passes | V passes, 32 columns (128 B per thread) each
+
+__device__ __forceinline__ void abar() { asm volatile("bar.sync 6, %0;" ::"n"(DEC_ATHREADS) : "memory"); }
+
+__device__ __forceinline__ void att_load_k(uint32_t (&b)[32], const __nv_bfloat16* kc, const KvAddr& ka, int k_begin, int n_old, int pass, int atid) {
+  const int idx = pass * ATT_PASS + (atid >> 1);
+  if (idx < n_old) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kc + ka.row(k_begin + idx) + (atid & 1) * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 v = ldg_nc_v4(kr + j);
+      b[4 * j] = v.x, b[4 * j + 1] = v.y, b[4 * j + 2] = v.z, b[4 * j + 3] = v.w;
+    }
+  }
+}
+__device__ __forceinline__ void att_load_v(uint32_t (&b)[32], const __nv_bfloat16* vc, const KvAddr& ka, int k_begin, int n_old, int pass, int atid) {
+  const int slice = atid >> 5, quad = atid & 31;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int idx = pass * ATT_PASS + slice + 4 * u;
+    uint2 v = make_uint2(0, 0);
+    if (idx < n_old) v = ldg_nc_v2(vc + ka.row(k_begin + idx) + 4 * quad);
+    b[2 * u] = v.x, b[2 * u + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void att_score(const uint32_t (&b)[32], float* sm, int n_old, int pass, int atid, float scale) {
+  const int idx = pass * ATT_PASS + (atid >> 1);
+  const float* q = sm + ((atid & 1) ? ATT_SQ2 : ATT_SQ);
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 qa = *reinterpret_cast<const float4*>(q + 8 * j), qb = *reinterpret_cast<const float4*>(q + 8 * j + 4);
+    d0 = fmaf(qa.x, bf16_lo(b[4 * j]), d0), d1 = fmaf(qa.y, bf16_hi(b[4 * j]), d1);
+    d0 = fmaf(qa.z, bf16_lo(b[4 * j + 1]), d0), d1 = fmaf(qa.w, bf16_hi(b[4 * j + 1]), d1);
+    d0 = fmaf(qb.x, bf16_lo(b[4 * j + 2]), d0), d1 = fmaf(qb.y, bf16_hi(b[4 * j + 2]), d1);
+    d0 = fmaf(qb.z, bf16_lo(b[4 * j + 3]), d0), d1 = fmaf(qb.w, bf16_hi(b[4 * j + 3]), d1);
+  }
+  float d = d0 + d1;
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  if (idx < n_old && !(atid & 1)) sm[ATT_SSCORE + idx] = d * scale;
+}
+__device__ __forceinline__ void att_pv(const uint32_t (&b)[32], const float* sm, int n_old, int pass, int atid, float (&a)[4]) {
+  const int slice = atid >> 5;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int idx = pass * ATT_PASS + slice + 4 * u;
+    const float pw = (idx < n_old) ? sm[ATT_SSCORE + idx] : 0.f;
+    a[0] = fmaf(pw, bf16_lo(b[2 * u]), a[0]), a[1] = fmaf(pw, bf16_hi(b[2 * u]), a[1]);
+    a[2] = fmaf(pw, bf16_lo(b[2 * u + 1]), a[2]), a[3] = fmaf(pw, bf16_hi(b[2 * u + 1]), a[3]);
   }
 }
 
-// shared-memory carve-up of the (idle) activation area during attention, in floats
-constexpr int ATT_SQ = 0, ATT_SKNEW = 128, ATT_SVNEW = 256, ATT_SACC = 384 /*[8][128]*/, ATT_SSCORE = 384 + 1024;
-
-__device__ void attention_item(const emx_decode_params& p, const int32_t* s_table, const uint32_t* s_rope, int layer, int head, int split, int pos,
-                               uint32_t tag, bool check, float* sm, float* red) {
+template <bool PROF>
+__device__ void attention_loop(const emx_decode_params& p, const int32_t* s_table, const uint32_t* s_rope, int pos, uint32_t tag0, bool check,
+                               float* sm, float* red, uint32_t* tmem_holder, int atid) {
   constexpr int HALF = DEC_HD / 2;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = pos + 1, S = p.kv_splits;
+  const int item = blockIdx.x, S = p.kv_splits;
+  if (item >= p.heads * S || (p.debug_flags & 2)) return;
+  const int head = item / S, split = item % S;
+  const int awarp = atid >> 5, lane = atid & 31;
+  const int n = pos + 1;
   const int k_begin = static_cast<int>(static_cast<long>(n) * split / S), k_end = static_cast<int>(static_cast<long>(n) * (split + 1) / S);
-  const int nk = k_end - k_begin;
-  float* sq = sm + ATT_SQ;          // [128] rotated q
-  float* sknew = sm + ATT_SKNEW;    // [128] rotated new k
-  float* svnew = sm + ATT_SVNEW;    // [128] new v
-  float* sacc = sm + ATT_SACC;      // [8][128] PV partials
-  float* sscore = sm + ATT_SSCORE;  // [nk] scores -> probabilities (host guarantees capacity)
-  __nv_bfloat16* kc = static_cast<__nv_bfloat16*>(p.k_cache);
-  __nv_bfloat16* vc = static_cast<__nv_bfloat16*>(p.v_cache);
+  const bool owns_new = (split == S - 1);         // the last split contains the token being decoded (its last key) and combines
+  const int n_old = k_end - k_begin - (owns_new ? 1 : 0);  // cached keys of this split: k_begin .. k_begin + n_old - 1
+  const int passes = (n_old + ATT_PASS - 1) / ATT_PASS;
+  const __nv_bfloat16* kc = static_cast<const __nv_bfloat16*>(p.k_cache);
+  const __nv_bfloat16* vc = static_cast<const __nv_bfloat16*>(p.v_cache);
   const uint64_t* qkv = static_cast<const uint64_t*>(p.qkv);
-  const int H = p.hidden;
-  const bool owns_new = (k_end == n);  // the split that contains the token being decoded
-  const KvAddr ka = kv_addr(p, s_table, layer, head);
+  const int H = p.hidden, L = p.layers;
+  const float scale = rsqrtf(static_cast<float>(DEC_HD));
+  long long* dbg = (PROF && blockIdx.x == 0 && atid == 0 && p.dbg) ? reinterpret_cast<long long*>(p.dbg) + 15 * L + 16 + 148 : nullptr;
+  long long t_q = 0, t_old = 0, t_new = 0, t_pub = 0, t_sc = 0, t_sm = 0, t_pre = 0;
 
-  // Neither the cached K rows nor the cached V rows depend on the token being decoded, and every dependent global access costs
-  // 2-3 us while the weight stream saturates HBM. So ALL cache loads of the item are issued up front, in one batch, before q is
-  // even waited for (addresses come from the shared-memory block table):
-  //  K: one LANE per key, the 16 x 16-B loads of its 256-B row (nk <= 256 is guaranteed by the host: one key per thread);
-  //  V: thread = (key slice of 8, 4 output dims), 32 threads read one 256-B V row coalesced; the first 128 keys of the split.
-  const int mykey = k_begin + tid;
-  const bool has_key = tid < nk && mykey != pos;
-  uint4 kreg[16];
-  if (has_key) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kc + ka.row(mykey));
-#pragma unroll
-    for (int j = 0; j < 16; ++j) kreg[j] = ldg_nc_v4(kr + j);
-  }
-  const int quad = tid & 31, slice = tid >> 5;
-  constexpr int VU = 16;
-  uint2 vv[VU];
-#pragma unroll
-  for (int u = 0; u < VU; ++u) {
-    const int kk = slice + 8 * u;
-    vv[u] = make_uint2(0, 0);
-    if (kk < nk && k_begin + kk != pos) vv[u] = ldg_cg_v2(vc + ka.row(k_begin + kk) + 4 * quad);
-  }
+  // tensor memory: K pass i at columns [32 i, 32 i + 32), V pass i at [32 (MAX_PASSES + i), ...); a warp owns TMEM lanes 32 (warp % 4) ..
+  if (awarp == 0) tmem_alloc(tmem_holder, ATT_TMEM_COLS);
+  tc_fence_before();
+  abar();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_holder + (static_cast<uint32_t>(((DEC_CWARPS + awarp) & 3) * 32) << 16);
 
-  // q / k / v rows of this head arrive as LL units (unit = 2 consecutive elements): warp 0 takes q, warp 1 k, warp 2 v.
-  // Lane t owns units t and t + 32, i.e. elements (2t, 2t+1) and their rotate_half partners (2t+64, 2t+65).
-  if (warp < 3 && (warp == 0 || owns_new)) {
-    const uint64_t* src = qkv + warp * (H / 2) + head * HALF;
-    const uint32_t lo = ll_wait(src + lane, tag, check), hi = ll_wait(src + lane + 32, tag, check);
-    const float x1a = bf16_lo(lo), x1b = bf16_hi(lo), x2a = bf16_lo(hi), x2b = bf16_hi(hi);
-    if (warp == 2) {
-      svnew[2 * lane] = x1a, svnew[2 * lane + 1] = x1b, svnew[2 * lane + HALF] = x2a, svnew[2 * lane + 1 + HALF] = x2b;
-      const long dst = ka.row(pos);
-      reinterpret_cast<uint32_t*>(vc + dst)[lane] = lo, reinterpret_cast<uint32_t*>(vc + dst + HALF)[lane] = hi;
-    } else {
-      const uint32_t cw = s_rope[lane], sw = s_rope[32 + lane];  // bf16 cos / sin of this position (staged at kernel start)
+  uint32_t buf[32];
+  auto stage = [&](int layer) {  // HBM -> registers -> TMEM for every cached row of the item (the long-latency part, off the critical path)
+    const KvAddr a = kv_addr(p, s_table, layer, head);
+#pragma unroll 1
+    for (int ps = 0; ps < passes; ++ps) {
+      att_load_k(buf, kc, a, k_begin, n_old, ps, atid);
+      tmem_st_32x32(tbase + 32 * ps, buf);
+      att_load_v(buf, vc, a, k_begin, n_old, ps, atid);
+      tmem_st_32x32(tbase + 32 * (ATT_MAX_PASSES + ps), buf);
+    }
+    tmem_st_wait();
+  };
+  stage(0);
+
+#pragma unroll 1
+  for (int layer = 0; layer < L; ++layer) {
+    const uint32_t tag = tag0 + layer;
+    const long long ts0 = PROF ? global_ns() : 0;
+    // ---- q: LL units (unit = 2 consecutive elements); lane t of warp 0 owns units t and t + 32, i.e. elements (2t, 2t+1) and their
+    // rotate_half partners (2t+64, 2t+65)
+    if (awarp == 0) {
+      const uint64_t* src = qkv + head * HALF;
+      const uint32_t lo = ll_wait(src + lane, tag, check), hi = ll_wait(src + lane + 32, tag, check);
+      const float x1a = bf16_lo(lo), x1b = bf16_hi(lo), x2a = bf16_lo(hi), x2b = bf16_hi(hi);
+      const uint32_t cw = s_rope[lane], sw = s_rope[32 + lane];  // bf16 cos / sin of this position
       const float ca = bf16_lo(cw), cb = bf16_hi(cw), sa = bf16_lo(sw), sb = bf16_hi(sw);
       // x_embed = bf16(bf16(x*cos) + bf16(rotate_half(x)*sin)), rotate_half(x) = [-x2, x1]
-      const float r1a = bf16_round(bf16_round(x1a * ca) + bf16_round(-x2a * sa)), r1b = bf16_round(bf16_round(x1b * cb) + bf16_round(-x2b * sb));
-      const float r2a = bf16_round(bf16_round(x2a * ca) + bf16_round(x1a * sa)), r2b = bf16_round(bf16_round(x2b * cb) + bf16_round(x1b * sb));
-      float* dstv = (warp == 0) ? sq : sknew;
-      dstv[2 * lane] = r1a, dstv[2 * lane + 1] = r1b, dstv[2 * lane + HALF] = r2a, dstv[2 * lane + 1 + HALF] = r2b;
-      if (warp == 1) {
-        const long dst = ka.row(pos);
-        reinterpret_cast<uint32_t*>(kc + dst)[lane] = pack_bf16(r1a, r1b), reinterpret_cast<uint32_t*>(kc + dst + HALF)[lane] = pack_bf16(r2a, r2b);
-      }
+      sm[ATT_SQ + 2 * lane] = bf16_round(bf16_round(x1a * ca) + bf16_round(-x2a * sa));
+      sm[ATT_SQ + 2 * lane + 1] = bf16_round(bf16_round(x1b * cb) + bf16_round(-x2b * sb));
+      sm[ATT_SQ2 + 2 * lane] = bf16_round(bf16_round(x2a * ca) + bf16_round(x1a * sa));
+      sm[ATT_SQ2 + 2 * lane + 1] = bf16_round(bf16_round(x2b * cb) + bf16_round(x1b * sb));
     }
-  }
-  cbar();
+    abar();
+    const long long ts1 = PROF ? global_ns() : 0;
 
-  // scores
-  const float scale = rsqrtf(static_cast<float>(DEC_HD));
-  float sc = -INFINITY;
-  if (tid < nk) {
-    float d = 0.f;
-    if (mykey == pos) {
-#pragma unroll 8
-      for (int j = 0; j < DEC_HD; ++j) d = fmaf(sq[j], sknew[j], d);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 qa = *reinterpret_cast<const float4*>(sq + 8 * j), qb = *reinterpret_cast<const float4*>(sq + 8 * j + 4);
-        d = fmaf(qa.x, bf16_lo(kreg[j].x), d), d = fmaf(qa.y, bf16_hi(kreg[j].x), d);
-        d = fmaf(qa.z, bf16_lo(kreg[j].y), d), d = fmaf(qa.w, bf16_hi(kreg[j].y), d);
-        d = fmaf(qb.x, bf16_lo(kreg[j].z), d), d = fmaf(qb.y, bf16_hi(kreg[j].z), d);
-        d = fmaf(qb.z, bf16_lo(kreg[j].w), d), d = fmaf(qb.w, bf16_hi(kreg[j].w), d);
-      }
-    }
-    sc = d * scale;
-  }
-
-  // softmax over the split with two block barriers: per-warp maxima -> everyone reduces the 8 values; same for the row sum
-  const float wm = warp_max(sc);
-  if (lane == 0) red[warp] = wm;
-  cbar();
-  float m = red[0];
-#pragma unroll
-  for (int w = 1; w < DEC_CWARPS; ++w) m = fmaxf(m, red[w]);
-  const float pr = (tid < nk) ? __expf(sc - m) : 0.f;
-  if (tid < nk) sscore[tid] = bf16_round(pr);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
-  const float wl = warp_sum(pr);
-  if (lane == 0) red[DEC_CWARPS + warp] = wl;
-  cbar();  // also publishes the probabilities
-  float l = 0.f;
-#pragma unroll
-  for (int w = 0; w < DEC_CWARPS; ++w) l += red[DEC_CWARPS + w];
-
-  float a[4] = {0.f, 0.f, 0.f, 0.f};
-  if (owns_new && slice == (pos - k_begin) % 8) {  // the token being decoded: V comes from shared memory
-    const float pw = sscore[pos - k_begin];
-    a[0] = pw * bf16_round(svnew[4 * quad]), a[1] = pw * bf16_round(svnew[4 * quad + 1]);
-    a[2] = pw * bf16_round(svnew[4 * quad + 2]), a[3] = pw * bf16_round(svnew[4 * quad + 3]);
-  }
-#pragma unroll
-  for (int u = 0; u < VU; ++u) {
-    const int kk = slice + 8 * u;
-    const float pw = (kk < nk) ? sscore[kk] : 0.f;
-    a[0] = fmaf(pw, bf16_lo(vv[u].x), a[0]), a[1] = fmaf(pw, bf16_hi(vv[u].x), a[1]);
-    a[2] = fmaf(pw, bf16_lo(vv[u].y), a[2]), a[3] = fmaf(pw, bf16_hi(vv[u].y), a[3]);
-  }
-  for (int kk0 = slice + 8 * VU; kk0 < nk; kk0 += 8 * VU) {  // contexts beyond 128 keys per split
-    uint2 v2[VU];
-#pragma unroll
-    for (int u = 0; u < VU; ++u) {
-      const int kk = kk0 + 8 * u;
-      v2[u] = make_uint2(0, 0);
-      if (kk < nk && k_begin + kk != pos) v2[u] = ldg_cg_v2(vc + ka.row(k_begin + kk) + 4 * quad);
-    }
-#pragma unroll
-    for (int u = 0; u < VU; ++u) {
-      const int kk = kk0 + 8 * u;
-      const float pw = (kk < nk) ? sscore[kk] : 0.f;
-      a[0] = fmaf(pw, bf16_lo(v2[u].x), a[0]), a[1] = fmaf(pw, bf16_hi(v2[u].x), a[1]);
-      a[2] = fmaf(pw, bf16_lo(v2[u].y), a[2]), a[3] = fmaf(pw, bf16_hi(v2[u].y), a[3]);
-    }
-  }
-  *reinterpret_cast<float4*>(sacc + slice * 128 + 4 * quad) = make_float4(a[0], a[1], a[2], a[3]);
-  cbar();
-  // threads 0..63 reduce the 8 key slices for output elements (2 tid, 2 tid + 1)
-  float n0 = 0.f, n1 = 0.f;
-  if (tid < HALF) {
-#pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2) {
-      const float2 v = *reinterpret_cast<const float2*>(sacc + s2 * 128 + 2 * tid);
-      n0 += v.x, n1 += v.y;
-    }
-  }
-  uint64_t* part = static_cast<uint64_t*>(p.part) + (static_cast<long>(head) * S + split) * (DEC_HD + 2);
-  if (split != 0) {
-    // hand the partial (m, l, acc[128]) to the combining CTA of this head as LL units
-    if (tid < HALF) ll_store(part + 2 + 2 * tid, __float_as_uint(n0), tag), ll_store(part + 3 + 2 * tid, __float_as_uint(n1), tag);
-    if (tid == 0) ll_store(part, __float_as_uint(m), tag), ll_store(part + 1, __float_as_uint(l), tag);
-    cbar();  // the caller reuses `sm` (the activation vector) right away
-    return;
-  }
-  // split 0 combines: own partial from registers, the others as they arrive
-  if (tid < HALF) {
-    // online merge of the splits; a split with l == 0 is empty
-    float M = (l > 0.f) ? m : -INFINITY, den = l;
+    // ---- cached keys, out of TMEM (loops are NOT unrolled: one instance of each helper keeps the instruction footprint of these
+    // warps small next to the consumers' hot loop)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float m = -INFINITY, l = 0.f;
+    if (n_old > 0) {
 #pragma unroll 1
-    for (int s2 = 1; s2 < S; ++s2) {
-      const uint64_t* ph = part + s2 * (DEC_HD + 2);
-      const float ms = __uint_as_float(ll_wait(ph, tag, check)), ls = __uint_as_float(ll_wait(ph + 1, tag, check));
-      const float x0 = __uint_as_float(ll_wait(ph + 2 + 2 * tid, tag, check)), x1 = __uint_as_float(ll_wait(ph + 3 + 2 * tid, tag, check));
-      if (ls > 0.f) {
-        const float Mn = fmaxf(M, ms);
-        const float wo = (M == -INFINITY) ? 0.f : __expf(M - Mn), wn = __expf(ms - Mn);
-        n0 = n0 * wo + x0 * wn, n1 = n1 * wo + x1 * wn, den = den * wo + ls * wn;
-        M = Mn;
+      for (int ps = 0; ps < passes; ++ps) {
+        tmem_ld_32x32(tbase + 32 * ps, buf);
+        tmem_ld_wait();
+        att_score(buf, sm, n_old, ps, atid, scale);
+      }
+      abar();
+      if (PROF) t_sc += global_ns() - ts1;
+      // softmax statistics over the cached keys: thread t owns keys t and t + 128
+      const float s0 = (atid < n_old) ? sm[ATT_SSCORE + atid] : -INFINITY, s1 = (atid + DEC_ATHREADS < n_old) ? sm[ATT_SSCORE + atid + DEC_ATHREADS] : -INFINITY;
+      const float wm = warp_max(fmaxf(s0, s1));
+      if (lane == 0) red[awarp] = wm;
+      abar();
+      m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+      const float p0 = (atid < n_old) ? __expf(s0 - m) : 0.f, p1 = (atid + DEC_ATHREADS < n_old) ? __expf(s1 - m) : 0.f;
+      if (atid < n_old) sm[ATT_SSCORE + atid] = bf16_round(p0);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
+      if (atid + DEC_ATHREADS < n_old) sm[ATT_SSCORE + atid + DEC_ATHREADS] = bf16_round(p1);
+      const float wl = warp_sum(p0 + p1);
+      if (lane == 0) red[4 + awarp] = wl;
+      abar();  // also publishes the probabilities
+      l = (red[4] + red[5]) + (red[6] + red[7]);
+      if (PROF) t_sm += global_ns() - ts1;
+#pragma unroll 1
+      for (int ps = 0; ps < passes; ++ps) {
+        tmem_ld_32x32(tbase + 32 * (ATT_MAX_PASSES + ps), buf);
+        tmem_ld_wait();
+        att_pv(buf, sm, n_old, ps, atid, acc);
       }
     }
-    ll_store(static_cast<uint64_t*>(p.attn) + head * HALF + tid, pack_bf16(n0 / den, n1 / den), tag);
+    *reinterpret_cast<float4*>(sm + ATT_SACC + (atid >> 5) * 128 + 4 * lane) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    abar();
+    // threads 0..63 reduce the 4 key slices for output elements (2t, 2t + 1)
+    float n0 = 0.f, n1 = 0.f;
+    if (atid < HALF) {
+#pragma unroll
+      for (int s2 = 0; s2 < DEC_AWARPS; ++s2) {
+        const float2 v = *reinterpret_cast<const float2*>(sm + ATT_SACC + s2 * 128 + 2 * atid);
+        n0 += v.x, n1 += v.y;
+      }
+    }
+    const long long ts2 = PROF ? global_ns() : 0;
+
+    uint64_t* part = static_cast<uint64_t*>(p.part) + static_cast<long>(head) * S * (DEC_HD + 2);
+    if (!owns_new) {
+      // hand the partial (m, l, acc[128]) to the combining CTA of this head as LL units
+      uint64_t* mine = part + split * (DEC_HD + 2);
+      if (atid < HALF) ll_store(mine + 2 + 2 * atid, __float_as_uint(n0), tag), ll_store(mine + 3 + 2 * atid, __float_as_uint(n1), tag);
+      if (atid == 0) ll_store(mine, __float_as_uint(m), tag), ll_store(mine + 1, __float_as_uint(l), tag);
+    } else {
+      // ---- the token being decoded: k (warp 0) and v (warp 1) arrive at the end of the projection
+      if (awarp < 2) {
+        const uint64_t* src = qkv + (awarp + 1) * (H / 2) + head * HALF;
+        const uint32_t lo = ll_wait(src + lane, tag, check), hi = ll_wait(src + lane + 32, tag, check);
+        const long dst = kv_addr(p, s_table, layer, head).row(pos);
+        if (awarp == 1) {
+          sm[ATT_SVNEW + 2 * lane] = bf16_lo(lo), sm[ATT_SVNEW + 2 * lane + 1] = bf16_hi(lo);
+          sm[ATT_SVNEW + 2 * lane + HALF] = bf16_lo(hi), sm[ATT_SVNEW + 2 * lane + 1 + HALF] = bf16_hi(hi);
+          __nv_bfloat16* vw = static_cast<__nv_bfloat16*>(p.v_cache);
+          reinterpret_cast<uint32_t*>(vw + dst)[lane] = lo, reinterpret_cast<uint32_t*>(vw + dst + HALF)[lane] = hi;
+        } else {
+          const float x1a = bf16_lo(lo), x1b = bf16_hi(lo), x2a = bf16_lo(hi), x2b = bf16_hi(hi);
+          const uint32_t cw = s_rope[lane], sw = s_rope[32 + lane];
+          const float ca = bf16_lo(cw), cb = bf16_hi(cw), sa = bf16_lo(sw), sb = bf16_hi(sw);
+          const float r1a = bf16_round(bf16_round(x1a * ca) + bf16_round(-x2a * sa)), r1b = bf16_round(bf16_round(x1b * cb) + bf16_round(-x2b * sb));
+          const float r2a = bf16_round(bf16_round(x2a * ca) + bf16_round(x1a * sa)), r2b = bf16_round(bf16_round(x2b * cb) + bf16_round(x1b * sb));
+          __nv_bfloat16* kw = static_cast<__nv_bfloat16*>(p.k_cache);
+          reinterpret_cast<uint32_t*>(kw + dst)[lane] = pack_bf16(r1a, r1b), reinterpret_cast<uint32_t*>(kw + dst + HALF)[lane] = pack_bf16(r2a, r2b);
+          float d = sm[ATT_SQ + 2 * lane] * r1a;
+          d = fmaf(sm[ATT_SQ + 2 * lane + 1], r1b, d), d = fmaf(sm[ATT_SQ2 + 2 * lane], r2a, d), d = fmaf(sm[ATT_SQ2 + 2 * lane + 1], r2b, d);
+          d = warp_sum(d);
+          if (lane == 0) red[8] = d * scale;
+        }
+      }
+      abar();
+      const long long ts3 = PROF ? global_ns() : 0;
+      if (PROF) t_new += ts3 - ts2;
+      if (atid < HALF) {
+        // one online-softmax step with the new key, then the other splits' partials (a split with l == 0 is empty)
+        const float s_new = red[8];
+        float M = fmaxf(m, s_new);
+        const float wo0 = (l > 0.f) ? __expf(m - M) : 0.f, pn = __expf(s_new - M), pb = bf16_round(pn);
+        n0 = n0 * wo0 + pb * sm[ATT_SVNEW + 2 * atid], n1 = n1 * wo0 + pb * sm[ATT_SVNEW + 2 * atid + 1];
+        float den = l * wo0 + pn;
+#pragma unroll 1
+        for (int s2 = 0; s2 < S - 1; ++s2) {
+          const uint64_t* ph = part + s2 * (DEC_HD + 2);
+          const float ms = __uint_as_float(ll_wait(ph, tag, check)), ls = __uint_as_float(ll_wait(ph + 1, tag, check));
+          const float x0 = __uint_as_float(ll_wait(ph + 2 + 2 * atid, tag, check)), x1 = __uint_as_float(ll_wait(ph + 3 + 2 * atid, tag, check));
+          if (ls > 0.f) {
+            const float Mn = fmaxf(M, ms);
+            const float wo = __expf(M - Mn), wn = __expf(ms - Mn);
+            n0 = n0 * wo + x0 * wn, n1 = n1 * wo + x1 * wn, den = den * wo + ls * wn;
+            M = Mn;
+          }
+        }
+        ll_store(static_cast<uint64_t*>(p.attn) + head * HALF + atid, pack_bf16(n0 / den, n1 / den), tag);
+      }
+      if (PROF) t_pub += global_ns() - ts3;
+    }
+    const long long ts4 = PROF ? global_ns() : 0;
+    abar();  // sq / sacc / scores are rewritten by the next layer; everyone is done with the TMEM rows
+    if (layer + 1 < L) stage(layer + 1);
+    if (PROF) t_q += ts1 - ts0, t_old += ts2 - ts1, t_pre += global_ns() - ts4;
   }
-  cbar();
+  if (PROF && dbg) dbg[0] = t_q, dbg[1] = t_old, dbg[2] = t_new, dbg[3] = t_pub, dbg[4] = t_sc, dbg[5] = t_sm, dbg[6] = t_pre;
+  tc_fence_before();
+  abar();
+  if (awarp == 0) tmem_dealloc(*tmem_holder, ATT_TMEM_COLS);
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
@@ -775,14 +837,17 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   uint32_t* s_resid = reinterpret_cast<uint32_t*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP);  // [DEC_MAX_RESID] residual bf16 pairs of this CTA's rows
   volatile uint32_t* s_issued = reinterpret_cast<volatile uint32_t*>(misc + 24);  // [2] producers -> prefetch warp
   PhaseTab& tab = *reinterpret_cast<PhaseTab*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID);  // 8-byte aligned
-  static_assert(sizeof(PhaseTab) == 160, "PhaseTab layout");
-  int32_t* s_table = reinterpret_cast<int32_t*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID + 40);  // [DEC_MAX_PAGES] block table
+  static_assert(sizeof(PhaseTab) == 224, "PhaseTab layout");
+  int32_t* s_table = reinterpret_cast<int32_t*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID + 56);  // [DEC_MAX_PAGES] block table
   uint32_t* s_rope = reinterpret_cast<uint32_t*>(s_table + DEC_MAX_PAGES);  // [32] cos pairs | [32] sin pairs of this position (bf16)
-  static_assert((64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID + 40 + DEC_MAX_PAGES + 64) * 4 <= DEC_MISC_BYTES, "misc area overflow");
+  static_assert((64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID + 56 + DEC_MAX_PAGES + 64) * 4 <= DEC_MISC_BYTES, "misc area overflow");
+  float* att_red = misc + 48;  // [9] attention warps: per-warp maxima / sums, score of the new key
+  float* att_sm = reinterpret_cast<float*>(smem + DEC_STAGES * DEC_STAGE_BYTES + ATT_SM_OFFSET);
+  static_assert(ATT_SM_OFFSET + ATT_SM_FLOATS * 4 <= DEC_XS_BYTES, "attention scratch exceeds the activation area");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   emx_decode_state* st = p.state;
-  if (tid >= 32 && tid < 37) build_phase_tab(p, tab, tid - 32);
+  if (tid >= 32 && tid < 39) build_phase_tab(p, tab, tid - 32);
   if (tid >= 64 && tid < 64 + p.max_pages) s_table[tid - 64] = __ldg(p.block_table + (tid - 64));
   if (tid >= 128 && tid < 192) {  // RoPE row of the position being decoded: the same for all layers
     const int i = tid - 128;
@@ -810,12 +875,20 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   const int L = p.layers, H = p.hidden;
   long long* dbg = (PROF && blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
-  if (warp >= DEC_CWARPS + DEC_PWARPS) {
-    prefetch_loop(p, tab, lane, s_issued, full);
+  // LL tags of this launch: tag0 + l for everything exchanged inside layer l (and for the residual stream ENTERING layer l);
+  // tag0 + L enters the final norm, tag0 + L + 1 carries the argmax candidates. Never 0, unique across launches.
+  const uint32_t tag0 = static_cast<uint32_t>(s_state[4]) * static_cast<uint32_t>(L + 2) + 1u;
+  const bool check = !(p.debug_flags & 1);
+  if (warp >= DEC_CWARPS + DEC_AWARPS + DEC_PWARPS) {
+    if (warp == DEC_CWARPS + DEC_AWARPS + DEC_PWARPS) prefetch_loop(p, tab, lane, s_issued, full);
+    return;  // (the 16th warp only pads the block to 512 threads = 128 registers per thread)
+  }
+  if (warp >= DEC_CWARPS + DEC_AWARPS) {
+    producer_loop(p, tab, ring, full, empty, lane, warp - DEC_CWARPS - DEC_AWARPS, s_issued, dbg);
     return;
   }
   if (warp >= DEC_CWARPS) {
-    producer_loop(p, tab, ring, full, empty, lane, warp - DEC_CWARPS, s_issued, dbg);
+    attention_loop<PROF>(p, s_table, s_rope, pos, tag0, check, att_sm, att_red, reinterpret_cast<uint32_t*>(misc + 60), tid - DEC_CTHREADS);
     return;
   }
 
@@ -832,15 +905,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   };
   ConsumerState cs{0, 0, 0, 0, 0};
   long long gprof[4] = {0, 0, 0, 0};  // PROF: cycles of the gather + RMSNorm steps (loads back | ln wait | sum | normalise + barrier)
-  // LL tags of this launch: tag0 + l for everything exchanged inside layer l (and for the residual stream ENTERING layer l);
-  // tag0 + L enters the final norm, tag0 + L + 1 carries the argmax candidates. Never 0, unique across launches.
-  const uint32_t tag0 = static_cast<uint32_t>(s_state[4]) * static_cast<uint32_t>(L + 2) + 1u;
-  const bool check = !(p.debug_flags & 1);
   const bool drop = p.debug_flags & 16;
 
   uint64_t* xd = static_cast<uint64_t*>(p.x);      // residual stream after down_proj   [H/2] units
   uint64_t* xo = static_cast<uint64_t*>(p.xo);     // residual stream after o_proj      [H/2]
-  uint64_t* qkv = static_cast<uint64_t*>(p.qkv);   // [3H/2]
+  uint64_t* qkv = static_cast<uint64_t*>(p.qkv);   // [3H/2]: q | k | v
   uint64_t* attn = static_cast<uint64_t*>(p.attn); // [H/2]
   uint64_t* hbuf = static_cast<uint64_t*>(p.h);    // [inter/2]
   const uint32_t* emb_row = reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(p.embed) + static_cast<long>(token) * H);
@@ -854,42 +923,34 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   int best_i = 0x7fffffff;
 
   ln_fetch_async(static_cast<const __nv_bfloat16*>(p.ln1), ln_s, H);
-  const int n_steps = 4 * L + 1;
+  const int n_steps = PH_STEPS * L + 1;
+  int layer = 0, kind = PH_Q;
 #pragma unroll 1
   for (int step = 0; step < n_steps; ++step) {
-    const int layer = step >> 2;
-    const int kind = (step == n_steps - 1) ? PH_LMHEAD : (step & 3);
     const uint32_t tag = tag0 + layer;  // (the lm_head step has layer == L)
     mark();
-    if (kind == PH_QKV || kind == PH_GATEUP || kind == PH_LMHEAD) {
+    if (kind == PH_Q || kind == PH_GATEUP || kind == PH_LMHEAD) {
       // ---- residual stream in + RMSNorm ----
       const uint64_t* src = (kind == PH_GATEUP) ? xo : xd;
       gather_rmsnorm(src, step == 0 ? emb_row : nullptr, H, tag, check, ln_s, p.rms_eps, xs, red, own, (PROF && dbg && tid == 0) ? gprof : nullptr);
       if (kind != PH_LMHEAD) {  // norm weights of the next RMSNorm: ln2 of this layer, ln1 of the next one, the final norm
-        const __nv_bfloat16* next_w = (kind == PH_QKV)   ? static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H
+        const __nv_bfloat16* next_w = (kind == PH_Q)     ? static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H
                                       : (layer + 1 < L) ? static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer + 1) * H
                                                         : static_cast<const __nv_bfloat16*>(p.final_norm);
         ln_fetch_async(next_w, ln_s, H);
       }
-      if (kind == PH_QKV) prefetch_kv(p, s_table, layer, pos);
-    } else {
-      // ---- (attention,) then a plain vector in: attention output for o_proj, SwiGLU output for down_proj ----
-      if (kind == PH_O) {
-        // RoPE + KV append + split-KV attention: starts as soon as THIS head's q/k/v have arrived
-        const int item = blockIdx.x;
-        if (item < p.heads * p.kv_splits && !(p.debug_flags & 2))
-          attention_item(p, s_table, s_rope, layer, item / p.kv_splits, item % p.kv_splits, pos, tag, check, reinterpret_cast<float*>(xs), red);
-        mark();
-      }
+    } else if (kind == PH_O || kind == PH_DOWN) {
+      // ---- a plain vector in: the attention output (published by the attention warps of the split-0 CTAs) for o_proj, the
+      // SwiGLU output for down_proj ----
       ll_gather<11>(kind == PH_O ? attn : hbuf, (kind == PH_O ? H : p.inter) >> 1, tag, check, [&](int u, uint32_t w) { xs[xs_pos(u)] = w; });
       cbar();
-    }
+    }  // PH_K, PH_V: same input vector as PH_Q
     mark();
     consume_phase<PROF>(phase_desc(tab, layer, kind), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
                         p.debug_flags, [&](int row, float a0, float a1, bool valid) {
                           // lanes 0..7 of warp 0, converged; `kind` is uniform
-                          if (kind == PH_QKV) {
-                            if (valid) ll_store(qkv + (row >> 1), pack_bf16(a0, a1), tag, drop);
+                          if (kind <= PH_V) {
+                            if (valid) ll_store(qkv + kind * (H >> 1) + (row >> 1), pack_bf16(a0, a1), tag, drop);
                           } else if (kind == PH_GATEUP) {
                             // lane i holds (gate, up) of output row/2; two outputs make one LL unit
                             const float hv = bf16_round(bf16_round(silu(bf16_round(a0))) * bf16_round(a1));
@@ -908,7 +969,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
                                      kind == PH_O ? tag : tag + 1, drop);
                           }
                         });
-    if (PROF && p.dbg && step == 7 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 16 + blockIdx.x] = global_ns();  // end of layer 1
+    if (PROF && p.dbg && step == 2 * PH_STEPS - 1 && tid == 0) reinterpret_cast<long long*>(p.dbg)[15 * L + 16 + blockIdx.x] = global_ns();  // end of layer 1
+    if (++kind == PH_LMHEAD) {
+      kind = PH_Q;
+      if (++layer == L) kind = PH_LMHEAD;
+    }
   }
   mark();
   if (PROF && dbg && tid == 0) dbg[15 * L + 4] = gprof[0], dbg[15 * L + 5] = gprof[1], dbg[15 * L + 6] = gprof[2], dbg[15 * L + 7] = gprof[3];
@@ -968,7 +1033,7 @@ extern "C" int emx_decode_step(const emx_decode_params* params, cudaStream_t str
   EMX_REQUIRE(p.max_pages <= DEC_MAX_PAGES, "emx_decode_step: block table of %d pages exceeds %d", p.max_pages, DEC_MAX_PAGES);
   EMX_REQUIRE(p.heads * p.kv_splits <= kNumSMs, "emx_decode_step: heads x kv_splits must not exceed the grid (one attention item per CTA)");
   EMX_REQUIRE(p.hidden / 2 / kNumSMs + 2 <= DEC_MAX_RESID, "emx_decode_step: hidden too large for the residual staging buffer");
-  const int max_keys_per_split = min(DEC_XS_BYTES / 4 - ATT_SSCORE, DEC_CTHREADS);
+  const int max_keys_per_split = ATT_PASS * ATT_MAX_PASSES;
   EMX_REQUIRE((static_cast<long>(p.max_pages) * p.page_size + p.kv_splits - 1) / p.kv_splits <= max_keys_per_split,
               "emx_decode_step: context capacity %d x %d exceeds the per-split score buffer (%d keys)", p.max_pages, p.page_size,
               max_keys_per_split);

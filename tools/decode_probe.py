@@ -31,7 +31,8 @@ ids = torch.tensor([[1] + np.random.default_rng(1234).integers(3, 31744, 39).tol
 pv = torch.randn(1, 6, 224, 224, device="cuda").to(torch.bfloat16)
 eng.generate(ids, pv, 2 + args.advance, eos_token_id=None)
 lib = _lib.load()
-names = ["x in + rmsnorm1", "qkv", "attention", "attn in", "o_proj", "x in + rmsnorm2", "gate/up", "h in", "down"]
+names = ["x in + rmsnorm1", "q rows", "-", "k rows", "-", "v rows", "attn in (waits for attention)", "o_proj", "x in + rmsnorm2", "gate/up", "h in", "down"]
+NM = len(names)  # timestamps per layer
 clk = 1.965e9
 
 for conf in args.configs.split(","):
@@ -40,7 +41,8 @@ for conf in args.configs.split(","):
     p.l2_lookahead_kb, p.debug_flags = la, flags
     dbg = torch.zeros(15 * L + 16 + 2 * 148 + 8, dtype=torch.int64, device="cuda")
     skews, late, tot, cw, pw, ts, te = [], [], [], [], [], [], []
-    acc, tail = np.zeros(9), np.zeros(3)
+    acc, tail = np.zeros(NM), np.zeros(3)
+    att = np.zeros(7)
     for s in range(args.warm + args.steps):
         p.dbg = dbg.data_ptr() if s >= args.warm else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -50,10 +52,11 @@ for conf in args.configs.split(","):
         torch.cuda.synchronize()
         if s >= args.warm:
             t = dbg.cpu().numpy()
-            marks = t[: 9 * L + 4].astype(np.float64)
-            iv = np.array([[marks[9 * l + k + 1] - marks[9 * l + k] for k in range(9)] for l in range(L)])
+            marks = t[: NM * L + 4].astype(np.float64)
+            iv = np.array([[marks[NM * l + k + 1] - marks[NM * l + k] for k in range(NM)] for l in range(L)])
             acc += iv.mean(0)
-            base = 9 * L
+            base = NM * L
+            att += t[15 * L + 16 + 148 : 15 * L + 16 + 155].astype(np.float64) / L
             tail += np.array([marks[base + 1] - marks[base], marks[base + 2] - marks[base + 1], marks[base + 3] - marks[base + 2]])
             tot.append(e0.elapsed_time(e1))
             arr = t[15 * L + 16 : 15 * L + 16 + 148].astype(np.float64)  # end of layer 1 on every CTA
@@ -69,8 +72,8 @@ for conf in args.configs.split(","):
     a = acc / n / 1e3
     sk = np.array(skews).mean(0) / 1e3
     print(f"== lookahead {la} KiB, debug_flags {flags}: kernel {np.mean(tot):.3f} ms (min {np.min(tot):.3f}) | per layer {a.sum():.2f} us: "
-          f"weights {a[1] + a[4] + a[6] + a[8]:.2f} (qkv {a[1]:.2f} o {a[4]:.2f} gateup {a[6]:.2f} down {a[8]:.2f}) exchanges "
-          f"{a[0] + a[3] + a[5] + a[7]:.2f} (x {a[0]:.2f} attn {a[3]:.2f} xo {a[5]:.2f} h {a[7]:.2f}) attention {a[2]:.2f} | lm_head {tail[1] / n / 1e3:.1f} us | "
+          f"weights {a[1] + a[3] + a[5] + a[7] + a[9] + a[11]:.2f} (q {a[1]:.2f} k {a[3]:.2f} v {a[5]:.2f} o {a[7]:.2f} gateup {a[9]:.2f} down {a[11]:.2f}) exchanges "
+          f"{a[0] + a[2] + a[4] + a[6] + a[8] + a[10]:.2f} (x {a[0]:.2f} attn {a[6]:.2f} xo {a[8]:.2f} h {a[10]:.2f}) | attention warps of CTA 0 (us/layer): wait q {att[0] / n / 1e3:.2f}, cached keys {att[1] / n / 1e3:.2f} (scores done at {att[4] / n / 1e3:.2f}, softmax at {att[5] / n / 1e3:.2f}), new key {att[2] / n / 1e3:.2f}, combine+publish {att[3] / n / 1e3:.2f}, staging next layer into TMEM {att[6] / n / 1e3:.2f} | lm_head {tail[1] / n / 1e3:.1f} us | "
           f"consumer wait {np.mean(cw) / clk * 1e3:.3f} ms, warp0 partial-sync {np.mean(ts) / clk * 1e3:.3f} ms, epilogue {np.mean(te) / clk * 1e3:.3f} ms, CTA0 prefetched {pfb / 1e6:.1f} MB of 89.3 | layer-1 end skew max-min {sk[0]:.2f} us | gather+norm us/call: loads {gp[0]:.2f} ln-wait {gp[1]:.2f} sum {gp[2]:.2f} norm+bar {gp[3]:.2f}", flush=True)  # fmt: skip
     if args.brief:
         continue
