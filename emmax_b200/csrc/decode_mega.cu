@@ -165,6 +165,28 @@ __device__ __forceinline__ void ll_gather(const uint64_t* buf, int n_units, uint
   }
 }
 
+// NP unit pairs at computed addresses: all loads in flight before the first tag is checked, missing pairs are re-polled.
+template <int NP, typename Addr>
+__device__ __forceinline__ void ll_fetch_pairs(Addr&& addr, uint32_t (&out)[2 * NP], uint32_t tag, bool check) {
+  uint64_t a[NP], b[NP];
+  uint32_t pending = (1u << NP) - 1;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) ll_load2(addr(i), a[i], b[i]);
+  uint32_t spins = 0;
+  while (pending) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      if (pending & (1u << i)) {
+        if (!check || (static_cast<uint32_t>(a[i] >> 32) == tag && static_cast<uint32_t>(b[i] >> 32) == tag)) pending &= ~(1u << i);
+        else ll_load2(addr(i), a[i], b[i]);
+      }
+    }
+    if (++spins > EMX_SPIN_LIMIT) __trap();
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) out[2 * i] = static_cast<uint32_t>(a[i]), out[2 * i + 1] = static_cast<uint32_t>(b[i]);
+}
+
 __device__ __forceinline__ float cblock_sum(float v, float* red) {
   v = warp_sum(v);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -792,15 +814,24 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
         n0 = n0 * wo0 + pb * sm[ATT_SVNEW + 2 * atid], n1 = n1 * wo0 + pb * sm[ATT_SVNEW + 2 * atid + 1];
         float den = l * wo0 + pn;
 #pragma unroll 1
-        for (int s2 = 0; s2 < S - 1; ++s2) {
-          const uint64_t* ph = part + s2 * (DEC_HD + 2);
-          const float ms = __uint_as_float(ll_wait(ph, tag, check)), ls = __uint_as_float(ll_wait(ph + 1, tag, check));
-          const float x0 = __uint_as_float(ll_wait(ph + 2 + 2 * atid, tag, check)), x1 = __uint_as_float(ll_wait(ph + 3 + 2 * atid, tag, check));
-          if (ls > 0.f) {
-            const float Mn = fmaxf(M, ms);
-            const float wo = __expf(M - Mn), wn = __expf(ms - Mn);
-            n0 = n0 * wo + x0 * wn, n1 = n1 * wo + x1 * wn, den = den * wo + ls * wn;
-            M = Mn;
+        for (int s0 = 0; s0 < S - 1; s0 += 3) {  // up to three other splits at a time: all six unit pairs in flight before the first tag check
+          const int cnt = min(3, S - 1 - s0);
+          uint32_t w[12];
+          ll_fetch_pairs<6>(
+              [&](int i) -> const uint64_t* {
+                const uint64_t* ph = part + (s0 + min(i >> 1, cnt - 1)) * (DEC_HD + 2);
+                return (i & 1) ? ph + 2 + 2 * atid : ph;
+              },
+              w, tag, check);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float ms = __uint_as_float(w[4 * c]), ls = __uint_as_float(w[4 * c + 1]);
+            if (c < cnt && ls > 0.f) {
+              const float Mn = fmaxf(M, ms);
+              const float wo = __expf(M - Mn), wn = __expf(ms - Mn);
+              n0 = n0 * wo + __uint_as_float(w[4 * c + 2]) * wn, n1 = n1 * wo + __uint_as_float(w[4 * c + 3]) * wn, den = den * wo + ls * wn;
+              M = Mn;
+            }
           }
         }
         ll_store(static_cast<uint64_t*>(p.attn) + head * HALF + atid, pack_bf16(n0 / den, n1 / den), tag);

@@ -43,6 +43,17 @@ for conf in args.configs.split(","):
     skews, late, tot, cw, pw, ts, te = [], [], [], [], [], [], []
     acc, tail = np.zeros(NM), np.zeros(3)
     att = np.zeros(7)
+    # the product kernel (no dbg buffer: the un-instrumented twin), timed over args.steps launches with one event pair
+    p.dbg = None
+    for s in range(args.warm):
+        _lib.check(lib.emx_decode_step(C.byref(p), _lib.stream()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        _lib.check(lib.emx_decode_step(C.byref(p), _lib.stream()))
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"-- lookahead {la} KiB, debug_flags {flags}: PRODUCT kernel {e0.elapsed_time(e1) / args.steps:.3f} ms/token (ctx {int(eng.d_state[1].item())})", flush=True)
     for s in range(args.warm + args.steps):
         p.dbg = dbg.data_ptr() if s >= args.warm else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
