@@ -664,7 +664,7 @@ __device__ __forceinline__ void att_pv(const uint32_t (&b)[32], const float* sm,
 
 template <bool PROF>
 __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_table, const uint32_t* s_rope, int pos, uint32_t tag0, bool check,
-                               float* sm, float* red, uint32_t* tmem_holder, int atid) {
+                               float* sm, float* red, uint32_t* tmem_holder, volatile int* s_step, int atid) {
   constexpr int HALF = DEC_HD / 2;
   const int item = blockIdx.x, S = p.kv_splits;
   if (item >= p.heads * S || (p.debug_flags & 2)) return;
@@ -840,7 +840,20 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
     }
     const long long ts4 = PROF ? global_ns() : 0;
     abar();  // sq / sacc / scores are rewritten by the next layer; everyone is done with the TMEM rows
-    if (layer + 1 < L) stage(layer + 1);
+    if (layer + 1 < L) {
+      // The staging loads (up to 24 outstanding 16-B loads per thread) share the SM's load path with the consumers' LL polling:
+      // issued right away they sit in front of the o_proj-output gather and delay it by ~2 us. Hold them until the consumers are
+      // inside the gate/up weight phase (22 us without a single global load of theirs; staging takes 8-13 us).
+      if (atid == 0 && !(p.debug_flags & 32)) {
+        uint32_t spins = 0;
+        while (*s_step < PH_STEPS * layer + PH_GATEUP) {
+          __nanosleep(200);
+          if (++spins > EMX_SPIN_LIMIT) __trap();
+        }
+      }
+      abar();
+      stage(layer + 1);
+    }
     if (PROF) t_q += ts1 - ts0, t_old += ts2 - ts1, t_pre += global_ns() - ts4;
   }
   if (PROF && dbg) dbg[0] = t_q, dbg[1] = t_old, dbg[2] = t_new, dbg[3] = t_pub, dbg[4] = t_sc, dbg[5] = t_sm, dbg[6] = t_pre;
@@ -873,6 +886,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   uint32_t* s_rope = reinterpret_cast<uint32_t*>(s_table + DEC_MAX_PAGES);  // [32] cos pairs | [32] sin pairs of this position (bf16)
   static_assert((64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP + DEC_MAX_RESID + 56 + DEC_MAX_PAGES + 64) * 4 <= DEC_MISC_BYTES, "misc area overflow");
   float* att_red = misc + 48;  // [9] attention warps: per-warp maxima / sums, score of the new key
+  volatile int* s_step = reinterpret_cast<volatile int*>(misc + 58);  // consumers -> attention warps: the (layer, phase) step being consumed
   float* att_sm = reinterpret_cast<float*>(smem + DEC_STAGES * DEC_STAGE_BYTES + ATT_SM_OFFSET);
   static_assert(ATT_SM_OFFSET + ATT_SM_FLOATS * 4 <= DEC_XS_BYTES, "attention scratch exceeds the activation area");
 
@@ -893,6 +907,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     s_state[3] = static_cast<int>(ldg_cg_u32(&st->finished));
     s_state[4] = static_cast<int>(ldg_cg_u32(&st->epoch));
     s_issued[0] = 0, s_issued[1] = 0;
+    *reinterpret_cast<volatile int*>(misc + 58) = -1;
     for (int s = 0; s < DEC_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], DEC_CWARPS);
@@ -919,7 +934,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     return;
   }
   if (warp >= DEC_CWARPS) {
-    attention_loop<PROF>(p, s_table, s_rope, pos, tag0, check, att_sm, att_red, reinterpret_cast<uint32_t*>(misc + 60), tid - DEC_CTHREADS);
+    attention_loop<PROF>(p, s_table, s_rope, pos, tag0, check, att_sm, att_red, reinterpret_cast<uint32_t*>(misc + 60), s_step, tid - DEC_CTHREADS);
     return;
   }
 
@@ -977,6 +992,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
       cbar();
     }  // PH_K, PH_V: same input vector as PH_Q
     mark();
+    if (tid == 0) *s_step = step;
     consume_phase<PROF>(phase_desc(tab, layer, kind), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
                         p.debug_flags, [&](int row, float a0, float a1, bool valid) {
                           // lanes 0..7 of warp 0, converged; `kind` is uniform
