@@ -491,7 +491,7 @@ struct ConsumerState {
 __device__ __forceinline__ void part_arrive(uint32_t buf) { asm volatile("bar.arrive %0, %1;" ::"r"(2u + buf), "n"(DEC_CTHREADS) : "memory"); }
 __device__ __forceinline__ void part_sync(uint32_t buf) { asm volatile("bar.sync %0, %1;" ::"r"(2u + buf), "n"(DEC_CTHREADS) : "memory"); }
 
-// epi(row, v0, v1, valid) is called for row pairs (row even) by lanes 0..7 of warp 0 (all eight, converged), rows ascending
+// epi(row, v0, v1, valid) is called for row pairs (row even) by lanes 0..7 of ONE warp per row group (all eight lanes, converged), rows ascending
 // per lane; valid == false marks lanes beyond the last row of a short group
 template <bool PROF, typename Epi>
 __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t* ring, uint64_t* full, uint64_t* empty, ConsumerState& cs,
@@ -553,7 +553,9 @@ __device__ __forceinline__ void consume_phase(const PhaseDesc& d, const uint8_t*
       pb[warp * DEC_GROUP + (lane >> 2)] = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
       pb[warp * DEC_GROUP + (lane >> 2) + 8] = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]);
     }
-    if (warp == 0) {
+    // the epilogue duty rotates over the warps (group g -> warp g % 8): the ring slot of a stage is released by the SLOWEST warp, so a
+    // fixed epilogue warp would trail the others by one epilogue per row group and hold every slot that much longer
+    if (warp == static_cast<int>(cs.group % DEC_CWARPS)) {
       const long long t1 = PROF ? clock64() : 0;
       part_sync(buf);
       const long long t2 = PROF ? clock64() : 0;
@@ -876,7 +878,6 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   uint2* ln_s = reinterpret_cast<uint2*>(smem + DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128);
   float* red = misc;                                 // [8]
   int* s_state = reinterpret_cast<int*>(misc + 16);  // [5]
-  float* s_best = misc + 32;                         // [8] values + [8] indices
   float* part = misc + 64;                           // [DEC_PARTBUFS][8 warps][16 rows] partial row sums
   uint32_t* s_resid = reinterpret_cast<uint32_t*>(misc + 64 + DEC_PARTBUFS * DEC_CWARPS * DEC_GROUP);  // [DEC_MAX_RESID] residual bf16 pairs of this CTA's rows
   volatile uint32_t* s_issued = reinterpret_cast<volatile uint32_t*>(misc + 24);  // [2] producers -> prefetch warp
@@ -1025,13 +1026,15 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   mark();
   if (PROF && dbg && tid == 0) dbg[15 * L + 4] = gprof[0], dbg[15 * L + 5] = gprof[1], dbg[15 * L + 6] = gprof[2], dbg[15 * L + 7] = gprof[3];
   if (PROF && dbg && tid == 0) dbg[15 * L + 8] = cs.waited, dbg[15 * L + 11] = cs.t_sync, dbg[15 * L + 12] = cs.t_epi;
-  if (warp == 0 && lane < 8) s_best[lane] = best, reinterpret_cast<int*>(s_best + 8)[lane] = best_i;
+  cbar();  // every epilogue is done: the partial-sum buffers are free
+  float* s_best = part;  // [64] values + [64] indices: lanes 0..7 of every warp hold candidates (rotating epilogue duty)
+  if (lane < 8) s_best[warp * 8 + lane] = best, reinterpret_cast<int*>(s_best + 64)[warp * 8 + lane] = best_i;
   cbar();
   uint64_t* cand = static_cast<uint64_t*>(p.argmax_part);  // [grid][2] LL units: value bits, index
   if (tid == 0) {
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < 64; ++w) {
       const float v = s_best[w];
-      const int i = reinterpret_cast<int*>(s_best + 8)[w];
+      const int i = reinterpret_cast<int*>(s_best + 64)[w];
       if (v > best || (v == best && i < best_i)) best = v, best_i = i;
     }
     ll_store(cand + 2 * blockIdx.x, __float_as_uint(best), tag0 + L + 1);
