@@ -126,6 +126,18 @@ __device__ __forceinline__ uint32_t ll_wait(const uint64_t* unit, uint32_t tag, 
   return static_cast<uint32_t>(v);
 }
 
+// two units at once: both loads are in flight before the first tag is checked (one L2 round trip instead of two when both are there)
+__device__ __forceinline__ void ll_wait2(const uint64_t* ua, const uint64_t* ub, uint32_t tag, bool check, uint32_t& a, uint32_t& b) {
+  uint64_t va = ll_load(ua), vb = ll_load(ub);
+  uint32_t spins = 0;
+  while (check && (static_cast<uint32_t>(va >> 32) != tag || static_cast<uint32_t>(vb >> 32) != tag)) {
+    if (static_cast<uint32_t>(va >> 32) != tag) va = ll_load(ua);
+    if (static_cast<uint32_t>(vb >> 32) != tag) vb = ll_load(ub);
+    if (++spins > EMX_SPIN_LIMIT) __trap();
+  }
+  a = static_cast<uint32_t>(va), b = static_cast<uint32_t>(vb);
+}
+
 // Gather a whole vector of `n_units` (even) LL units tagged `tag`: thread t takes the unit pairs t, t + 256, ...; all loads of a
 // chunk of MAXP pairs are in flight before the first tag is checked, pairs that are not there yet are re-polled.
 // sink(u, word) is called exactly once per unit (by the thread that fetched it).
@@ -714,7 +726,8 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
     // rotate_half partners (2t+64, 2t+65)
     if (awarp == 0) {
       const uint64_t* src = qkv + head * HALF;
-      const uint32_t lo = ll_wait(src + lane, tag, check), hi = ll_wait(src + lane + 32, tag, check);
+      uint32_t lo, hi;
+      ll_wait2(src + lane, src + lane + 32, tag, check, lo, hi);
       const float x1a = bf16_lo(lo), x1b = bf16_hi(lo), x2a = bf16_lo(hi), x2b = bf16_hi(hi);
       const uint32_t cw = s_rope[lane], sw = s_rope[32 + lane];  // bf16 cos / sin of this position
       const float ca = bf16_lo(cw), cb = bf16_hi(cw), sa = bf16_lo(sw), sb = bf16_hi(sw);
@@ -781,10 +794,39 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
       if (atid < HALF) ll_store(mine + 2 + 2 * atid, __float_as_uint(n0), tag), ll_store(mine + 3 + 2 * atid, __float_as_uint(n1), tag);
       if (atid == 0) ll_store(mine, __float_as_uint(m), tag), ll_store(mine + 1, __float_as_uint(l), tag);
     } else {
+      // ---- the other splits' partials first: they are published while the k/v rows are still being projected, so merging them
+      // now keeps their L2 round trip off the critical path (a split with l == 0 is empty)
+      float M = (l > 0.f) ? m : -INFINITY, den = l;
+      if (atid < HALF) {
+#pragma unroll 1
+        for (int s0 = 0; s0 < S - 1; s0 += 3) {  // up to three other splits at a time: all six unit pairs in flight before the first tag check
+          const int cnt = min(3, S - 1 - s0);
+          uint32_t w[12];
+          ll_fetch_pairs<6>(
+              [&](int i) -> const uint64_t* {
+                const uint64_t* ph = part + (s0 + min(i >> 1, cnt - 1)) * (DEC_HD + 2);
+                return (i & 1) ? ph + 2 + 2 * atid : ph;
+              },
+              w, tag, check);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float ms = __uint_as_float(w[4 * c]), ls = __uint_as_float(w[4 * c + 1]);
+            if (c < cnt && ls > 0.f) {
+              const float Mn = fmaxf(M, ms);
+              const float wo = (M == -INFINITY) ? 0.f : __expf(M - Mn), wn = __expf(ms - Mn);
+              n0 = n0 * wo + __uint_as_float(w[4 * c + 2]) * wn, n1 = n1 * wo + __uint_as_float(w[4 * c + 3]) * wn, den = den * wo + ls * wn;
+              M = Mn;
+            }
+          }
+        }
+      }
+      const long long ts3 = PROF ? global_ns() : 0;
+      if (PROF) t_pub += ts3 - ts2;
       // ---- the token being decoded: k (warp 0) and v (warp 1) arrive at the end of the projection
       if (awarp < 2) {
         const uint64_t* src = qkv + (awarp + 1) * (H / 2) + head * HALF;
-        const uint32_t lo = ll_wait(src + lane, tag, check), hi = ll_wait(src + lane + 32, tag, check);
+        uint32_t lo, hi;
+        ll_wait2(src + lane, src + lane + 32, tag, check, lo, hi);
         const long dst = kv_addr(p, s_table, layer, head).row(pos);
         if (awarp == 1) {
           sm[ATT_SVNEW + 2 * lane] = bf16_lo(lo), sm[ATT_SVNEW + 2 * lane + 1] = bf16_hi(lo);
@@ -806,39 +848,16 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
         }
       }
       abar();
-      const long long ts3 = PROF ? global_ns() : 0;
-      if (PROF) t_new += ts3 - ts2;
+      if (PROF) t_new += global_ns() - ts3;
       if (atid < HALF) {
-        // one online-softmax step with the new key, then the other splits' partials (a split with l == 0 is empty)
+        // one online-softmax step with the new key
         const float s_new = red[8];
-        float M = fmaxf(m, s_new);
-        const float wo0 = (l > 0.f) ? __expf(m - M) : 0.f, pn = __expf(s_new - M), pb = bf16_round(pn);
-        n0 = n0 * wo0 + pb * sm[ATT_SVNEW + 2 * atid], n1 = n1 * wo0 + pb * sm[ATT_SVNEW + 2 * atid + 1];
-        float den = l * wo0 + pn;
-#pragma unroll 1
-        for (int s0 = 0; s0 < S - 1; s0 += 3) {  // up to three other splits at a time: all six unit pairs in flight before the first tag check
-          const int cnt = min(3, S - 1 - s0);
-          uint32_t w[12];
-          ll_fetch_pairs<6>(
-              [&](int i) -> const uint64_t* {
-                const uint64_t* ph = part + (s0 + min(i >> 1, cnt - 1)) * (DEC_HD + 2);
-                return (i & 1) ? ph + 2 + 2 * atid : ph;
-              },
-              w, tag, check);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float ms = __uint_as_float(w[4 * c]), ls = __uint_as_float(w[4 * c + 1]);
-            if (c < cnt && ls > 0.f) {
-              const float Mn = fmaxf(M, ms);
-              const float wo = __expf(M - Mn), wn = __expf(ms - Mn);
-              n0 = n0 * wo + __uint_as_float(w[4 * c + 2]) * wn, n1 = n1 * wo + __uint_as_float(w[4 * c + 3]) * wn, den = den * wo + ls * wn;
-              M = Mn;
-            }
-          }
-        }
+        const float Mn = fmaxf(M, s_new);
+        const float wo = (M == -INFINITY) ? 0.f : __expf(M - Mn), pn = __expf(s_new - Mn), pb = bf16_round(pn);
+        n0 = n0 * wo + pb * sm[ATT_SVNEW + 2 * atid], n1 = n1 * wo + pb * sm[ATT_SVNEW + 2 * atid + 1];
+        den = den * wo + pn;
         ll_store(static_cast<uint64_t*>(p.attn) + head * HALF + atid, pack_bf16(n0 / den, n1 / den), tag);
       }
-      if (PROF) t_pub += global_ns() - ts3;
     }
     const long long ts4 = PROF ? global_ns() : 0;
     abar();  // sq / sacc / scores are rewritten by the next layer; everyone is done with the TMEM rows
