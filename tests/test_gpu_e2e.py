@@ -130,6 +130,86 @@ def test_tiny_vs_live_oracle_teacher_forced(tiny):
             assert ours[t] == forced[t], f"step {t}: argmax differs although the oracle margin {margin[t]:.3g} > {2 * tol:.3g}"
 
 
+def test_from_pretrained_directory_round_trip(tiny, tmp_path):
+    """`AutoModelForVision2Seq.from_pretrained(dir)` + `AutoProcessor.from_pretrained(dir)` on a HF-export-shaped directory
+    (config.json, sharded safetensors + index, dataset_statistics.json; convert_openvla_weights_to_hf.py:244-250, openvla_utils.py:43-70)
+    must give the same tokens and action as the in-memory model built from the same state dict."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from emmax_b200 import AutoModelForVision2Seq, AutoProcessor, tiny_config
+    from emmax_b200.synthetic import make_state_dict
+
+    model, tok, g, input_ids, script = tiny
+    cfg = tiny_config()
+    sd = make_state_dict(cfg, seed=0, device="cpu", script=script, script_prev=int(input_ids[0, -1]))
+    d = str(tmp_path / "ckpt")
+    cfg.save_pretrained(d)
+    names = sorted(sd)
+    shards = {"model-00001-of-00002.safetensors": names[: len(names) // 2], "model-00002-of-00002.safetensors": names[len(names) // 2 :]}
+    for fn, keys in shards.items():
+        save_file({k: sd[k].to(BF).contiguous() for k in keys}, os.path.join(d, fn))
+    with open(os.path.join(d, "model.safetensors.index.json"), "w") as f:
+        json.dump({"metadata": {}, "weight_map": {k: fn for fn, keys in shards.items() for k in keys}}, f)
+    stats = {"bridge_orig": {"action": {"q01": [-0.5] * 7, "q99": [0.5] * 7, "mask": [True] * 6 + [False]}}}
+    with open(os.path.join(d, "dataset_statistics.json"), "w") as f:
+        json.dump(stats, f)
+    loaded = AutoModelForVision2Seq.from_pretrained(d, attn_implementation="flash_attention_2", torch_dtype=BF, low_cpu_mem_usage=True,
+                                                    trust_remote_code=True).to("cuda")  # fmt: skip
+    assert loaded.norm_stats == stats and loaded.get_action_dim("bridge_orig") == 7
+    proc = AutoProcessor.from_pretrained(d, trust_remote_code=True)
+    pv = torch.from_numpy(g["pixel_values"]).to("cuda", BF)
+    n_new = len(script)
+    a, _ = loaded.engine.generate(input_ids.cuda(), pv, n_new, eos_token_id=2)
+    b, _ = model.engine.generate(input_ids.cuda(), pv, n_new, eos_token_id=2)
+    assert a.cpu().tolist() == b.cpu().tolist() == g["generated_ids"][0, input_ids.shape[1] :].tolist()
+    inputs = {"input_ids": input_ids.cuda(), "pixel_values": pv}
+    act, text = loaded.generate_actions(inputs, proc.tokenizer, do_sample=False, max_new_tokens=n_new)
+    act2, text2 = model.generate_actions(inputs, tok, do_sample=False, max_new_tokens=n_new)
+    assert text == text2 and act.shape == (7,)
+    # same normalised action, un-normalised with the directory's statistics (mask: last dim passes through)
+    from emmax_b200.solver import unnormalize
+
+    norm, _ = model.solver.extract_action_policies(text2)
+    want = unnormalize(np.asarray(norm[0], dtype=np.float64), stats["bridge_orig"]["action"])
+    assert np.array_equal(np.asarray(act, dtype=np.float64), want)
+
+
+@pytest.mark.parametrize("n_ids", [300, 730])
+def test_tiny_long_context_vs_oracle(tiny, n_ids):
+    """Long prompts: 256 + n_ids prefill positions + 24 new tokens, i.e. contexts of ~580 and ~1010 of the 1024-position capacity.
+    Each kv-split of the decode kernel then holds 3 and 4 64-key passes (TMEM staging, multi-pass softmax) instead of the 1-2
+    the 40-id prompts exercise. Teacher-forced logits against the oracle on this GPU, every step."""
+    from emmax_b200 import OpenVLAForActionPrediction, tiny_config
+    from emmax_b200.synthetic import make_state_dict
+    from oracle.model import OracleVLA
+
+    _, _, g, _, _ = tiny
+    cfg = tiny_config()
+    sd = make_state_dict(cfg, seed=4, device="cpu")
+    oracle = OracleVLA.from_state_dict(cfg, sd, device="cuda", dtype=BF, attn_implementation="sdpa")
+    model = OpenVLAForActionPrediction(cfg, dict(sd)).to("cuda")
+    pv = torch.from_numpy(g["pixel_values"]).to("cuda", BF)
+    rng = np.random.default_rng(n_ids)
+    input_ids = torch.tensor([[1] + rng.integers(3, cfg.text_config.vocab_size - 64, n_ids - 1).tolist()], dtype=torch.long, device="cuda")
+    n_new = 24
+    ids_o, logits_o = oracle.generate(input_ids, pv, n_new, eos_token_id=None, return_logits=True)
+    forced = ids_o[0, input_ids.shape[1] :].tolist()
+    new, logits = model.engine.generate(input_ids, pv, n_new, eos_token_id=None, return_logits=True, forced=forced)
+    err = _rel_err(logits.cpu(), logits_o)
+    assert err < 1e-2, f"teacher-forced logits at context {256 + n_ids}+: max|diff| / max|logit| = {err:.4g} (tolerance 1e-2)"
+    top2 = logits_o.topk(2, dim=-1).values
+    margin = (top2[:, 0] - top2[:, 1]).numpy()
+    tol = 2e-2 * float(logits_o.abs().max())
+    ours = new.cpu().numpy()
+    for t in range(n_new):
+        if margin[t] > 2 * tol:
+            assert ours[t] == forced[t], f"step {t}: argmax differs although the oracle margin {margin[t]:.3g} > {2 * tol:.3g}"
+    with pytest.raises(ValueError):  # capacity is checked, not silently truncated
+        model.engine.generate(input_ids, pv, 1024, eos_token_id=None)
+
+
 @pytest.mark.parametrize("n_new", [64])
 def test_full_size_vs_live_oracle(n_new):
     """Full Emma-X architecture (DINOv2-L + SigLIP-so400m + Llama-2-7B shapes), seeded synthetic weights generated on the
