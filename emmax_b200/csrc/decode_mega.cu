@@ -199,25 +199,17 @@ __device__ __forceinline__ void ll_fetch_pairs(Addr&& addr, uint32_t (&out)[2 * 
   for (int i = 0; i < NP; ++i) out[2 * i] = static_cast<uint32_t>(a[i]), out[2 * i + 1] = static_cast<uint32_t>(b[i]);
 }
 
-__device__ __forceinline__ float cblock_sum(float v, float* red) {
+// Block sum over the 8 consumer warps with ONE barrier: per-warp partials go to one of two 8-float buffers (alternating per call, so
+// the next call's writes cannot overtake a slow reader of this call: there is at least one block barrier between two calls), every
+// thread adds the 8 partials itself.
+__device__ __forceinline__ float cblock_sum(float v, float* red, uint32_t parity) {
   v = warp_sum(v);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) red[warp] = v;
+  float* r = red + 8 * (parity & 1);
+  if (lane == 0) r[warp] = v;
   cbar();
-  float t = (lane < DEC_CWARPS) ? red[lane] : 0.f;
-  t = warp_sum(t);
-  cbar();
-  return t;
-}
-__device__ __forceinline__ float cblock_max(float v, float* red) {
-  v = warp_max(v);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) red[warp] = v;
-  cbar();
-  float t = (lane < DEC_CWARPS) ? red[lane] : -INFINITY;
-  t = warp_max(t);
-  cbar();
-  return t;
+  const float4 a = *reinterpret_cast<const float4*>(r), b = *reinterpret_cast<const float4*>(r + 4);
+  return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
 }
 
 // Activation vector layout in shared memory: inside every block of 16 words (32 bf16) the 4 x 4 word matrix is transposed.
@@ -247,7 +239,7 @@ __device__ __forceinline__ void ln_fetch_async(const __nv_bfloat16* w, uint2* ln
 // `ln_s` by ln_fetch_async; own(u, word) sees every raw word once.
 template <typename Own>
 __device__ __forceinline__ void gather_rmsnorm(const uint64_t* ll, const uint32_t* plain, int H, uint32_t tag, bool check,
-                                               const uint2* ln_s, float eps, uint32_t* xs, float* red, Own&& own, long long* prof = nullptr) {
+                                               const uint2* ln_s, float eps, uint32_t* xs, float* red, uint32_t parity, Own&& own, long long* prof = nullptr) {
   const long long tp0 = prof ? clock64() : 0;
   constexpr int MAXP = 4;
   const int n_pairs = H >> 2;
@@ -292,7 +284,7 @@ __device__ __forceinline__ void gather_rmsnorm(const uint64_t* ll, const uint32_
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXP; ++i) ss += sumsq2(static_cast<uint32_t>(a[i])) + sumsq2(static_cast<uint32_t>(b[i]));  // absent pairs are 0
-  const float rs = 1.0f / sqrtf(cblock_sum(ss, red) / H + eps);
+  const float rs = 1.0f / sqrtf(cblock_sum(ss, red, parity) / H + eps);
   const long long tp3 = prof ? clock64() : 0;
 #pragma unroll
   for (int i = 0; i < MAXP; ++i) {
@@ -998,7 +990,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     if (kind == PH_Q || kind == PH_GATEUP || kind == PH_LMHEAD) {
       // ---- residual stream in + RMSNorm ----
       const uint64_t* src = (kind == PH_GATEUP) ? xo : xd;
-      gather_rmsnorm(src, step == 0 ? emb_row : nullptr, H, tag, check, ln_s, p.rms_eps, xs, red, own, (PROF && dbg && tid == 0) ? gprof : nullptr);
+      gather_rmsnorm(src, step == 0 ? emb_row : nullptr, H, tag, check, ln_s, p.rms_eps, xs, red, kind == PH_GATEUP ? 1u : 0u, own, (PROF && dbg && tid == 0) ? gprof : nullptr);
       if (kind != PH_LMHEAD) {  // norm weights of the next RMSNorm: ln2 of this layer, ln1 of the next one, the final norm
         const __nv_bfloat16* next_w = (kind == PH_Q)     ? static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H
                                       : (layer + 1 < L) ? static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer + 1) * H
