@@ -11,6 +11,10 @@
 // bias / GELU / LayerScale / residual / SwiGLU chain with the SAME bf16 rounding points as the unfused torch-eager
 // reference (each reference op output is bf16).
 //
+// Persistent: one CTA per SM walks the output tiles (M index fastest, so neighbouring CTAs share the W tile in L2); the fp32
+// accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so the epilogue of tile i (TMEM read-out, fused math, global stores)
+// overlaps the TMA / MMA main loop of tile i + 1 — the short-K ViT GEMMs (16-18 k-blocks per tile) were epilogue-bound without it.
+//
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue.
 #include "common.cuh"
 #include "emmax.h"
@@ -48,12 +52,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty = full + Cfg::kStages;
-  uint64_t* tmem_full = empty + Cfg::kStages;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + Cfg::kStages;  // [2] MMA -> epilogue: accumulator buffer complete
+  uint64_t* tmem_empty = tmem_full + 2;        // [2] epilogue -> MMA: accumulator buffer read out
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int nkb = (K + BK - 1) / BK;
+  const int mt = (M + BM - 1) / BM, n_tiles = mt * ((N + BN - 1) / BN);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -64,10 +69,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);  // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_holder, BN);
+  if (warp == 2) tmem_alloc(tmem_holder, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -75,49 +83,64 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sa = smem + s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-        tma_load_2d(sa, &tmA, kb * BK, m0, &full[s]);
-        tma_load_2d(sa + Cfg::kABytes, &tmB, kb * BK, n0, &full[s]);
+      uint32_t it = 0;  // ring iteration, continues across tiles: the producer runs ahead into the next tile
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmA, kb * BK, m0, &full[s]);
+          tma_load_2d(sa + Cfg::kABytes, &tmB, kb * BK, n0, &full[s]);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+        mbar_wait(&tmem_empty[buf], bph ^ 1);  // the epilogue has read this accumulator buffer out (first two uses: free)
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + Cfg::kABytes);
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + Cfg::kABytes);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 elements (32 B) along K inside the 128-B swizzle span: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle span: +2 in the (addr >> 4) field
+            umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[s]);  // smem slot reusable once these MMAs retire
         }
-        umma_commit(&empty[s]);  // smem slot reusable once these MMAs retire
+        umma_commit(&tmem_full[buf]);  // accumulator complete
       }
-      umma_commit(tmem_full);  // accumulator complete
     }
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp - 4;  // TMEM lane quarter this warp may read
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int m = m0 + q * 32 + lane;
     const bool has_bias = ep.bias != nullptr, has_ls = ep.ls != nullptr, has_res = ep.resid != nullptr;
     const bool do_gelu = ep.flags & EMX_EPI_GELU, do_swiglu = ep.flags & EMX_EPI_SWIGLU;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+    const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+    const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+    mbar_wait(&tmem_full[buf], bph);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
     const long rrow = has_res ? static_cast<long>(ep.resid_mod > 0 ? m % ep.resid_mod : m) * ep.ldr : 0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 32, r);
       tmem_ld_wait();
       const int nb = n0 + c * 32;
       if (m >= M || nb >= N) continue;
@@ -171,12 +194,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    // this warp's quarter of the accumulator buffer is read out: hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -223,8 +251,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat
     EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  gemm_tn_kernel<BN><<<grid, 256, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
+  const int n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  gemm_tn_kernel<BN><<<n_tiles < kNumSMs ? n_tiles : kNumSMs, 256, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
