@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     fence_mbar_init();
   }
   __syncthreads();
-  const int token = s_state[0], pos = s_state[1], n_gen = s_state[2];
+  const int token = min(max(s_state[0], 0), p.vocab - 1), pos = s_state[1], n_gen = s_state[2];  // (clamped: a profiling mode that skips the LL waits may have written garbage)
   if (s_state[3]) return;  // sequence already hit EOS: nothing to do (uniform across the grid)
 
   const int L = p.layers, H = p.hidden;

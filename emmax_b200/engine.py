@@ -54,6 +54,7 @@ class Engine:
         self.max_context = _ceil_to(max_context, self.PAGE)
         self._graphs: Dict[Tuple[int, int], Tuple[torch.cuda.CUDAGraph, int]] = {}
         self.last_decode = None
+        self._side: Optional[torch.cuda.Stream] = None  # second vision tower at small batch
         with torch.cuda.device(device):
             self._pack(state_dict)
             self._alloc()
@@ -183,26 +184,44 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------------------
     def _vision(self, ws: dict, B: int) -> None:
-        """pixels [B,6,h,w] -> feats [B*P, vision_dim]  (modeling_prismatic.py:114-123)"""
+        """pixels [B,6,h,w] -> feats [B*P, vision_dim]  (modeling_prismatic.py:114-123).
+        The two towers are independent until their features are concatenated: at small batch neither fills the GPU
+        (24-96 CTAs per GEMM), so the second tower runs on a side stream (fork / join with stream waits, which a CUDA-graph
+        capture records as parallel branches)."""
+        main = torch.cuda.current_stream()
+        d0 = self.vits[0].dims.embed_dim
+        if len(self.vits) == 2 and B * self.vits[0].dims.num_tokens < 4096:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)  # fork (after the pixel upload on `main`)
+            with torch.cuda.stream(self._side):
+                self._vision_tower(ws, B, 1, d0)
+            self._vision_tower(ws, B, 0, 0)
+            main.wait_stream(self._side)  # join
+        else:
+            col0 = 0
+            for i, vw in enumerate(self.vits):
+                self._vision_tower(ws, B, i, col0)
+                col0 += vw.dims.embed_dim
+
+    def _vision_tower(self, ws: dict, B: int, i: int, col0: int) -> None:
         cfg = self.config
         P, side = cfg.num_patches, cfg.image_sizes[0]
-        col0 = 0
-        for i, vw in enumerate(self.vits):
-            v, w = vw.dims, ws[f"v{i}"]
-            D, T, hd = v.embed_dim, v.num_tokens, v.head_dim
-            call("emx_patch_im2col", ptr(ws["pixels"]), B, 6, 3 * i, side, side, v.patch_size, ptr(w["im2col"]), vw.kpad, stream())
-            self.gemm(w["im2col"], vw.w_pe, w["pe"], bias=vw.b_pe)
-            call("emx_vit_assemble", ptr(w["pe"]), ptr(vw.pos), ptr(vw.prefix), ptr(w["tok"]), B, P, v.num_prefix_tokens, D, stream())
-            for blk in vw.blocks:
-                call("emx_layernorm", ptr(w["tok"]), ptr(blk["norm1.weight"]), ptr(blk["norm1.bias"]), ptr(w["n"]), B * T, D, v.ln_eps, stream())
-                self.gemm(w["n"], blk["attn.qkv.weight"], w["qkv"], bias=blk["attn.qkv.bias"])
-                call("emx_attn_fwd", ptr(w["qkv"]), ptr(w["att"]), B, T, v.num_heads, hd, 0, hd**-0.5, stream())
-                self.gemm(w["att"], blk["attn.proj.weight"], w["tok"], bias=blk["attn.proj.bias"], ls=blk.get("ls1.scale_factor"), resid=w["tok"])
-                call("emx_layernorm", ptr(w["tok"]), ptr(blk["norm2.weight"]), ptr(blk["norm2.bias"]), ptr(w["n"]), B * T, D, v.ln_eps, stream())
-                self.gemm(w["n"], blk["mlp.fc1.weight"], w["hid"], bias=blk["mlp.fc1.bias"], flags=EPI_GELU)
-                self.gemm(w["hid"], blk["mlp.fc2.weight"], w["tok"], bias=blk["mlp.fc2.bias"], ls=blk.get("ls2.scale_factor"), resid=w["tok"])
-            call("emx_vit_gather_features", ptr(w["tok"]), ptr(ws["feats"]), B, P, v.num_prefix_tokens, D, cfg.vision_embed_dim, col0, stream())
-            col0 += D
+        vw = self.vits[i]
+        v, w = vw.dims, ws[f"v{i}"]
+        D, T, hd = v.embed_dim, v.num_tokens, v.head_dim
+        call("emx_patch_im2col", ptr(ws["pixels"]), B, 6, 3 * i, side, side, v.patch_size, ptr(w["im2col"]), vw.kpad, stream())
+        self.gemm(w["im2col"], vw.w_pe, w["pe"], bias=vw.b_pe)
+        call("emx_vit_assemble", ptr(w["pe"]), ptr(vw.pos), ptr(vw.prefix), ptr(w["tok"]), B, P, v.num_prefix_tokens, D, stream())
+        for blk in vw.blocks:
+            call("emx_layernorm", ptr(w["tok"]), ptr(blk["norm1.weight"]), ptr(blk["norm1.bias"]), ptr(w["n"]), B * T, D, v.ln_eps, stream())
+            self.gemm(w["n"], blk["attn.qkv.weight"], w["qkv"], bias=blk["attn.qkv.bias"])
+            call("emx_attn_fwd", ptr(w["qkv"]), ptr(w["att"]), B, T, v.num_heads, hd, 0, hd**-0.5, stream())
+            self.gemm(w["att"], blk["attn.proj.weight"], w["tok"], bias=blk["attn.proj.bias"], ls=blk.get("ls1.scale_factor"), resid=w["tok"])
+            call("emx_layernorm", ptr(w["tok"]), ptr(blk["norm2.weight"]), ptr(blk["norm2.bias"]), ptr(w["n"]), B * T, D, v.ln_eps, stream())
+            self.gemm(w["n"], blk["mlp.fc1.weight"], w["hid"], bias=blk["mlp.fc1.bias"], flags=EPI_GELU)
+            self.gemm(w["hid"], blk["mlp.fc2.weight"], w["tok"], bias=blk["mlp.fc2.bias"], ls=blk.get("ls2.scale_factor"), resid=w["tok"])
+        call("emx_vit_gather_features", ptr(w["tok"]), ptr(ws["feats"]), B, P, v.num_prefix_tokens, D, cfg.vision_embed_dim, col0, stream())
 
     def _projector(self, ws: dict) -> None:
         """fc1 -> GELU -> fc2 -> GELU -> fc3  (modeling_prismatic.py:152-156)"""
