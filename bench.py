@@ -13,7 +13,8 @@ A "step" is one complete action request: one synthetic 224x224 image + a fixed 4
 
 `value`  : actions/s with inputs already resident in HBM (engine.generate on device tensors).
 `e2e`    : actions/s through the public API (`model.generate_actions(inputs, tokenizer, ...)`) from PINNED HOST
-           buffers: H2D of pixels+ids, D2H of the generated ids, host text decode + Solver parse, every step.
+           buffers: H2D of the raw uint8 frame + ids, GPU image transform, D2H of the generated ids, host text decode +
+           Solver parse, every step.
 `roofline`: the decode-step kernel (99 % of a step): algorithmic bytes per launch / measured launch duration vs the
            measured HBM peak in MEASURED_PEAKS.json.
 """
@@ -213,11 +214,12 @@ def run_ours(args) -> None:
     # request stream: rank r serves frames r, r+N, ...; same fixed prompt
     def request(i: int):
         image, ids = synthetic_request(rank + i * world)
-        return proc.image_processor(image, return_tensors="pt")["pixel_values"].to(torch.bfloat16), ids
+        return proc.image_processor(image, return_tensors="pt")["pixel_values"].to(torch.bfloat16), ids, torch.from_numpy(np.asarray(image).copy())
 
     reqs = [request(i) for i in range(W + K)]
-    d_reqs = [(pv.to(dev), ids.to(dev)) for pv, ids in reqs]
-    h_reqs = [(pv.pin_memory(), ids.pin_memory()) for pv, ids in reqs]
+    d_reqs = [(pv.to(dev), ids.to(dev)) for pv, ids, _ in reqs]
+    # e2e inputs: the RAW uint8 frame (224x224x3, as the robot loop delivers it) + prompt ids, in pinned host memory
+    h_reqs = [(frame.pin_memory(), ids.pin_memory()) for _, ids, frame in reqs]
     gathered = torch.zeros((world, 8), dtype=torch.int32, device=dev)
     act_lo = script.index(tok.key_id("POLICIES:")) + 2  # first policy's 7 action tokens
 
@@ -271,8 +273,10 @@ def run_ours(args) -> None:
     last_action = [None]
 
     def step_e2e(i: int) -> None:
-        pv, ids = h_reqs[i]
-        inputs = {"input_ids": ids.to(dev, non_blocking=True), "pixel_values": pv.to(dev, non_blocking=True)}
+        frame, ids = h_reqs[i]
+        # H2D of the raw frame + ids, image transform on the GPU (emx_preprocess_u8: bit-exact twin of the host processor)
+        inputs = {"input_ids": ids.to(dev, non_blocking=True),
+                  "pixel_values": proc.image_processor.preprocess_device(frame.to(dev, non_blocking=True))}
         action, text = model.generate_actions(inputs, proc.tokenizer, do_sample=False, max_new_tokens=N_NEW)
         if world > 1:
             tick_gather(eng.d_out_tokens)
@@ -280,7 +284,7 @@ def run_ours(args) -> None:
 
     e2e_ms, _ = timed(step_e2e, 1, K)
     e2e_value = world * K / (e2e_ms / 1e3)
-    h2d = reqs[0][0].numel() * 2 + reqs[0][1].numel() * 8
+    h2d = reqs[0][2].numel() + reqs[0][1].numel() * 8
     d2h = N_NEW * 4 + 4
 
     # ---- per-token latency distribution (untimed extra pass, events around every launch) ---------------------------

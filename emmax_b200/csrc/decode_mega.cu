@@ -127,10 +127,12 @@ __device__ __forceinline__ uint32_t ll_wait(const uint64_t* unit, uint32_t tag, 
 }
 
 // two units at once: both loads are in flight before the first tag is checked (one L2 round trip instead of two when both are there)
+template <bool BACKOFF = false>
 __device__ __forceinline__ void ll_wait2(const uint64_t* ua, const uint64_t* ub, uint32_t tag, bool check, uint32_t& a, uint32_t& b) {
   uint64_t va = ll_load(ua), vb = ll_load(ub);
   uint32_t spins = 0;
   while (check && (static_cast<uint32_t>(va >> 32) != tag || static_cast<uint32_t>(vb >> 32) != tag)) {
+    if (BACKOFF) __nanosleep(96);  // long waits (tens of us): do not burn issue slots and L2 requests spinning
     if (static_cast<uint32_t>(va >> 32) != tag) va = ll_load(ua);
     if (static_cast<uint32_t>(vb >> 32) != tag) vb = ll_load(ub);
     if (++spins > EMX_SPIN_LIMIT) __trap();
@@ -719,7 +721,7 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
     if (awarp == 0) {
       const uint64_t* src = qkv + head * HALF;
       uint32_t lo, hi;
-      ll_wait2(src + lane, src + lane + 32, tag, check, lo, hi);
+      ll_wait2<true>(src + lane, src + lane + 32, tag, check, lo, hi);  // ~40 us of waiting per layer
       const float x1a = bf16_lo(lo), x1b = bf16_hi(lo), x2a = bf16_lo(hi), x2b = bf16_hi(hi);
       const uint32_t cw = s_rope[lane], sw = s_rope[32 + lane];  // bf16 cos / sin of this position
       const float ca = bf16_lo(cw), cb = bf16_hi(cw), sa = bf16_lo(sw), sb = bf16_hi(sw);

@@ -285,6 +285,26 @@ __global__ void detok_kernel(const int32_t* __restrict__ ids, int n, int vocab, 
   }
 }
 
+
+// uint8 HWC frame -> the [6, H, W] bf16 tensor the two ViT towers eat, for frames that already have the model's input size (the robot
+// path pre-resizes, experiments/robot/bridge/bridgev2_utils.py:152-166; `resize-naive` on a 224x224 input is the identity).
+// Per backbone b (DINOv2 first, then SigLIP), channel c: torchvision's to_tensor + normalize in fp32, op by op, then the bf16 cast of
+// `.to(device, dtype=bfloat16)`: bf16(((float(u8) / 255) - mean[b][c]) / std[b][c])  — processing_prismatic.py:128-145.
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ hwc, __nv_bfloat16* __restrict__ out, int HW, int n_backbones,
+                                     const float* __restrict__ mean, const float* __restrict__ stdv) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const uint8_t* px = hwc + (static_cast<long>(b) * HW + i) * 3;
+    for (int k = 0; k < n_backbones; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(px[c]), 255.0f), mean[3 * k + c]), stdv[3 * k + c]);
+        out[(static_cast<long>(b) * 3 * n_backbones + 3 * k + c) * HW + i] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
 }  // namespace emx
 
 using namespace emx;
@@ -305,6 +325,14 @@ extern "C" int emx_layernorm(const void* x, const void* w, const void* b, void* 
 extern "C" int emx_rmsnorm(const void* x, const void* w, void* y, int rows, int dim, float eps, cudaStream_t s) {
   EMX_REQUIRE(rows > 0 && dim % 8 == 0, "emx_rmsnorm: rows=%d dim=%d (dim must be a multiple of 8)", rows, dim);
   rmsnorm_kernel<<<rows, 256, 0, s>>>(BF(x), BF(w), BFM(y), dim, eps);
+  EMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int emx_preprocess_u8(const void* hwc, int B, int H, int W, int n_backbones, const float* mean, const float* stdv, void* out,
+                                 cudaStream_t s) {
+  EMX_REQUIRE(B > 0 && H > 0 && W > 0 && n_backbones >= 1 && n_backbones <= 2, "emx_preprocess_u8: B=%d H=%d W=%d backbones=%d", B, H, W, n_backbones);
+  EMX_REQUIRE(hwc && mean && stdv && out, "emx_preprocess_u8: null pointer");
+  preprocess_u8_kernel<<<dim3((H * W + 255) / 256, B), 256, 0, s>>>(static_cast<const uint8_t*>(hwc), BFM(out), H * W, n_backbones, mean, stdv);
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

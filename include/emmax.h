@@ -49,6 +49,12 @@ int emx_rmsnorm(const void* x, const void* weight, void* y, int rows, int dim, f
  * Patch-embed conv as im2col + GEMM (timm PatchEmbed.proj = Conv2d(3,D,14,14), invoked at modeling_prismatic.py:121).
  * pixels: [B, C_total, H, W] bf16; channels [chan0, chan0+3) are gathered into rows of (c,ky,kx)-ordered patches,
  * zero-padded to `kpad` columns: out [B*gh*gw, kpad]. */
+/* GPU twin of PrismaticImageProcessor.apply_transform for frames that already have the model's input size
+ * (processing_prismatic.py:128-145: to_tensor -> normalize per backbone -> channel stack; then `.to(device, bf16)`):
+ * hwc uint8 [B, H, W, 3] (device) -> out bf16 [B, 3*n_backbones, H, W]; mean/stdv: device fp32 [n_backbones*3]. Bit-exact with the
+ * host transform followed by the bf16 cast. */
+int emx_preprocess_u8(const void* hwc, int B, int H, int W, int n_backbones, const float* mean, const float* stdv, void* out,
+                      emx_stream_t stream);
 int emx_patch_im2col(const void* pixels, int B, int c_total, int chan0, int H, int W, int patch, void* out, int kpad, emx_stream_t stream);
 /* tokens[b, 0:prefix] = prefix_tokens; tokens[b, prefix+i] = bf16(patch_out[b,i] + pos[i])  (timm _pos_embed) */
 int emx_vit_assemble(const void* patch_out, const void* pos, const void* prefix_tokens, void* tokens, int B, int n_patches, int prefix,

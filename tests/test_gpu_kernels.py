@@ -214,3 +214,22 @@ def test_detokenize_bit_exact(lib, golden_dir):
     norm, act = torch.empty(7, dtype=torch.float64, device="cuda"), torch.empty(7, dtype=torch.float64, device="cuda")
     call("emx_detokenize_actions", ptr(ids), 7, g["vocab_size"], 256, ptr(q01), ptr(q99), ptr(mask), 7, ptr(norm), ptr(act), stream())
     assert np.array_equal(act.cpu().numpy(), np.array([float.fromhex(x) for x in u["actions_hex"]]))
+
+
+def test_preprocess_u8_bit_exact(lib):
+    """GPU image transform == host PrismaticImageProcessor (torchvision to_tensor + normalize per backbone) + bf16 cast, bit for bit."""
+    from PIL import Image
+
+    from emmax_b200 import PrismaticImageProcessor
+
+    proc = PrismaticImageProcessor()
+    rng = np.random.default_rng(7)
+    frames = rng.integers(0, 256, (3, 224, 224, 3), dtype=np.uint8)
+    frames[0, :4] = 0
+    frames[0, 4:8] = 255  # extremes
+    want = torch.stack([proc.apply_transform(Image.fromarray(f)) for f in frames]).to(BF)
+    got = proc.preprocess_device(torch.from_numpy(frames).cuda())
+    assert got.shape == (3, 6, 224, 224) and got.dtype == BF
+    assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16)), "device transform must be bit-exact with the host transform"
+    with pytest.raises(ValueError):
+        proc.preprocess_device(torch.zeros((1, 256, 256, 3), dtype=torch.uint8, device="cuda"))
