@@ -20,6 +20,8 @@ Third-party arithmetic that is NOT in /root/reference (pins from requirements-mi
 PARITY PINNING: the reference has no tests, fixtures or golden vectors for the neural path, and it
 cannot be imported here (no timm/draccus/tensorflow; gated tokenizer), so for ViT / projector / Llama arithmetic this
 oracle is **parity unpinned** (anchored only on the reference's call sites and on the third-party classes themselves).
+The ViT restatement is additionally cross-checked against an independent implementation of the same architectures
+(`transformers.Dinov2WithRegistersModel`, `transformers.SiglipVisionModel`; tests/test_oracle_vit_crosscheck.py).
 The integer/fp64 de-tokeniser and the Solver text parser ARE pinned: `oracle/gen_golden.py` imports
 `prismatic/vla/action_tokenizer.py` and executes the `Solver` class source of `prismatic/vla/solver.py` from
 /root/reference and freezes their outputs in `tests/golden/detok_golden.json`.
