@@ -614,7 +614,8 @@ __device__ __forceinline__ KvAddr kv_addr(const emx_decode_params& p, const int3
 //      there by then — and publishes the head's output.
 // The consumers only ever see the finished attention vector (ll_gather before o_proj).
 constexpr int ATT_PASS = 64;                     // keys per pass: 2 threads per key (K), 4 key slices x 32 quads (V)
-constexpr int ATT_MAX_PASSES = 4;                // <= 256 cached keys per split (host-checked)
+constexpr int ATT_MAX_PASSES = 8;                // <= 512 cached keys per split (host-checked): contexts up to 2048 = the reference's llm_max_length
+constexpr int ATT_KPT = ATT_PASS * ATT_MAX_PASSES / DEC_ATHREADS;  // keys per thread in the softmax-statistics step
 constexpr int ATT_SQ = 0, ATT_SQ2 = 68 /* second half of q, skewed by 4 banks */, ATT_SVNEW = 136, ATT_SACC = 264 /*[4][128]*/, ATT_SSCORE = 776;
 constexpr int ATT_SM_FLOATS = ATT_SSCORE + ATT_PASS * ATT_MAX_PASSES;  // 1032 floats
 constexpr int ATT_SM_OFFSET = 16384;             // inside the activation area: bytes [16 K, 22 K) are only used by the down_proj input
@@ -747,16 +748,30 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
       }
       abar();
       if (PROF) t_sc += global_ns() - ts1;
-      // softmax statistics over the cached keys: thread t owns keys t and t + 128
-      const float s0 = (atid < n_old) ? sm[ATT_SSCORE + atid] : -INFINITY, s1 = (atid + DEC_ATHREADS < n_old) ? sm[ATT_SSCORE + atid + DEC_ATHREADS] : -INFINITY;
-      const float wm = warp_max(fmaxf(s0, s1));
+      // softmax statistics over the cached keys: thread t owns keys t, t + 128, ...
+      float sv[ATT_KPT];
+      float wm = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < ATT_KPT; ++i) {
+        const int k = atid + i * DEC_ATHREADS;
+        sv[i] = (k < n_old) ? sm[ATT_SSCORE + k] : -INFINITY;
+        wm = fmaxf(wm, sv[i]);
+      }
+      wm = warp_max(wm);
       if (lane == 0) red[awarp] = wm;
       abar();
       m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-      const float p0 = (atid < n_old) ? __expf(s0 - m) : 0.f, p1 = (atid + DEC_ATHREADS < n_old) ? __expf(s1 - m) : 0.f;
-      if (atid < n_old) sm[ATT_SSCORE + atid] = bf16_round(p0);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
-      if (atid + DEC_ATHREADS < n_old) sm[ATT_SSCORE + atid + DEC_ATHREADS] = bf16_round(p1);
-      const float wl = warp_sum(p0 + p1);
+      float wl = 0.f;
+#pragma unroll
+      for (int i = 0; i < ATT_KPT; ++i) {
+        const int k = atid + i * DEC_ATHREADS;
+        if (k < n_old) {
+          const float pk = __expf(sv[i] - m);
+          wl += pk;
+          sm[ATT_SSCORE + k] = bf16_round(pk);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
+        }
+      }
+      wl = warp_sum(wl);
       if (lane == 0) red[4 + awarp] = wl;
       abar();  // also publishes the probabilities
       l = (red[4] + red[5]) + (red[6] + red[7]);

@@ -74,7 +74,7 @@ class OpenVLAForActionPrediction:
     config_class = OpenVLAConfig
 
     def __init__(self, config: OpenVLAConfig, state_dict: Dict[str, torch.Tensor], tokenizer: Any = None,
-                 max_context: int = 1024, max_batch: int = 1) -> None:  # fmt: skip
+                 max_context: int = 2048, max_batch: int = 1) -> None:  # fmt: skip
         if config.use_fused_vision_backbone is None:
             raise ValueError("Missing config field `use_fused_vision_backbone`")
         self.config = config

@@ -176,11 +176,11 @@ def test_from_pretrained_directory_round_trip(tiny, tmp_path):
     assert np.array_equal(np.asarray(act, dtype=np.float64), want)
 
 
-@pytest.mark.parametrize("n_ids", [300, 730])
+@pytest.mark.parametrize("n_ids", [300, 730, 1700])
 def test_tiny_long_context_vs_oracle(tiny, n_ids):
-    """Long prompts: 256 + n_ids prefill positions + 24 new tokens, i.e. contexts of ~580 and ~1010 of the 1024-position capacity.
-    Each kv-split of the decode kernel then holds 3 and 4 64-key passes (TMEM staging, multi-pass softmax) instead of the 1-2
-    the 40-id prompts exercise. Teacher-forced logits against the oracle on this GPU, every step."""
+    """Long prompts: 256 + n_ids prefill positions + 24 new tokens, i.e. contexts of ~580, ~1010 and ~1980 of the 2048-position
+    capacity (the reference's llm_max_length). Each kv-split of the decode kernel then holds 3, 4 and 8 64-key passes (TMEM staging,
+    multi-pass softmax) instead of the 1-2 the 40-id prompts exercise. Teacher-forced logits against the oracle on this GPU, every step."""
     from emmax_b200 import OpenVLAForActionPrediction, tiny_config
     from emmax_b200.synthetic import make_state_dict
     from oracle.model import OracleVLA
@@ -207,7 +207,7 @@ def test_tiny_long_context_vs_oracle(tiny, n_ids):
         if margin[t] > 2 * tol:
             assert ours[t] == forced[t], f"step {t}: argmax differs although the oracle margin {margin[t]:.3g} > {2 * tol:.3g}"
     with pytest.raises(ValueError):  # capacity is checked, not silently truncated
-        model.engine.generate(input_ids, pv, 1024, eos_token_id=None)
+        model.engine.generate(input_ids, pv, 4096, eos_token_id=None)
 
 
 @pytest.mark.parametrize("n_new", [64])
