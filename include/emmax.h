@@ -89,10 +89,11 @@ int emx_lmhead_argmax(const void* W, int ldw, const void* x, int N, int K, float
                       emx_stream_t stream);
 
 /* ---- persistent decode step ---------------------------------------------------------------------------------
- * ONE launch = one new token for one sequence: embedding gather, 32 x (RMSNorm + QKV GEMV + RoPE + paged-KV append +
+ * ONE launch = one new token for one sequence: embedding gather, 32 x (RMSNorm + q|k|v GEMV + RoPE + paged-KV append +
  * split-KV attention + o_proj + residual + RMSNorm + gate/up GEMV + SwiGLU + down GEMV + residual), final norm,
- * lm_head GEMV + greedy argmax, all inside one persistent kernel (1 CTA/SM) that streams the 13.2 GB of weights through
- * a bulk-async (TMA) shared-memory ring. There are no grid barriers: CTAs exchange activation vectors as 8-byte
+ * lm_head GEMV + greedy argmax, all inside one persistent kernel (1 CTA/SM, 512 threads: consumer, attention, producer and
+ * L2-prefetch warps) that streams the 13.2 GB of weights through a bulk-async (TMA) shared-memory ring; the attention warps
+ * stage the cached K/V rows of their (head, split) item in tensor memory a layer ahead. Contexts up to 2048 (kv_splits = 4). There are no grid barriers: CTAs exchange activation vectors as 8-byte
  * "LL units" {2 x bf16 payload | 32-bit tag} (single 64-bit stores, polling 64-bit loads; tag = launch epoch x layer).
  * Replaces the cached branch of PrismaticForConditionalGeneration.forward (modeling_prismatic.py:325-341) + one
  * iteration of GenerationMixin's greedy loop (called at modeling_prismatic.py:519). */
@@ -142,14 +143,17 @@ typedef struct emx_decode_params {
   int32_t eos_token;    /* -1 disables EOS handling */
   int32_t kv_splits;
   emx_decode_state* state;
-  /* optional profiling buffer (device, >= 15*layers + 16 + grid int64): CTA 0 stores %globaltimer at every phase boundary,
-   * then [15*layers + 8 ..] = cycles warp 0 waited for weights / cycles the producer waited for a free ring slot */
+  /* optional profiling buffer (device, >= 15*layers + 16 + 2*grid + 8 int64; selects the instrumented twin of the kernel): CTA 0 stores
+   * %globaltimer at every phase boundary (12 per layer), then [15*layers + 4 ..] = gather/RMSNorm cycle counters, cycles the consumers
+   * waited for weights / the producers for a free ring slot, bytes prefetched to L2, per-CTA end-of-layer-1 times, and the attention
+   * warps' per-layer timings of CTA 0 (tools/decode_probe.py decodes it) */
   int64_t* dbg;
   /* per-CTA look-ahead (KiB) of cp.async.bulk.prefetch.L2 beyond the shared-memory ring; 0 disables (148 CTAs x 256 KiB
-   * = 37 MB of the 126 MB L2 keeps HBM streaming through grid barriers and the attention phase) */
+   * = 37 MB of the 126 MB L2 keeps HBM streaming while the consumers wait for an exchange and the ring is full) */
   int32_t l2_lookahead_kb;
-  /* profiling only (results become garbage): 1 = do not wait for LL tags, 2 = skip attention (needs 1), 4 = no L2 evict-first
-   * hint, 64 = skip the MMAs, bits 8.. = prefetch pace in 10 ns per 64 KB (default 700 ns) */
+  /* profiling only (results become garbage for 1, 2, 16, 64): 1 = do not wait for LL tags, 2 = skip attention (needs 1), 4 = no L2
+   * evict-first hint, 8 = L2 prefetch also in catch-up mode, 16 = drop LL stores, 32 = stage the next layer's K/V into TMEM immediately,
+   * 64 = skip the MMAs, bits 8..19 / 20.. = idle / catch-up prefetch pace in 10 ns per 64 KB (defaults 700 / 1300 ns) */
   int32_t debug_flags;
 } emx_decode_params;
 
