@@ -6,27 +6,28 @@
 // ~10^3 kernel launches per token, a full re-copy of the KV cache (DynamicCache torch.cat) and a host sync.
 //
 // B200 design (HBM-bound: 13.2 GB of bf16 weights per token):
-//   * grid = one CTA per SM (148), 8 consumer warps + 2 producer warps + 1 L2-prefetch warp, launched cooperatively
-//     (co-residency is what makes the spin-waits below safe);
-//   * the producer warps walk the STATIC weight schedule of their CTA (layer -> qkv, o, gate/up, down -> 16-row group ->
+//   * grid = one CTA per SM (148) x 512 threads at 128 registers: 8 consumer warps + 4 attention warps + 2 producer warps +
+//     1 L2-prefetch warp (+ 1 idle), launched cooperatively (co-residency is what makes the spin-waits below safe);
+//   * the producer warps walk the STATIC weight schedule of their CTA (layer -> q, k, v, o, gate/up, down -> 16-row group ->
 //     2048-column chunk) and keep a 3 x 64 KB shared-memory ring full with cp.async.bulk (TMA engine) copies, 16 x 4 KB per
 //     instruction, L2 evict-first. Producers never wait for anything but a free ring slot;
 //   * consumers: the 16 rows x 2048 columns of a stage are A operands of mma.sync.m16n8k16 (bf16, fp32 accumulate); each warp
 //     owns a 256-column slice (ldmatrix from a 16-B padded, conflict-free row stride), the activation vector is the B operand
 //     (one 16-B shared load per two k-steps thanks to a permuted layout), four independent accumulator chains; per-warp partial
-//     row sums are handed to warp 0 through named barriers. Measured: skipping the MMAs altogether changes the kernel time by
-//     3 % — the consumer is far from being the limit;
+//     row sums are handed to a ROTATING epilogue warp through named barriers (a fixed one would trail the others and hold
+//     every ring slot longer);
 //   * NO GRID BARRIERS. A 148-CTA barrier costs ~1.9 us on B200 even on an idle memory system (tools/skeleton_probe.py) and a
-//     decode step needs 160 of them. Instead every cross-CTA vector (qkv, attention output, residual stream, SwiGLU output,
+//     decode step needs 160 of them. Instead every cross-CTA vector (q|k|v, attention output, residual stream, SwiGLU output,
 //     split-KV partials, argmax candidates) travels as 8-byte "LL" units {2 x bf16 | 32-bit tag} written with one 64-bit
 //     store and read with polling 64-bit loads: data and flag arrive atomically, so no fence, no atomic and no barrier is
 //     needed; a consumer waits exactly for the words it needs, ~one L2 round trip after they were produced. The tag encodes
 //     (launch epoch, layer), so stale words of the previous layer / token never match. Reuse of a buffer is safe without
 //     further synchronisation because every phase gathers a COMPLETE vector before it produces anything (see ll_gather);
 //   * RMSNorm is recomputed per CTA from the 8 KB residual vector (cheaper than an extra exchange);
-//   * attention: (head, kv-split) items across CTAs start as soon as THEIR q/k/v rows have arrived (no global wait), RoPE + KV
-//     append fused in, lane-per-key scores with all row loads in flight at once, split 0 of each head combines;
-//   * an L2-prefetch warp keeps HBM busy while the consumers stall (attention, exchanges) and the ring is full.
+//   * attention runs on its OWN warps, concurrently with the consumers (see "attention warps" below): q rows are projected
+//     first, the cached-key work happens in the shadow of the k/v weight stream out of K/V rows staged in TENSOR MEMORY a layer
+//     ahead, and only the new token's k/v -> owner split -> head output -> o_proj chain is left on the critical path;
+//   * an L2-prefetch warp keeps HBM busy while the consumers wait for an exchange and the ring is full.
 // Rounding points mirror the torch-eager reference (bf16 after every Linear / norm / residual add / activation).
 #include "common.cuh"
 #include "emmax.h"
