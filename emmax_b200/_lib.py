@@ -57,6 +57,7 @@ _SIGNATURES = {
     "emx_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "emx_rmsnorm": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "emx_preprocess_u8": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "emx_resize_preprocess_u8": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "emx_patch_im2col": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "emx_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "emx_vit_gather_features": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

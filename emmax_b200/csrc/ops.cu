@@ -305,6 +305,60 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ hwc, __nv_bfloa
   }
 }
 
+// PIL's antialiased resample (Pillow src/libImaging/Resample.c, ImagingResampleHorizontal/Vertical_8bpc) — what torchvision's
+// `resize(PIL image, interpolation=BICUBIC, antialias=True)` runs at processing_prismatic.py:133 — restated in its own integer
+// arithmetic so the GPU result is bit-identical: two separable passes with a uint8 intermediate, 22-bit fixed-point coefficients
+// (computed on the host exactly as precompute_coeffs / normalize_coeffs_8bpc do), accumulator seeded with 1 << 21, arithmetic shift,
+// clamp to [0, 255].
+__global__ void resample_h_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int rows, int Win, int Wout,
+                                     const int32_t* __restrict__ kk, const int32_t* __restrict__ bounds, int ksize) {
+  // one thread per (row, output column); 3 interleaved channels
+  const long n = static_cast<long>(rows) * Wout;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(i % Wout);
+    const long r = i / Wout;
+    const int xmin = bounds[2 * xx], xmax = bounds[2 * xx + 1];
+    const int32_t* k = kk + static_cast<long>(xx) * ksize;
+    const uint8_t* px = in + (r * Win + xmin) * 3;
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+    for (int x = 0; x < xmax; ++x) {
+      const int w = k[x];
+      s0 += px[3 * x] * w, s1 += px[3 * x + 1] * w, s2 += px[3 * x + 2] * w;
+    }
+    uint8_t* o = out + i * 3;
+    o[0] = static_cast<uint8_t>(min(max(s0 >> 22, 0), 255));
+    o[1] = static_cast<uint8_t>(min(max(s1 >> 22, 0), 255));
+    o[2] = static_cast<uint8_t>(min(max(s2 >> 22, 0), 255));
+  }
+}
+// vertical pass fused with to_tensor + per-backbone normalize + bf16 cast (see preprocess_u8_kernel)
+__global__ void resample_v_norm_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, int Hin, int Hout, int W,
+                                       const int32_t* __restrict__ kk, const int32_t* __restrict__ bounds, int ksize, int n_backbones,
+                                       const float* __restrict__ mean, const float* __restrict__ stdv) {
+  const int b = blockIdx.y;
+  const int HW = Hout * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const int yy = i / W, x = i % W;
+    const int ymin = bounds[2 * yy], ymax = bounds[2 * yy + 1];
+    const int32_t* k = kk + static_cast<long>(yy) * ksize;
+    const uint8_t* px = in + ((static_cast<long>(b) * Hin + ymin) * W + x) * 3;
+    int s[3] = {1 << 21, 1 << 21, 1 << 21};
+    for (int y = 0; y < ymax; ++y) {
+      const int w = k[y];
+      const uint8_t* q = px + static_cast<long>(y) * W * 3;
+      s[0] += q[0] * w, s[1] += q[1] * w, s[2] += q[2] * w;
+    }
+    for (int kb = 0; kb < n_backbones; ++kb) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float u8 = static_cast<float>(min(max(s[c] >> 22, 0), 255));
+        const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(u8, 255.0f), mean[3 * kb + c]), stdv[3 * kb + c]);
+        out[(static_cast<long>(b) * 3 * n_backbones + 3 * kb + c) * HW + i] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
 }  // namespace emx
 
 using namespace emx;
@@ -325,6 +379,20 @@ extern "C" int emx_layernorm(const void* x, const void* w, const void* b, void* 
 extern "C" int emx_rmsnorm(const void* x, const void* w, void* y, int rows, int dim, float eps, cudaStream_t s) {
   EMX_REQUIRE(rows > 0 && dim % 8 == 0, "emx_rmsnorm: rows=%d dim=%d (dim must be a multiple of 8)", rows, dim);
   rmsnorm_kernel<<<rows, 256, 0, s>>>(BF(x), BF(w), BFM(y), dim, eps);
+  EMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int emx_resize_preprocess_u8(const void* hwc, int B, int Hin, int Win, int Hout, int Wout, const int32_t* kk_h,
+                                        const int32_t* bounds_h, int ksize_h, const int32_t* kk_v, const int32_t* bounds_v, int ksize_v,
+                                        void* tmp, int n_backbones, const float* mean, const float* stdv, void* out, cudaStream_t s) {
+  EMX_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && n_backbones >= 1 && n_backbones <= 2,
+              "emx_resize_preprocess_u8: B=%d in=%dx%d out=%dx%d backbones=%d", B, Hin, Win, Hout, Wout, n_backbones);
+  EMX_REQUIRE(hwc && kk_h && bounds_h && kk_v && bounds_v && tmp && mean && stdv && out, "emx_resize_preprocess_u8: null pointer");
+  const long n = static_cast<long>(B) * Hin * Wout;
+  resample_h_u8_kernel<<<static_cast<unsigned>(min((n + 255) / 256, 4096L)), 256, 0, s>>>(static_cast<const uint8_t*>(hwc), static_cast<uint8_t*>(tmp),
+                                                                                          B * Hin, Win, Wout, kk_h, bounds_h, ksize_h);
+  resample_v_norm_kernel<<<dim3((Hout * Wout + 255) / 256, B), 256, 0, s>>>(static_cast<const uint8_t*>(tmp), BFM(out), Hin, Hout, Wout, kk_v, bounds_v,
+                                                                          ksize_v, n_backbones, mean, stdv);
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

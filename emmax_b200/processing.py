@@ -64,6 +64,65 @@ def letterbox_pad_transform(image: Image.Image, padding_fill_value: Tuple[int, i
     return TVF.pad(image, (pw, ph, pw, ph), fill=padding_fill_value, padding_mode="constant")
 
 
+def pil_bicubic_coeffs(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Coefficient table of Pillow's antialiased bicubic resample for one axis (src/libImaging/Resample.c: `precompute_coeffs` with
+    `bicubic_filter` (a = -0.5, support 2) + `normalize_coeffs_8bpc`, PRECISION_BITS = 22), which is what torchvision's
+    `resize(PIL image, BICUBIC, antialias=True)` executes at processing_prismatic.py:133. Returns (kk int32 [out_size, ksize],
+    bounds int32 [out_size, 2] = (first input index, number of taps)). Same double-precision operations in the same order, so
+    the integer coefficients are identical to Pillow's (tests/test_detok_host.py pins the resulting resize against PIL itself)."""
+    import math
+
+    def filt(x: float) -> float:
+        a = -0.5
+        x = -x if x < 0.0 else x
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        if x < 2.0:
+            return (((x - 5) * x + 8) * x - 4) * a
+        return 0.0
+
+    scale = in_size / out_size
+    filterscale = scale if scale >= 1.0 else 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [filt((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x, v in enumerate(w):
+            if ww != 0.0:
+                v = v / ww
+            kk[xx, x] = int(-0.5 + v * (1 << 22)) if v < 0 else int(0.5 + v * (1 << 22))
+        bounds[xx] = (xmin, xmax)
+    return kk, bounds
+
+
+def pil_bicubic_resize_reference(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """numpy twin of the two integer passes (horizontal, then vertical on the uint8 intermediate) — the host-side statement of what
+    `emx_resize_preprocess_u8` computes; used by the CPU tests to pin the coefficient builder against Pillow."""
+
+    def axis_pass(x: np.ndarray, kk: np.ndarray, bounds: np.ndarray, axis: int) -> np.ndarray:
+        x = np.moveaxis(x, axis, 0).astype(np.int64)
+        out = np.empty((kk.shape[0],) + x.shape[1:], dtype=np.uint8)
+        for i in range(kk.shape[0]):
+            lo, n = bounds[i]
+            acc = np.full(x.shape[1:], 1 << 21, dtype=np.int64)
+            for j in range(n):
+                acc += x[lo + j] * int(kk[i, j])
+            out[i] = np.clip(acc >> 22, 0, 255).astype(np.uint8)
+        return np.moveaxis(out, 0, axis)
+
+    x = axis_pass(img, *pil_bicubic_coeffs(img.shape[1], out_w), axis=1)
+    return axis_pass(x, *pil_bicubic_coeffs(img.shape[0], out_h), axis=0)
+
+
 class PrismaticImageProcessor:
     model_input_names = ["pixel_values"]
 
@@ -108,10 +167,11 @@ class PrismaticImageProcessor:
         return torch.vstack(outs)
 
     def preprocess_device(self, frames: torch.Tensor) -> torch.Tensor:
-        """GPU path for frames that already have the model's input size (the robot loop pre-resizes to 224x224,
-        experiments/robot/bridge/bridgev2_utils.py:152-166; `resize-naive` is then the identity): uint8 [B, H, W, 3] or [H, W, 3] on a
-        CUDA device -> bf16 [B, 6, H, W], bit-exact with `preprocess(...)["pixel_values"].to(device, dtype=torch.bfloat16)`. One kernel
-        (`emx_preprocess_u8`) replaces PIL -> float -> normalize on the host and cuts the upload from 602 KB to 150 KB per frame."""
+        """GPU twin of `apply_transform` for the `resize-naive` strategy (Emma-X: conf/models.py:494): uint8 [B, H, W, 3] or [H, W, 3]
+        on a CUDA device -> bf16 [B, 6, 224, 224], bit-exact with `preprocess(...)["pixel_values"].to(device, dtype=torch.bfloat16)`.
+        Frames already at the input size (the robot loop pre-resizes, bridgev2_utils.py:152-166) take one kernel (`emx_preprocess_u8`);
+        other sizes (256x256 sim frames, run_bridgev2_eval.py:161) go through Pillow's antialiased bicubic resample restated in its
+        own integer arithmetic (`emx_resize_preprocess_u8`). Replaces PIL -> float -> normalize on the host and uploads the raw frame."""
         from ._lib import call, ptr, stream
 
         if frames.dim() == 3:
@@ -119,19 +179,36 @@ class PrismaticImageProcessor:
         if frames.dtype != torch.uint8 or frames.device.type != "cuda" or frames.shape[-1] != 3:
             raise ValueError("preprocess_device expects a uint8 CUDA tensor [B, H, W, 3]")
         B, H, W, _ = frames.shape
-        if self.image_resize_strategy != "resize-naive" or any(tuple(s[-2:]) != (H, W) for s in self.input_sizes):
-            raise ValueError(f"preprocess_device handles frames already at the input size {self.input_sizes}; got {H}x{W} "
-                             f"({self.image_resize_strategy}): use the host transform")  # fmt: skip
-        frames = frames.contiguous()
         n = len(self.input_sizes)
-        key = (str(frames.device), n)
+        Ho, Wo = self.input_sizes[0][-2:]
+        if self.image_resize_strategy != "resize-naive" or any(tuple(s[-2:]) != (Ho, Wo) for s in self.input_sizes):
+            raise ValueError(f"preprocess_device implements the `resize-naive` strategy with one common input size; got "
+                             f"{self.image_resize_strategy} / {self.input_sizes}: use the host transform")  # fmt: skip
+        if (H, W) != (Ho, Wo) and any(i != "bicubic" for i in self.interpolations):
+            raise ValueError(f"preprocess_device resizes with Pillow's antialiased bicubic only; got {self.interpolations}")
+        frames = frames.contiguous()
+        dev = frames.device
+        key = (str(dev), n)
         if getattr(self, "_dev_stats", {}).get("key") != key:
             self._dev_stats = {"key": key,
-                               "mean": torch.tensor([c for m in self.means for c in m], dtype=torch.float32, device=frames.device),
-                               "std": torch.tensor([c for m in self.stds for c in m], dtype=torch.float32, device=frames.device)}  # fmt: skip
-        out = torch.empty((B, 3 * n, H, W), dtype=torch.bfloat16, device=frames.device)
-        with torch.cuda.device(frames.device):
-            call("emx_preprocess_u8", ptr(frames), B, H, W, n, ptr(self._dev_stats["mean"]), ptr(self._dev_stats["std"]), ptr(out), stream())
+                               "mean": torch.tensor([c for m in self.means for c in m], dtype=torch.float32, device=dev),
+                               "std": torch.tensor([c for m in self.stds for c in m], dtype=torch.float32, device=dev)}  # fmt: skip
+        out = torch.empty((B, 3 * n, Ho, Wo), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            if (H, W) == (Ho, Wo):
+                call("emx_preprocess_u8", ptr(frames), B, H, W, n, ptr(self._dev_stats["mean"]), ptr(self._dev_stats["std"]), ptr(out), stream())
+            else:
+                ck = (str(dev), H, W, Ho, Wo)
+                tabs = getattr(self, "_dev_resample", {})
+                if ck not in tabs:  # Pillow's coefficient tables for this geometry, built once on the host
+                    kh, bh = pil_bicubic_coeffs(W, Wo)
+                    kv, bv = pil_bicubic_coeffs(H, Ho)
+                    tabs[ck] = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (kh, bh, kv, bv))
+                    self._dev_resample = tabs
+                kh, bh, kv, bv = tabs[ck]
+                tmp = torch.empty((B, H, Wo, 3), dtype=torch.uint8, device=dev)
+                call("emx_resize_preprocess_u8", ptr(frames), B, H, W, Ho, Wo, ptr(kh), ptr(bh), kh.shape[1], ptr(kv), ptr(bv), kv.shape[1],
+                     ptr(tmp), n, ptr(self._dev_stats["mean"]), ptr(self._dev_stats["std"]), ptr(out), stream())  # fmt: skip
         return out
 
     def preprocess(self, images: Union[Image.Image, List[Image.Image]], return_tensors: Optional[str] = None, **_: Any) -> BatchFeature:

@@ -55,6 +55,13 @@ int emx_rmsnorm(const void* x, const void* weight, void* y, int rows, int dim, f
  * host transform followed by the bf16 cast. */
 int emx_preprocess_u8(const void* hwc, int B, int H, int W, int n_backbones, const float* mean, const float* stdv, void* out,
                       emx_stream_t stream);
+/* The same with the `resize-naive` bicubic-antialias resize in front (torchvision resize of a PIL image == Pillow's ImagingResample,
+ * processing_prismatic.py:133): two separable integer passes, bit-exact with Pillow. hwc uint8 [B, Hin, Win, 3]; kk_* int32
+ * [out_size][ksize_*] 22-bit fixed-point coefficients and bounds_* int32 [out_size][2] = (first input index, count), built on the host as
+ * Pillow's precompute_coeffs + normalize_coeffs_8bpc do; tmp uint8 [B, Hin, Wout, 3] scratch; out bf16 [B, 3*n_backbones, Hout, Wout]. */
+int emx_resize_preprocess_u8(const void* hwc, int B, int Hin, int Win, int Hout, int Wout, const int32_t* kk_h, const int32_t* bounds_h,
+                             int ksize_h, const int32_t* kk_v, const int32_t* bounds_v, int ksize_v, void* tmp, int n_backbones,
+                             const float* mean, const float* stdv, void* out, emx_stream_t stream);
 int emx_patch_im2col(const void* pixels, int B, int c_total, int chan0, int H, int W, int patch, void* out, int kpad, emx_stream_t stream);
 /* tokens[b, 0:prefix] = prefix_tokens; tokens[b, prefix+i] = bf16(patch_out[b,i] + pos[i])  (timm _pos_embed) */
 int emx_vit_assemble(const void* patch_out, const void* pos, const void* prefix_tokens, void* tokens, int B, int n_patches, int prefix,

@@ -105,3 +105,19 @@ def test_tokenizer_roundtrip_properties():
     assert tok.decode([1, 29871, 300, 2], skip_special_tokens=True) == "POLICIES:"
     enc = tok(["ab", "a"], return_tensors="pt", padding=True)
     assert enc.input_ids.shape == (2, 4) and enc.attention_mask[1].tolist() == [1, 1, 1, 0]
+
+
+def test_pil_bicubic_restatement_is_bit_exact_with_pillow():
+    """The integer resample the GPU kernel implements (emx_resize_preprocess_u8) is pinned here against Pillow itself — the code
+    torchvision's `resize(PIL image, BICUBIC, antialias=True)` runs in the reference's processor (processing_prismatic.py:133)."""
+    from PIL import Image
+
+    from emmax_b200.processing import pil_bicubic_resize_reference
+
+    rng = np.random.default_rng(0)
+    for h, w in [(256, 256), (480, 640), (224, 224), (200, 300), (97, 131), (720, 1280)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.asarray(Image.fromarray(img).resize((224, 224), Image.BICUBIC))
+        assert np.array_equal(pil_bicubic_resize_reference(img, 224, 224), want), (h, w)
+    flat = np.full((300, 300, 3), 255, dtype=np.uint8)  # saturation: overshoot of the negative lobes must clamp, not wrap
+    assert np.array_equal(pil_bicubic_resize_reference(flat, 224, 224), np.asarray(Image.fromarray(flat).resize((224, 224), Image.BICUBIC)))

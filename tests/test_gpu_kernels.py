@@ -232,4 +232,20 @@ def test_preprocess_u8_bit_exact(lib):
     assert got.shape == (3, 6, 224, 224) and got.dtype == BF
     assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16)), "device transform must be bit-exact with the host transform"
     with pytest.raises(ValueError):
-        proc.preprocess_device(torch.zeros((1, 256, 256, 3), dtype=torch.uint8, device="cuda"))
+        proc.preprocess_device(torch.zeros((1, 224, 224, 3), dtype=torch.float32, device="cuda"))
+
+
+@pytest.mark.parametrize("h,w", [(256, 256), (480, 640), (200, 300)])
+def test_resize_preprocess_u8_bit_exact(lib, h, w):
+    """GPU resize (Pillow's antialiased bicubic in integer arithmetic) + normalise == the host processor, bit for bit, for frames that
+    are not at the model's input size (256x256 sim frames, run_bridgev2_eval.py:161; camera frames)."""
+    from PIL import Image
+
+    from emmax_b200 import PrismaticImageProcessor
+
+    proc = PrismaticImageProcessor()
+    frames = np.random.default_rng(h * w).integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    want = torch.stack([proc.apply_transform(Image.fromarray(f)) for f in frames]).to(BF)
+    got = proc.preprocess_device(torch.from_numpy(frames).cuda())
+    assert got.shape == (2, 6, 224, 224)
+    assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16)), "device resize + transform must be bit-exact with the host processor"
