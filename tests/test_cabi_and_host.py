@@ -102,3 +102,15 @@ def test_config_roundtrip(tmp_path):
     assert back.text_config.vocab_size == 32064 and back.vision_embed_dim == 2176 and back.num_patches == 256
     with pytest.raises(ValueError):
         OpenVLAConfig(vision_backbone_id="clip-vit-l")
+
+
+def test_roofline_denominator_matches_the_survey():
+    """bench.py's algorithmic bytes per decode step are SURVEY.md §8(d) / BASELINE.md §3: 13,214,679,040 B of weights (32 x 202,375,168
+    layer parameters + 131,334,144 lm_head, bf16) + 524,288 B per cached token (KV read) + 524,288 B (KV write)."""
+    import bench
+    from emmax_b200 import emma_x_config
+
+    cfg = emma_x_config()
+    assert bench.decode_bytes(cfg, 0) == 13_214_679_040 + 524_288
+    assert bench.decode_bytes(cfg, 300) - bench.decode_bytes(cfg, 0) == 300 * 524_288
+    assert round(bench.decode_bytes(cfg, 300) / 1e9, 2) == 13.37 and round(bench.decode_bytes(cfg, 812) / 1e9, 2) == 13.64
