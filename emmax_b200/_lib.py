@@ -69,6 +69,7 @@ _SIGNATURES = {
     "emx_lmhead_argmax": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P]),
     "emx_decode_step": (_I, [C.POINTER(DecodeParams), _P]),
     "emx_decode_grid": (_I, []),
+    "emx_decode_phase_rows": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "emx_detokenize_actions": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
     "emx_debug_stream": (_I, [_P, C.c_long, _I, _I, C.c_long, _I, _I, _I, _I, _P]),
     "emx_debug_skeleton": (_I, [_P, C.c_long, _I, _P, _P, _I, _I, _I, C.c_long, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P]),

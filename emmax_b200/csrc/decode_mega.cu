@@ -74,6 +74,15 @@ struct PhaseTab {
   int N[7], K[7], r_begin[7], r_end[7];
 };
 
+// [r_begin, r_end) of an n_rows-row phase owned by CTA `cta` of `grid`: contiguous, balanced to one granule (row pairs are one LL unit;
+// gate/up rows come in quads = two SwiGLU outputs = one LL unit), together covering every row exactly once. Host-callable so that the
+// CPU test suite checks the very formula the kernel uses (emx_decode_phase_rows).
+__host__ __device__ __forceinline__ void phase_rows(int n_rows, uint32_t granule, uint32_t cta, uint32_t grid, int& r_begin, int& r_end) {
+  const uint32_t U = static_cast<uint32_t>(n_rows) / granule;  // U * grid < 2^32
+  r_begin = static_cast<int>(U * cta / grid * granule);
+  r_end = static_cast<int>(U * (cta + 1) / grid * granule);
+}
+
 // Rows of a phase owned by this CTA. Row pairs are never split (one LL unit = one row pair); gate/up rows come in groups of
 // four (two SwiGLU outputs = one LL unit).
 __device__ __forceinline__ void build_phase_tab(const emx_decode_params& p, PhaseTab& t, int kind) {
@@ -87,10 +96,7 @@ __device__ __forceinline__ void build_phase_tab(const emx_decode_params& p, Phas
     case PH_DOWN: t.W[kind] = static_cast<const __nv_bfloat16*>(p.w_down), t.layer_stride[kind] = H * I, t.N[kind] = H, t.K[kind] = I; break;
     default: t.W[kind] = static_cast<const __nv_bfloat16*>(p.lm_head), t.layer_stride[kind] = 0, t.N[kind] = p.vocab, t.K[kind] = H; break;
   }
-  const uint32_t g = (kind == PH_GATEUP) ? 4 : 2;
-  const uint32_t U = t.N[kind] / g;  // U * gridDim.x < 2^32
-  t.r_begin[kind] = static_cast<int>(U * blockIdx.x / gridDim.x * g);
-  t.r_end[kind] = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x * g);
+  phase_rows(t.N[kind], (kind == PH_GATEUP) ? 4 : 2, blockIdx.x, gridDim.x, t.r_begin[kind], t.r_end[kind]);
 }
 
 __device__ __forceinline__ PhaseDesc phase_desc(const PhaseTab& t, int layer, int kind) {
@@ -1098,6 +1104,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
 }  // namespace emx
 
 extern "C" int emx_decode_grid(void) { return emx::kNumSMs; }
+
+extern "C" int emx_decode_phase_rows(int n_rows, int granule, int cta, int grid, int* r_begin, int* r_end) {
+  EMX_REQUIRE(n_rows > 0 && (granule == 2 || granule == 4) && grid > 0 && cta >= 0 && cta < grid && r_begin && r_end && n_rows % granule == 0,
+              "emx_decode_phase_rows: n_rows=%d granule=%d cta=%d grid=%d", n_rows, granule, cta, grid);
+  emx::phase_rows(n_rows, static_cast<uint32_t>(granule), static_cast<uint32_t>(cta), static_cast<uint32_t>(grid), *r_begin, *r_end);
+  return 0;
+}
 
 extern "C" int emx_decode_step(const emx_decode_params* params, cudaStream_t stream) {
   using namespace emx;

@@ -167,6 +167,9 @@ typedef struct emx_decode_params {
 int emx_decode_step(const emx_decode_params* params, emx_stream_t stream);
 /* number of CTAs emx_decode_step launches (== SM count) and its dynamic shared memory, for sizing scratch buffers */
 int emx_decode_grid(void);
+/* host-side view of the kernel's static row partition: rows [*r_begin, *r_end) of an n_rows-row weight phase belong to CTA `cta` of `grid`
+ * (granule 2 = row pairs; 4 = gate/up quads). Runs on the host; used by the CPU tests. */
+int emx_decode_phase_rows(int n_rows, int granule, int cta, int grid, int* r_begin, int* r_end);
 
 /* ---- action de-tokeniser (device twin of ActionTokenizer.decode_token_ids_to_actions + un-normalise) ---------
  * ids [n] int32 -> normalized[n], actions[n] fp64:  k = clip(vocab - id - 1, 0, n_bins-2); c = centres[k];

@@ -114,3 +114,31 @@ def test_roofline_denominator_matches_the_survey():
     assert bench.decode_bytes(cfg, 0) == 13_214_679_040 + 524_288
     assert bench.decode_bytes(cfg, 300) - bench.decode_bytes(cfg, 0) == 300 * 524_288
     assert round(bench.decode_bytes(cfg, 300) / 1e9, 2) == 13.37 and round(bench.decode_bytes(cfg, 812) / 1e9, 2) == 13.64
+
+
+def test_decode_row_partition_covers_every_row_once():
+    """The decode kernel's static schedule: each of the 148 CTAs owns a contiguous run of rows of every weight phase. Checked on the host
+    through the same formula the kernel compiles (emx_decode_phase_rows): the runs tile [0, N) without gaps or overlap, never split an
+    LL unit (row pair; gate/up quad), are balanced to one granule, and the residual-producing phases fit the kernel's staging buffer."""
+    import ctypes as C
+
+    from emmax_b200 import _lib, emma_x_config, tiny_config
+
+    lib = _lib.load()
+    grid = lib.emx_decode_grid()
+    for cfg in (emma_x_config(), tiny_config()):
+        t = cfg.text_config
+        H, I, V = t.hidden_size, t.intermediate_size, t.vocab_size
+        for n_rows, g in ((H, 2), (2 * I, 4), (V, 2)):
+            prev_end, sizes = 0, []
+            for cta in range(grid):
+                b, e = C.c_int(), C.c_int()
+                assert lib.emx_decode_phase_rows(n_rows, g, cta, grid, C.byref(b), C.byref(e)) == 0
+                assert b.value == prev_end and e.value >= b.value and b.value % g == 0 and e.value % g == 0
+                prev_end = e.value
+                sizes.append(e.value - b.value)
+            assert prev_end == n_rows, "all rows covered"
+            assert max(sizes) - min(sizes) <= g, "balanced to one granule"
+        assert max(1, H // 2 // grid + 2) <= 192, "residual pairs of one CTA fit DEC_MAX_RESID"
+    b, e = C.c_int(), C.c_int()
+    assert lib.emx_decode_phase_rows(10, 3, 0, grid, C.byref(b), C.byref(e)) != 0 and b"emx_decode_phase_rows" in lib.emx_last_error()
