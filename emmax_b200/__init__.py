@@ -17,12 +17,13 @@ from .configuration import OpenVLAConfig, PrismaticConfig, emma_x_config, tiny_c
 from .modeling import AutoConfig, AutoModelForVision2Seq, OpenVLAForActionPrediction, PrismaticCausalLMOutputWithPast
 from .processing import AutoImageProcessor, AutoProcessor, BatchFeature, PrismaticImageProcessor, PrismaticProcessor
 from .prompting import PurePromptBuilder, emma_x_prompt, openvla_prompt
+from .simpler_policy import OpenVLAInference
 from .solver import Solver
 from .tokenization import SyntheticLlamaTokenizer
 
 __all__ = [
     "ActionTokenizer", "AutoConfig", "AutoImageProcessor", "AutoModelForVision2Seq", "AutoProcessor", "BatchFeature",
-    "OpenVLAConfig", "OpenVLAForActionPrediction", "PrismaticCausalLMOutputWithPast", "PrismaticConfig",
+    "OpenVLAConfig", "OpenVLAForActionPrediction", "OpenVLAInference", "PrismaticCausalLMOutputWithPast", "PrismaticConfig",
     "PrismaticImageProcessor", "PrismaticProcessor", "PurePromptBuilder", "Solver", "SyntheticLlamaTokenizer",
     "emma_x_config", "emma_x_prompt", "openvla_prompt", "tiny_config",
 ]  # fmt: skip
