@@ -121,3 +121,17 @@ def test_pil_bicubic_restatement_is_bit_exact_with_pillow():
         assert np.array_equal(pil_bicubic_resize_reference(img, 224, 224), want), (h, w)
     flat = np.full((300, 300, 3), 255, dtype=np.uint8)  # saturation: overshoot of the negative lobes must clamp, not wrap
     assert np.array_equal(pil_bicubic_resize_reference(flat, 224, 224), np.asarray(Image.fromarray(flat).resize((224, 224), Image.BICUBIC)))
+
+
+def test_prompt_builder_matches_the_reference_class(golden_dir):
+    """PurePromptBuilder vs the reference's own class (base_prompter.py:28-73, loaded by path and frozen by oracle/gen_golden_prompts.py):
+    per-turn wrapped strings, `get_prompt`, `get_potential_prompt` (which does not consume a turn), `<image>` stripping, empty gpt turns."""
+    g = json.load(open(os.path.join(golden_dir, "prompt_golden.json")))
+    for case in g["cases"]:
+        pb = PurePromptBuilder("prismatic")
+        wrapped = [pb.add_turn(role, msg) for role, msg in case["turns"]]
+        assert wrapped == case["wrapped"] and pb.get_prompt() == case["prompt"]
+        assert pb.get_potential_prompt("next question") == case["potential"] and pb.turn_count == case["turn_count"]
+    with pytest.raises(AssertionError):
+        PurePromptBuilder("prismatic").add_turn("gpt", "out of turn")
+    assert emma_x_prompt("put carrot in pot") == g["cases"][0]["prompt"]
