@@ -22,7 +22,8 @@ cannot be imported here (no timm/draccus/tensorflow; gated tokenizer), so for Vi
 oracle is **parity unpinned** (anchored only on the reference's call sites and on the third-party classes themselves).
 The ViT restatement is additionally cross-checked against an independent implementation of the same architectures
 (`transformers.Dinov2WithRegistersModel`, `transformers.SiglipVisionModel`; tests/test_oracle_vit_crosscheck.py).
-The integer/fp64 de-tokeniser and the Solver text parser ARE pinned: `oracle/gen_golden.py` imports
+The image processor (`gen_golden_processor.py`), the prompt builder (`gen_golden_prompts.py`) and the SimplerEnv policy post-processing
+(`gen_golden_simpler.py`) are pinned the same way as the integer/fp64 de-tokeniser and the Solver text parser: `oracle/gen_golden.py` imports
 `prismatic/vla/action_tokenizer.py` and executes the `Solver` class source of `prismatic/vla/solver.py` from
 /root/reference and freezes their outputs in `tests/golden/detok_golden.json`.
 """

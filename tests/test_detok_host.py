@@ -135,3 +135,32 @@ def test_prompt_builder_matches_the_reference_class(golden_dir):
     with pytest.raises(AssertionError):
         PurePromptBuilder("prismatic").add_turn("gpt", "out of turn")
     assert emma_x_prompt("put carrot in pot") == g["cases"][0]["prompt"]
+
+
+def test_image_processor_matches_the_reference_class(golden_dir):
+    """`PrismaticImageProcessor.apply_transform` vs the reference's own class (processing_prismatic.py:128-145 executed by
+    oracle/gen_golden_processor.py on Pillow + torchvision): all three resize strategies, square / landscape / portrait inputs, the
+    bf16-rounded OpenVLA means/stds. Bit-exact: sha256 of the float32 output bytes."""
+    import hashlib
+
+    import torch
+    from PIL import Image
+
+    from emmax_b200 import PrismaticImageProcessor
+
+    g = json.load(open(os.path.join(golden_dir, "processor_golden.json")))
+    for case in g["cases"]:
+        h, w = case["h"], case["w"]
+        img = Image.fromarray(np.random.default_rng(h * 1000 + w).integers(0, 256, (h, w, 3), dtype=np.uint8))
+        proc = PrismaticImageProcessor(use_fused_vision_backbone=True, image_resize_strategy=case["strategy"], input_sizes=[(3, 224, 224)] * 2,
+                                       interpolations=["bicubic"] * 2, means=[tuple(m) for m in g["means"]], stds=[tuple(s) for s in g["stds"]])  # fmt: skip
+        t = proc.apply_transform(img.convert("RGB")).float().contiguous()
+        assert list(t.shape) == case["shape"], case
+        flat = t.flatten()
+        for i, v in case["probes"].items():
+            assert float(flat[int(i)]) == v, (case["strategy"], h, w, i)
+        assert hashlib.sha256(t.numpy().tobytes()).hexdigest() == case["sha256"], (case["strategy"], h, w)
+    # the defaults of this package are the OpenVLA export values used above
+    d = PrismaticImageProcessor()
+    assert [list(m) for m in d.means] == g["means"] and [list(s) for s in d.stds] == g["stds"] and d.image_resize_strategy == "resize-naive"
+    assert isinstance(d.apply_transform(Image.new("RGB", (300, 200))), torch.Tensor)
