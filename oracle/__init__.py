@@ -17,9 +17,12 @@ Third-party arithmetic that is NOT in /root/reference (pins from requirements-mi
   * transformers==4.40.1 `LlamaForCausalLM` — the container's transformers 5.5.0 class is used directly (same math)
   * flash-attn==2.5.5 — container has 2.8.3; used on the GPU box via `attn_implementation="flash_attention_2"`
 
-PARITY PINNING: the reference has no tests, fixtures or golden vectors for the neural path, and it
-cannot be imported here (no timm/draccus/tensorflow; gated tokenizer), so for ViT / projector / Llama arithmetic this
-oracle is **parity unpinned** (anchored only on the reference's call sites and on the third-party classes themselves).
+PARITY PINNING: the reference has no tests, fixtures or golden vectors for the neural path and the `prismatic` package
+cannot be imported here (no timm/draccus/tensorflow; gated tokenizer). Its HF model FILE can be executed, though: `gen_golden_hf_model.py`
+loads prismatic/extern/hf/modeling_prismatic.py by path and runs the reference's own `OpenVLAForActionPrediction` (CPU, fp32, toy widths;
+timm stood in by the ViT restatement, two transformers-5.x shims) and freezes its outputs in tests/golden/hf_model_golden.npz — the oracle's
+wiring (state-dict names, backbone split/concat, projector, sequence assembly, cached step, predict_action) is pinned against that.
+What stays **parity unpinned**: timm's ViT block internals, transformers 4.40.1 vs 5.5.0 Llama, flash-attn 2.5.5 vs 2.8.3, full size / bf16.
 The ViT restatement is additionally cross-checked against an independent implementation of the same architectures
 (`transformers.Dinov2WithRegistersModel`, `transformers.SiglipVisionModel`; tests/test_oracle_vit_crosscheck.py).
 The image processor (`gen_golden_processor.py`), the prompt builder (`gen_golden_prompts.py`) and the SimplerEnv policy post-processing

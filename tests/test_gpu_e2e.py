@@ -176,6 +176,34 @@ def test_from_pretrained_directory_round_trip(tiny, tmp_path):
     assert np.array_equal(np.asarray(act, dtype=np.float64), want)
 
 
+def test_predict_action_matches_the_reference_hf_model_class(golden_dir):
+    """Direct pin of the CUDA path against the reference's OWN `OpenVLAForActionPrediction.predict_action` (modeling_prismatic.py:506-537,
+    executed on the CPU with toy widths by oracle/gen_golden_hf_model.py; fixture tests/golden/hf_model_golden.npz): same seeded state dict
+    with 7 planted action tokens, same prompt and pixels -> the 7 generated token ids and the un-normalised fp64 action vector must be
+    identical; the greedy continuation without the planted prefix must agree wherever the reference's own top-2 margin is clear of bf16."""
+    from emmax_b200 import OpenVLAForActionPrediction, tiny_config
+    from emmax_b200.synthetic import make_state_dict
+
+    g = np.load(os.path.join(golden_dir, "hf_model_golden.npz"))
+    cfg = tiny_config()
+    script = [int(x) for x in g["action_script"]]
+    sd = make_state_dict(cfg, seed=int(g["pixel_seed"]), device="cpu", script=script, script_prev=29871)
+    model = OpenVLAForActionPrediction(cfg, sd).to("cuda")
+    ids = torch.from_numpy(g["input_ids"]).cuda()
+    pv = torch.randn(1, 6, 224, 224, generator=torch.Generator().manual_seed(int(g["pixel_seed"]))).to("cuda", BF)
+    action = model.predict_action(input_ids=ids, pixel_values=pv, unnorm_key=None, do_sample=False)
+    assert np.array_equal(np.asarray(action, dtype=np.float64), g["predict_action"]), (action, g["predict_action"])
+    ids29871 = torch.cat([ids, torch.tensor([[29871]], device="cuda")], dim=1)
+    new, _ = model.engine.generate(ids29871, pv, 7, eos_token_id=None)
+    assert new.cpu().tolist() == g["action_ids"].tolist()
+    # first free-running token: argmax of the reference's prefill logits at the last position (margin check against bf16 noise)
+    last = torch.from_numpy(g["prefill_last_logits"])
+    top2 = last.topk(2).values
+    if float(top2[0] - top2[1]) > 4e-2 * float(last.abs().max()):
+        first, _ = model.engine.generate(ids, pv, 1, eos_token_id=None)
+        assert int(first[0]) == int(last.argmax())
+
+
 @pytest.mark.parametrize("n_ids", [300, 730, 1700])
 def test_tiny_long_context_vs_oracle(tiny, n_ids):
     """Long prompts: 256 + n_ids prefill positions + 24 new tokens, i.e. contexts of ~580, ~1010 and ~1980 of the 2048-position

@@ -87,3 +87,41 @@ def test_oracle_skipping_last_vit_block_is_exact():
         for vit in (m.vision_backbone.featurizer, m.vision_backbone.fused_featurizer):
             assert torch.equal(vit(x), vit(x, run_all_blocks=True))
             assert vit(x).shape == (2, 256, vit.v.embed_dim)
+
+
+def test_oracle_wiring_matches_the_reference_hf_model_class(golden_dir):
+    """tests/golden/hf_model_golden.npz holds outputs of the reference's OWN `OpenVLAForActionPrediction` (modeling_prismatic.py executed on the
+    CPU with toy widths by oracle/gen_golden_hf_model.py; only timm's ViT internals and two transformers-5.x shims are stand-ins). The oracle,
+    built from the same seeded state dict, must reproduce them: state-dict key set, vision features, projector output, multimodal prefill
+    logits at every position, the cached single-token step, greedy continuation ids (4.40.1-style loop over the reference's forward) and
+    `predict_action` on planted action tokens. fp32 CPU; logits to 1e-4
+    (thread-count-dependent summation order), integer and fp64 results exactly."""
+    from emmax_b200 import tiny_config
+    from emmax_b200.synthetic import make_state_dict
+    from oracle.model import OracleVLA
+
+    g = np.load(os.path.join(golden_dir, "hf_model_golden.npz"))
+    cfg = tiny_config()
+    script = [int(x) for x in g["action_script"]]  # 7 planted action tokens after the id 29871, then EOS
+    sd = make_state_dict(cfg, seed=int(g["pixel_seed"]), device="cpu", script=script, script_prev=29871)
+    assert sorted(sd.keys()) == list(g["state_dict_keys"]), "state-dict names accepted by the reference class (0 missing / 0 unexpected)"
+    oracle = OracleVLA.from_state_dict(cfg, sd, device="cpu", dtype=torch.float32, attn_implementation="eager")
+    ids = torch.from_numpy(g["input_ids"])
+    pv = torch.randn(1, 6, 224, 224, generator=torch.Generator().manual_seed(int(g["pixel_seed"])))
+    with torch.no_grad():
+        feats = oracle.vision_backbone(pv)
+        proj = oracle.projector(feats)
+    assert np.allclose(feats[0, ::37, ::53].numpy(), g["features_probe"], atol=1e-5) and np.allclose(proj[0, ::37, ::29].numpy(), g["projected_probe"], atol=1e-5)
+    logits, past = oracle.prefill(ids, pv)
+    assert logits.shape[1] == ids.shape[1] + cfg.num_patches
+    assert np.array_equal(logits.argmax(-1).numpy(), g["prefill_argmax"]), "argmax at every one of the 277 positions"
+    assert np.allclose(logits[0, -1].numpy(), g["prefill_last_logits"], atol=1e-4)
+    step_logits, _ = oracle.step(torch.from_numpy(g["step_token"]), past)
+    assert np.allclose(step_logits[0, -1].numpy(), g["step_logits"], atol=1e-4)
+    n_new = g["generated_ids"].shape[1] - ids.shape[1]
+    assert np.array_equal(oracle.generate(ids, pv, n_new, eos_token_id=None).numpy(), g["generated_ids"])
+    # predict_action: the reference appends 29871 itself (:512-515), generates action_dim tokens, de-tokenises, un-normalises
+    ids29871 = torch.cat([ids, torch.tensor([[29871]])], dim=1)
+    assert oracle.generate(ids29871, pv, 7, eos_token_id=None)[0, -7:].tolist() == g["action_ids"].tolist() == script[:7]
+    assert np.array_equal(np.asarray(oracle.predict_action(ids, pv), dtype=np.float64), g["predict_action"])
+    assert len(set(np.round(g["predict_action"], 6))) == 7, "seven distinct action values: the de-tokeniser saw real action tokens, not the clip value"
