@@ -16,32 +16,7 @@ import torch
 tokenizers = pytest.importorskip("tokenizers")
 
 
-def _build_llama_shaped_tokenizer(path: str) -> None:
-    from tokenizers import Tokenizer, decoders, models, pre_tokenizers, processors
-
-    vocab = {"<unk>": 0, "<s>": 1, "</s>": 2}
-    text_chars = list("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789:;,._-?!\n")
-    for i, ch in enumerate(text_chars):
-        vocab[ch] = 3 + i
-    vocab["▁"] = 29871
-    action_chars = [chr(0x4E00 + i) for i in range(256)]  # 256 distinct single code points (CJK block), like Llama-2's tail
-    for i, ch in enumerate(action_chars):
-        vocab[ch] = 31744 + i
-    used = set(vocab.values())
-    for i in range(32000):  # fill the remaining ids so that vocab_size == 32000
-        if i not in used:
-            vocab[f"<filler_{i}>"] = i
-    tok = Tokenizer(models.WordLevel(vocab=vocab, unk_token="<unk>"))
-    # "▁" is prepended to the text and every character is its own token (a WordLevel stand-in for SentencePiece pieces)
-    tok.pre_tokenizer = pre_tokenizers.Sequence([pre_tokenizers.Metaspace(replacement="▁", prepend_scheme="first", split=False),
-                                                 pre_tokenizers.Split("", behavior="isolated")])  # fmt: skip
-    tok.post_processor = processors.TemplateProcessing(single="<s> $A", special_tokens=[("<s>", 1)])
-    tok.decoder = decoders.Sequence([decoders.Replace("▁", " "), decoders.Fuse(), decoders.Strip(" ", 1, 0)])
-    os.makedirs(path, exist_ok=True)
-    tok.save(os.path.join(path, "tokenizer.json"))
-    with open(os.path.join(path, "tokenizer_config.json"), "w") as f:
-        json.dump({"tokenizer_class": "PreTrainedTokenizerFast", "bos_token": "<s>", "eos_token": "</s>", "unk_token": "<unk>",
-                   "model_max_length": 2048, "clean_up_tokenization_spaces": False}, f)  # fmt: skip
+from _llama_shaped_tokenizer import build_llama_shaped_tokenizer as _build_llama_shaped_tokenizer  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -90,3 +65,28 @@ def test_processor_and_solver_through_a_real_fast_tokenizer(tok_dir):
     # decode() of generated ids with specials skipped, as generate_actions does
     ids = [1] + proc.tokenizer("ok", add_special_tokens=False).input_ids + [2]
     assert proc.tokenizer.decode(ids, skip_special_tokens=True).strip() == "ok"
+
+
+def test_processor_call_matches_the_reference_class(tok_dir, golden_dir):
+    """`PrismaticProcessor.__call__` vs the reference's own class (processing_prismatic.py:187-216, run by oracle/gen_golden_processor_call.py with
+    the same Llama-shaped tokenizer): key order, dtypes, shapes, ids, mask, pixel bytes (sha256), `model_input_names`, and the malformed-batch error."""
+    import hashlib
+
+    from PIL import Image
+
+    from emmax_b200 import AutoProcessor
+
+    g = json.load(open(os.path.join(golden_dir, "processor_call_golden.json")))
+    proc = AutoProcessor.from_pretrained(tok_dir, trust_remote_code=True)
+    for case in g["cases"]:
+        h, w = case["h"], case["w"]
+        img = Image.fromarray(np.random.default_rng(h * 1000 + w).integers(0, 256, (h, w, 3), dtype=np.uint8))
+        out = proc(case["prompt"], img)
+        assert list(out.keys()) == case["keys"]
+        assert {k: str(v.dtype) for k, v in out.items()} == case["dtypes"] and {k: list(v.shape) for k, v in out.items()} == case["shapes"]
+        assert out["input_ids"].tolist() == case["input_ids"] and out["attention_mask"].tolist() == case["attention_mask"]
+        assert hashlib.sha256(out["pixel_values"].float().contiguous().numpy().tobytes()).hexdigest() == case["pixel_sha256"]
+    assert proc.model_input_names == g["model_input_names"]
+    with pytest.raises(ValueError) as e:
+        proc([g["cases"][1]["prompt"]] * 2, Image.new("RGB", (224, 224)))
+    assert str(e.value) == g["batch_error"] == "Batch is malformed; expected same number of images and text inputs!"
