@@ -90,36 +90,34 @@ class OpenVLAInference:
         return self.postprocess(raw_actions)
 
     def postprocess(self, raw_actions: np.ndarray) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]:
-        """Everything of `step` after the model call (:103-145): split, euler -> axis-angle, gripper handling."""
-        raw_action = {
-            "world_vector": np.array(raw_actions[0, :3]),
-            "rotation_delta": np.array(raw_actions[0, 3:6]),
-            "open_gripper": np.array(raw_actions[0, 6:7]),  # range [0, 1]; 1 = open; 0 = close
+        """Everything of `step` after the model call (:103-145): split the 7-DoF vector, euler -> axis-angle, gripper handling."""
+        vec = np.asarray(raw_actions)[0]
+        raw_action = {"world_vector": np.array(vec[:3]), "rotation_delta": np.array(vec[3:6]), "open_gripper": np.array(vec[6:7])}  # 1 = open
+        axis, angle = euler2axangle(*np.asarray(raw_action["rotation_delta"], dtype=np.float64))
+        action: Dict[str, np.ndarray] = {
+            "world_vector": raw_action["world_vector"] * self.action_scale,
+            "rot_axangle": axis * angle * self.action_scale,
         }
-        action: Dict[str, np.ndarray] = {}
-        action["world_vector"] = raw_action["world_vector"] * self.action_scale
-        roll, pitch, yaw = np.asarray(raw_action["rotation_delta"], dtype=np.float64)
-        ax, angle = euler2axangle(roll, pitch, yaw)
-        action["rot_axangle"] = ax * angle * self.action_scale
-        if self.policy_setup == "google_robot":
-            current = raw_action["open_gripper"]
-            relative = np.array([0]) if self.previous_gripper_action is None else self.previous_gripper_action - current
-            self.previous_gripper_action = current
-            if np.abs(relative) > 0.5 and (not self.sticky_action_is_on):
-                self.sticky_action_is_on = True
-                self.sticky_gripper_action = relative
-            if self.sticky_action_is_on:
-                self.gripper_action_repeat += 1
-                relative = self.sticky_gripper_action
-            if self.gripper_action_repeat == self.sticky_gripper_num_repeat:
-                self.sticky_action_is_on = False
-                self.gripper_action_repeat = 0
-                self.sticky_gripper_action = 0.0
-            action["gripper"] = relative
-        elif self.policy_setup == "widowx_bridge":
+        if self.policy_setup == "widowx_bridge":  # binarised absolute command: +1 open, -1 close
             action["gripper"] = 2.0 * (raw_action["open_gripper"] > 0.5) - 1.0
+        else:  # google_robot: relative command with a sticky repeat
+            action["gripper"] = self._sticky_gripper(raw_action["open_gripper"])
         action["terminate_episode"] = np.array([0.0])
         return raw_action, action
+
+    def _sticky_gripper(self, opening: np.ndarray) -> np.ndarray:
+        """google_robot gripper (:121-140): the command is the CHANGE of the opening; a change larger than 0.5 latches and is repeated for
+        `sticky_gripper_num_repeat` steps (the first latched step included), then the latch clears."""
+        delta = np.array([0]) if self.previous_gripper_action is None else self.previous_gripper_action - opening
+        self.previous_gripper_action = opening
+        if not self.sticky_action_is_on and np.abs(delta) > 0.5:
+            self.sticky_action_is_on, self.sticky_gripper_action = True, delta
+        if self.sticky_action_is_on:
+            self.gripper_action_repeat += 1
+            delta = self.sticky_gripper_action
+        if self.gripper_action_repeat == self.sticky_gripper_num_repeat:
+            self.sticky_action_is_on, self.gripper_action_repeat, self.sticky_gripper_action = False, 0, 0.0
+        return delta
 
     def _resize_image(self, image: np.ndarray) -> np.ndarray:
         import cv2 as cv  # the reference resizes with OpenCV's area interpolation (:147-149)
