@@ -182,6 +182,50 @@ def run_reference(args) -> None:
 
 
 # =====================================================================================================================
+# parity gate ("parity gate before any timing counts")
+# =====================================================================================================================
+def parity_gate(cfg, sd, script, eng, dev, with_oracle: bool, n_forced: int = 8) -> dict:
+    """Runs BEFORE anything is timed and raises if the CUDA path is wrong:
+    (1) the full 512-token greedy continuation of the bench request must equal the planted script, id for id;
+    (2) (rank 0) prefill + the first `n_forced` teacher-forced decode steps: every step's logits within 1e-2 * max|logit| of the
+        torch-eager oracle (transformers Llama + flash-attn / sdpa) run on this GPU with the same weights, and the same argmax.
+    The oracle is the checker only; it is freed before the timed region."""
+    image, ids = synthetic_request(0)
+    from emmax_b200 import PrismaticImageProcessor
+
+    pv = PrismaticImageProcessor()(image, return_tensors="pt")["pixel_values"].to(dev, torch.bfloat16)
+    ids = ids.to(dev)
+    new, _ = eng.generate(ids, pv, N_NEW, eos_token_id=2)
+    got = new.cpu().tolist()
+    if got != list(script):
+        bad = next(i for i, (a, b) in enumerate(zip(got, script)) if a != b) if len(got) == len(script) else min(len(got), len(script))
+        raise SystemExit(f"PARITY GATE FAILED: greedy ids differ from the planted script at token {bad} ({len(got)} generated)")
+    out = {"ids_equal_script": True, "n_ids": len(got), "oracle": None}
+    if with_oracle:
+        from oracle.model import OracleVLA
+
+        try:
+            import flash_attn  # noqa: F401
+
+            attn = "flash_attention_2"
+        except Exception:
+            attn = "sdpa"
+        forced = list(script[:n_forced])
+        _, logits = eng.generate(ids, pv, n_forced, eos_token_id=None, return_logits=True, forced=forced)
+        oracle = OracleVLA.from_state_dict(cfg, sd, device=dev, dtype=torch.bfloat16, attn_implementation=attn)
+        _, logits_o = oracle.generate(ids, pv, n_forced, eos_token_id=None, return_logits=True, forced=forced)
+        del oracle
+        lo = logits_o.float()
+        err = float(((logits.cpu().float() - lo).abs().max() / lo.abs().max()).item())
+        same_argmax = bool((logits.cpu().argmax(-1) == lo.argmax(-1)).all())
+        if not (err < 1e-2 and same_argmax):
+            raise SystemExit(f"PARITY GATE FAILED: teacher-forced logits vs the oracle: rel err {err:.3g} (tolerance 1e-2), argmax equal: {same_argmax}")
+        out["oracle"] = {"kind": f"torch-eager oracle on this GPU ({attn})", "steps": n_forced, "logits_rel_err": err, "tolerance": 1e-2,
+                         "argmax_equal": same_argmax}  # fmt: skip
+    return out
+
+
+# =====================================================================================================================
 # our arm
 # =====================================================================================================================
 def run_ours(args) -> None:
@@ -207,9 +251,12 @@ def run_ours(args) -> None:
 
     cfg, tok, sd, script = build_weights(dev)
     cpu_sd = {k: v.cpu() for k, v in sd.items()} if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
-    model = OpenVLAForActionPrediction(cfg, sd, max_context=1024).to(dev)
+    model = OpenVLAForActionPrediction(cfg, dict(sd), max_context=1024).to(dev)
     eng = model.engine
     proc = AutoProcessor.from_pretrained(None)
+    parity = parity_gate(cfg, sd, script, eng, dev, with_oracle=(rank == 0 and not args.no_parity_oracle))
+    del sd
+    torch.cuda.empty_cache()
 
     # request stream: rank r serves frames r, r+N, ...; same fixed prompt
     def request(i: int):
@@ -282,7 +329,11 @@ def run_ours(args) -> None:
             tick_gather(eng.d_out_tokens)
         last_action[0] = action
 
-    e2e_ms, _ = timed(step_e2e, 1, K)
+    e2e_ms, _ = timed(step_e2e, W, K)
+    if world > 1:  # the collective's result is checked too: every replica's 7 action tokens, as planted
+        want = torch.tensor(script[act_lo : act_lo + 7], dtype=torch.int32, device=dev)
+        assert bool((gathered[:, :7] == want[None]).all()), f"all-gathered action tokens differ from the script: {gathered.tolist()}"
+        parity["gathered_rows_checked"] = world
     e2e_value = world * K / (e2e_ms / 1e3)
     h2d = reqs[0][2].numel() + reqs[0][1].numel() * 8
     d2h = N_NEW * 4 + 4
@@ -322,12 +373,13 @@ def run_ours(args) -> None:
                        "weights": "seeded random-init, full Emma-X architecture (DINOv2-L/14-reg4 + SigLIP-so400m/14 + Llama-2-7B)",
                        "parallelism": f"replicas x{world}" + (" + 1 NCCL all-gather of action tokens per step" if world > 1 else ""),
                        "l2": "per-step inputs (13.2 GB of weights streamed per token) exceed the 126 MB L2; no flush needed"},
-            "clocks": clocks,
+            "clocks": clocks, "parity": parity,
             "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "decode_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/decode_traffic.json (ncu --set full capture of this kernel, dram read+write per launch)",
+                         "peak_source": peak_src,
                          "bytes_per_launch": decode_bytes_total[0] / max(decode_launches[0], 1), "avg_launch_ms": avg_launch_ms,
                          "launches_timed": decode_launches[0], "share_of_step": decode_ms[0] / total_ms},
             "decode_ms_per_token": {"p50": tok_ms[64], "p10": tok_ms[12], "p90": tok_ms[115], "context": "296..424"},
@@ -356,6 +408,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-oracle", action="store_true", help="skip the live-oracle leg of the parity gate (the id check always runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -74,6 +74,15 @@ class LlamaDims:
         return self.hidden_size // self.num_attention_heads
 
 
+# Defaults of `transformers.LlamaConfig()` (the class behind CONFIG_MAPPING["llama"], configuration_prismatic.py:119-123) for the
+# fields this package reads; used to complete a `text_config` read from a checkpoint's config.json.
+HF_LLAMA_CONFIG_DEFAULTS: Dict[str, Any] = dict(
+    vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
+    num_key_value_heads=None, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=2048, bos_token_id=1,
+    eos_token_id=2,
+)  # fmt: skip
+
+
 # timm model id -> dims (values as created by `timm.create_model(id, img_size=224, num_classes=0)`)
 TIMM_VIT_DIMS: Dict[str, ViTDims] = {
     "vit_large_patch14_reg4_dinov2.lvd142m": ViTDims(
@@ -188,6 +197,13 @@ class PrismaticConfig:
     @classmethod
     def from_dict(cls, d: Dict[str, Any]) -> "PrismaticConfig":
         d = dict(d)
+        # The reference builds `text_config` as `LlamaConfig(**text_config)` (configuration_prismatic.py:119-123), so a key that a
+        # checkpoint's config.json omits takes the *transformers* default there (the HF exporter only patches vocab_size, pad_token_id
+        # and the dtype, convert_openvla_weights_to_hf.py:175-177) - NOT the defaults of `LlamaDims`, which describe the synthetic /
+        # native Llama-2 configuration. Every RMSNorm of the path depends on `rms_norm_eps`, so the fill-in must match.
+        d["text_config"] = {**HF_LLAMA_CONFIG_DEFAULTS, **(d.get("text_config") or {})}
+        if d["text_config"].get("num_key_value_heads") is None:
+            d["text_config"]["num_key_value_heads"] = d["text_config"]["num_attention_heads"]
         for derived in ("model_type", "timm_model_ids", "timm_override_act_layers", "image_sizes", "hf_llm_id"):
             d.pop(derived, None)
         for hf_noise in ("architectures", "auto_map", "torch_dtype", "transformers_version", "_name_or_path"):

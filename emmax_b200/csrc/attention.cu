@@ -292,7 +292,9 @@ template <int HD>
 static int launch_attn_mma(const __nv_bfloat16* in, __nv_bfloat16* o, int B, int T, int heads, int causal, float scale, cudaStream_t s) {
   // 64-query CTAs when that still gives every SM two CTAs, else 32-query CTAs (bs = 1: 16-32 heads x 5 query blocks)
   const long ctas64 = static_cast<long>((T + 63) / 64) * heads * B;
-  if (ctas64 >= 2L * kNumSMs) {
+  const int sms = device_sms();
+  if (sms < 0) return -2;
+  if (ctas64 >= 2L * sms) {
     attn_fwd_mma_kernel<HD, 4><<<dim3((T + 63) / 64, heads, B), 128, 0, s>>>(in, o, T, heads, causal, scale);
   } else {
     attn_fwd_mma_kernel<HD, 2><<<dim3((T + 31) / 32, heads, B), 64, 0, s>>>(in, o, T, heads, causal, scale);

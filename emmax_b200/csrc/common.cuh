@@ -15,7 +15,14 @@
 
 namespace emx {
 
-constexpr int kNumSMs = 148;
+constexpr int kNumSMs = 148;  // B200; launchers size their grids from the device actually in use (device_sms()), this is the design point
+
+// Per-device launch state (ops.cu): SM count of the CURRENT device, and whether the function attributes of kernel family `slot` (dynamic
+// shared-memory opt-in) have been set on it. cudaFuncSetAttribute is per device, so a process driving several GPUs needs it once per GPU.
+constexpr int kMaxDevices = 64;
+enum AttrSlot { ATTR_GEMM128 = 0, ATTR_GEMM256, ATTR_DECODE, ATTR_DECODE_BATCH, ATTR_ATTN_TC, ATTR_MISC, ATTR_SLOTS };
+int device_sms(int* device = nullptr);  // < 0 on error (emx_last_error set)
+bool* device_attr_flag(int slot);       // nullptr on error
 
 // ---------------------------------------------------------------------------------------------------------------
 // error plumbing (host)

@@ -362,9 +362,9 @@ __device__ __forceinline__ void prefetch_l2(const void* gptr, uint32_t bytes) {
 
 // ---- producer warps -------------------------------------------------------------------------------------------------
 // Both producer warps walk the same schedule; warp `pidx` issues the ring stages with it % DEC_PWARPS == pidx.
-__device__ void producer_loop(const emx_decode_params& p, const PhaseTab& tab, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane, int pidx,
-                              volatile uint32_t* s_groups_issued, long long* dbg) {
-  const uint64_t policy = (p.debug_flags & 4) ? l2_policy_evict_last() : l2_policy_evict_first();
+__device__ void producer_loop(const emx_decode_params& p, int dflags, const PhaseTab& tab, uint8_t* ring, uint64_t* full, uint64_t* empty,
+                                              int lane, int pidx, volatile uint32_t* s_groups_issued, long long* dbg) {
+  const uint64_t policy = (dflags & 4) ? l2_policy_evict_last() : l2_policy_evict_first();
   SchedIter cur;
   cur.init(tab, p.layers);
   uint32_t it = 0, groups = 0;
@@ -403,12 +403,13 @@ __device__ void producer_loop(const emx_decode_params& p, const PhaseTab& tab, u
 // newest ring copy of this CTA has LANDED, i.e. nothing of ours is in flight — and then pulls the next groups of the static
 // schedule HBM -> L2 with cp.async.bulk.prefetch.L2, paced at about twice the SM's fair share, at most `l2_lookahead_kb`
 // ahead of the ring. In the HBM-bound steady state it never triggers, so it costs nothing there.
-__device__ void prefetch_loop(const emx_decode_params& p, const PhaseTab& tab, int lane, volatile uint32_t* s_issued, uint64_t* full) {
+__device__ void prefetch_loop(const emx_decode_params& p, int dflags, const PhaseTab& tab, int lane, volatile uint32_t* s_issued, uint64_t* full,
+                                              long long* dbg) {
   const long lookahead = static_cast<long>(p.l2_lookahead_kb) * 1024;
   if (lookahead <= 0) return;
-  const long long pace_ns = ((p.debug_flags >> 8) & 0xfff) ? ((p.debug_flags >> 8) & 0xfff) * 10 : 700;  // per 64 KB while the ring is idle
-  const long long pace_catchup_ns = (p.debug_flags >> 20) ? (p.debug_flags >> 20) * 10 : 1300;            // per 64 KB while the ring drains L2
-  const bool catchup = p.debug_flags & 8;  // measured neutral-to-slightly-negative on B200 (profiles/r01_decode_v5_prefetch_modes.txt): off by default
+  const long long pace_ns = ((dflags >> 8) & 0xfff) ? ((dflags >> 8) & 0xfff) * 10 : 700;  // per 64 KB while the ring is idle
+  const long long pace_catchup_ns = (dflags >> 20) ? (dflags >> 20) * 10 : 1300;            // per 64 KB while the ring drains L2
+  const bool catchup = dflags & 8;  // measured neutral-to-slightly-negative on B200 (profiles/r01_decode_v5_prefetch_modes.txt): off by default
   SchedIter cur, pf;
   cur.init(tab, p.layers);
   pf.init(tab, p.layers);
@@ -478,7 +479,7 @@ __device__ void prefetch_loop(const emx_decode_params& p, const PhaseTab& tab, i
     const long long wait_ns = (idle ? pace_ns : pace_catchup_ns) * n / (64 * 1024);
     while (global_ns() - t0 < wait_ns) __nanosleep(100);
   }
-  if (p.dbg && blockIdx.x == 0 && lane == 0) reinterpret_cast<long long*>(p.dbg)[15 * p.layers + 13] = pf_total;
+  if (dbg && lane == 0) dbg[15 * p.layers + 13] = pf_total;
 }
 
 // ---- consumer: tensor-core dot products of one phase ---------------------------------------------------------------------
@@ -679,11 +680,11 @@ __device__ __forceinline__ void att_pv(const uint32_t (&b)[32], const float* sm,
 }
 
 template <bool PROF>
-__device__ void attention_loop(const emx_decode_params& p, const int32_t* s_table, const uint32_t* s_rope, int pos, uint32_t tag0, bool check,
+__device__ void attention_loop(const emx_decode_params& p, int dflags, const int32_t* s_table, const uint32_t* s_rope, int pos, uint32_t tag0, bool check,
                                float* sm, float* red, uint32_t* tmem_holder, volatile int* s_step, int atid) {
   constexpr int HALF = DEC_HD / 2;
   const int item = blockIdx.x, S = p.kv_splits;
-  if (item >= p.heads * S || (p.debug_flags & 2)) return;
+  if (item >= p.heads * S || (dflags & 2)) return;
   const int head = item / S, split = item % S;
   const int awarp = atid >> 5, lane = atid & 31;
   const int n = pos + 1;
@@ -881,7 +882,7 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
       // The staging loads (up to 24 outstanding 16-B loads per thread) share the SM's load path with the consumers' LL polling:
       // issued right away they sit in front of the o_proj-output gather and delay it by ~2 us. Hold them until the consumers are
       // inside the gate/up weight phase (22 us without a single global load of theirs; staging takes 8-13 us).
-      if (atid == 0 && !(p.debug_flags & 32)) {
+      if (atid == 0 && !(dflags & 32)) {
         uint32_t spins = 0;
         while (*s_step < PH_STEPS * layer + PH_GATEUP) {
           __nanosleep(200);
@@ -900,10 +901,13 @@ __device__ void attention_loop(const emx_decode_params& p, const int32_t* s_tabl
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
-// PROF = true: the instrumented twin used when `dbg` is given (phase timestamps, wait counters); it costs registers, so the
-// product launch uses PROF = false.
-template <bool PROF>
+// MODE 0: the PRODUCT kernel — `debug_flags` and `dbg` are not even read, every wait is checked, every store happens.
+// MODE 1: profiling twin that honours `debug_flags` (timing experiments whose results may be garbage), no instrumentation.
+// MODE 2: instrumented twin used when `dbg` is given (phase timestamps, wait counters; also honours `debug_flags`); it costs registers.
+template <int MODE>
 __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_decode_params p) {
+  constexpr bool PROF = (MODE == 2);
+  const int dflags = (MODE >= 1) ? p.debug_flags : 0;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ring = smem;
   uint32_t* xs = reinterpret_cast<uint32_t*>(smem + DEC_STAGES * DEC_STAGE_BYTES);  // activation vector, bf16 pairs, xs_pos order
@@ -952,7 +956,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   }
   __syncthreads();
   const int token = min(max(s_state[0], 0), p.vocab - 1), pos = s_state[1], n_gen = s_state[2];  // (clamped: a profiling mode that skips the LL waits may have written garbage)
-  if (s_state[3]) return;  // sequence already hit EOS: nothing to do (uniform across the grid)
+  // sequence already hit EOS, or the KV cache of this sequence is full (a caller driving its own loop past the capacity must not
+  // corrupt memory: the block table, the RoPE tables and out_tokens all end at max_pages * page_size): nothing to do, uniformly
+  if (s_state[3] || pos >= p.max_pages * p.page_size) return;
 
   const int L = p.layers, H = p.hidden;
   long long* dbg = (PROF && blockIdx.x == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
@@ -960,17 +966,17 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   // LL tags of this launch: tag0 + l for everything exchanged inside layer l (and for the residual stream ENTERING layer l);
   // tag0 + L enters the final norm, tag0 + L + 1 carries the argmax candidates. Never 0, unique across launches.
   const uint32_t tag0 = static_cast<uint32_t>(s_state[4]) * static_cast<uint32_t>(L + 2) + 1u;
-  const bool check = !(p.debug_flags & 1);
+  const bool check = !(dflags & 1);
   if (warp >= DEC_CWARPS + DEC_AWARPS + DEC_PWARPS) {
-    if (warp == DEC_CWARPS + DEC_AWARPS + DEC_PWARPS) prefetch_loop(p, tab, lane, s_issued, full);
+    if (warp == DEC_CWARPS + DEC_AWARPS + DEC_PWARPS) prefetch_loop(p, dflags, tab, lane, s_issued, full, dbg);
     return;  // (the 16th warp only pads the block to 512 threads = 128 registers per thread)
   }
   if (warp >= DEC_CWARPS + DEC_AWARPS) {
-    producer_loop(p, tab, ring, full, empty, lane, warp - DEC_CWARPS - DEC_AWARPS, s_issued, dbg);
+    producer_loop(p, dflags, tab, ring, full, empty, lane, warp - DEC_CWARPS - DEC_AWARPS, s_issued, dbg);
     return;
   }
   if (warp >= DEC_CWARPS) {
-    attention_loop<PROF>(p, s_table, s_rope, pos, tag0, check, att_sm, att_red, reinterpret_cast<uint32_t*>(misc + 60), s_step, tid - DEC_CTHREADS);
+    attention_loop<PROF>(p, dflags, s_table, s_rope, pos, tag0, check, att_sm, att_red, reinterpret_cast<uint32_t*>(misc + 60), s_step, tid - DEC_CTHREADS);
     return;
   }
 
@@ -987,7 +993,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
   };
   ConsumerState cs{0, 0, 0, 0, 0};
   long long gprof[4] = {0, 0, 0, 0};  // PROF: cycles of the gather + RMSNorm steps (loads back | ln wait | sum | normalise + barrier)
-  const bool drop = p.debug_flags & 16;
+  const bool drop = dflags & 16;
 
   uint64_t* xd = static_cast<uint64_t*>(p.x);      // residual stream after down_proj   [H/2] units
   uint64_t* xo = static_cast<uint64_t*>(p.xo);     // residual stream after o_proj      [H/2]
@@ -1030,7 +1036,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
     mark();
     if (tid == 0) *s_step = step;
     consume_phase<PROF>(phase_desc(tab, layer, kind), ring, full, empty, cs, reinterpret_cast<const __nv_bfloat16*>(xs), part, warp, lane,
-                        p.debug_flags, [&](int row, float a0, float a1, bool valid) {
+                        dflags, [&](int row, float a0, float a1, bool valid) {
                           // lanes 0..7 of warp 0, converged; `kind` is uniform
                           if (kind <= PH_V) {
                             if (valid) ll_store(qkv + kind * (H >> 1) + (row >> 1), pack_bf16(a0, a1), tag, drop);
@@ -1103,7 +1109,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_step_kernel(const emx_d
 
 }  // namespace emx
 
-extern "C" int emx_decode_grid(void) { return emx::kNumSMs; }
+// CTAs per launch = SMs of the current device (148 on B200; also the answer when no device is visible, e.g. the CPU test suite)
+extern "C" int emx_decode_grid(void) {
+  const int sms = emx::device_sms();
+  return sms > 0 ? sms : emx::kNumSMs;
+}
 
 extern "C" int emx_decode_phase_rows(int n_rows, int granule, int cta, int grid, int* r_begin, int* r_end) {
   EMX_REQUIRE(n_rows > 0 && (granule == 2 || granule == 4) && grid > 0 && cta >= 0 && cta < grid && r_begin && r_end && n_rows % granule == 0,
@@ -1123,27 +1133,29 @@ extern "C" int emx_decode_step(const emx_decode_params* params, cudaStream_t str
   EMX_REQUIRE(p.kv_splits >= 1 && p.kv_splits <= 8 && (p.kv_splits & (p.kv_splits - 1)) == 0, "emx_decode_step: kv_splits must be 1, 2, 4 or 8");
   EMX_REQUIRE(p.hidden <= 16 * DEC_CTHREADS && p.hidden * 2 <= DEC_LN_BYTES, "emx_decode_step: hidden > %d not supported by the fused gather + RMSNorm", DEC_LN_BYTES / 2);
   EMX_REQUIRE(p.max_pages <= DEC_MAX_PAGES, "emx_decode_step: block table of %d pages exceeds %d", p.max_pages, DEC_MAX_PAGES);
-  EMX_REQUIRE(p.heads * p.kv_splits <= kNumSMs, "emx_decode_step: heads x kv_splits must not exceed the grid (one attention item per CTA)");
-  EMX_REQUIRE(p.hidden / 2 / kNumSMs + 2 <= DEC_MAX_RESID, "emx_decode_step: hidden too large for the residual staging buffer");
   const int max_keys_per_split = ATT_PASS * ATT_MAX_PASSES;
   EMX_REQUIRE((static_cast<long>(p.max_pages) * p.page_size + p.kv_splits - 1) / p.kv_splits <= max_keys_per_split,
               "emx_decode_step: context capacity %d x %d exceeds the per-split score buffer (%d keys)", p.max_pages, p.page_size,
               max_keys_per_split);
-  static bool attr_set = false;
-  static int grid = 0;
-  if (!attr_set) {
-    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
-    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
-    int dev = 0, sms = 0, per_sm = 0;
-    EMX_CHECK_CUDA(cudaGetDevice(&dev));
-    EMX_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    EMX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<true>, DEC_THREADS, DEC_SMEM));
+  int dev = 0;
+  const int grid = device_sms(&dev);
+  bool* attr_set = device_attr_flag(ATTR_DECODE);
+  if (grid < 0 || !attr_set) return -2;
+  if (!*attr_set) {
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
+    int per_sm = 0;
+    EMX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<2>, DEC_THREADS, DEC_SMEM));
     EMX_REQUIRE(per_sm >= 1, "emx_decode_step: kernel does not fit on an SM (smem %d)", DEC_SMEM);
-    grid = sms;
-    attr_set = true;
+    *attr_set = true;
   }
+  EMX_REQUIRE(p.heads * p.kv_splits <= grid, "emx_decode_step: heads x kv_splits must not exceed the grid of %d CTAs (one attention item per CTA)", grid);
+  EMX_REQUIRE(p.hidden / 2 / grid + 2 <= DEC_MAX_RESID, "emx_decode_step: hidden too large for the residual staging buffer");
   void* args[] = {const_cast<emx_decode_params*>(params)};
-  void* fn = p.dbg ? reinterpret_cast<void*>(decode_step_kernel<true>) : reinterpret_cast<void*>(decode_step_kernel<false>);
+  // the product kernel unless the caller asks for a profiling twin: `dbg` -> instrumented, `debug_flags` alone -> flag-honouring
+  void* fn = p.dbg ? reinterpret_cast<void*>(decode_step_kernel<2>)
+                   : (p.debug_flags ? reinterpret_cast<void*>(decode_step_kernel<1>) : reinterpret_cast<void*>(decode_step_kernel<0>));
   EMX_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(DEC_THREADS), args, DEC_SMEM, stream));
   return 0;
 }

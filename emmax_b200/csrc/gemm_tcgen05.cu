@@ -246,13 +246,15 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat16* C, int ldc, int M, int N, int K, const EpiParams& ep,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  bool* attr_set = device_attr_flag(BN == 128 ? ATTR_GEMM128 : ATTR_GEMM256);  // per device: the opt-in is device state
+  const int sms = device_sms();
+  if (!attr_set || sms < 0) return -2;
+  if (!*attr_set) {
     EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    *attr_set = true;
   }
   const int n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  gemm_tn_kernel<BN><<<n_tiles < kNumSMs ? n_tiles : kNumSMs, 256, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
+  gemm_tn_kernel<BN><<<n_tiles < sms ? n_tiles : sms, 256, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -270,7 +272,9 @@ extern "C" int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, voi
                static_cast<const __nv_bfloat16*>(resid), ldr, resid_mod, flags};
   CUtensorMap ta, tb;
   // BN = 128 keeps the grid at >= ~1 wave for the M <= 300 problems of a bs=1 request; BN = 256 for large M.
-  const bool wide = (static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256) >= 2 * kNumSMs);
+  const int sms = device_sms();
+  if (sms < 0) return -2;
+  const bool wide = (static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256) >= 2 * sms);
   if (int r = make_tmap(&ta, A, M, K, lda, BM)) return r;
   if (int r = make_tmap(&tb, W, N, K, ldw, wide ? 256 : 128)) return r;
   return wide ? launch_gemm<256>(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, stream)

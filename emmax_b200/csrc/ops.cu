@@ -17,6 +17,33 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_sms[kMaxDevices];
+static bool g_attr[kMaxDevices][ATTR_SLOTS];
+
+int device_sms(int* device) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    set_last_error("device_sms: no current CUDA device (or index >= %d)", kMaxDevices);
+    return -1;
+  }
+  if (g_sms[dev] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+      set_last_error("device_sms: cudaDeviceGetAttribute failed for device %d", dev);
+      return -1;
+    }
+    g_sms[dev] = sms;
+  }
+  if (device) *device = dev;
+  return g_sms[dev];
+}
+
+bool* device_attr_flag(int slot) {
+  int dev = 0;
+  if (device_sms(&dev) < 0) return nullptr;
+  return &g_attr[dev][slot];
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;

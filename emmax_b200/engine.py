@@ -23,6 +23,19 @@ from .configuration import OpenVLAConfig, ViTDims
 BF16 = torch.bfloat16
 
 
+def _on_engine_device(fn):
+    """Run a method with the engine's GPU as the current CUDA device: the kernels are launched on `torch.cuda.current_stream()`, which
+    belongs to the CURRENT device, while every pointer they receive lives on `self.device` (a process may hold engines on several GPUs)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 def _ceil_to(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -263,6 +276,7 @@ class Engine:
         self._llm_prefill(ws, B, n_ids)
 
     # ------------------------------------------------------------------------------------------------------------
+    @_on_engine_device
     @torch.no_grad()
     def prefill(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, use_graph: bool = True) -> dict:
         """Vision + projector + LLM prefill for B same-length prompts. Returns the workspace (first tokens, logits, features)."""
@@ -309,9 +323,10 @@ class Engine:
         p.part, p.argmax_part = ptr(self.d_part), ptr(self.d_argmax)
         p.out_tokens, p.logits_out = ptr(self.d_out_tokens), None
         p.eos_token, p.kv_splits, p.state = -1, self.kv_splits, ptr(self.d_state)
-        p.dbg, p.l2_lookahead_kb, p.debug_flags = None, self.l2_lookahead_kb, int(os.environ.get("EMX_DECODE_DEBUG_FLAGS", "0"))
+        p.dbg, p.l2_lookahead_kb, p.debug_flags = None, self.l2_lookahead_kb, 0  # profiling twins: tools/decode_probe.py sets these itself
         return p
 
+    @_on_engine_device
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, max_new_tokens: int, eos_token_id: Optional[int] = 2,
                  return_logits: bool = False, forced: Optional[List[int]] = None, use_graph: bool = True,

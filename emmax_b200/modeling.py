@@ -210,8 +210,9 @@ class OpenVLAForActionPrediction:
         n = ids.numel()
         norm = torch.empty(n, dtype=torch.float64, device=self.device)
         act = torch.empty(n, dtype=torch.float64, device=self.device)
-        _lib.call("emx_detokenize_actions", ids.data_ptr(), n, self.vocab_size, self.config.n_action_bins, q01.data_ptr(), q99.data_ptr(),
-                  mask.data_ptr(), q01.numel(), norm.data_ptr(), act.data_ptr(), _lib.stream())  # fmt: skip
+        with torch.cuda.device(self.device):  # launch on a stream of the engine's GPU, whatever the caller's current device is
+            _lib.call("emx_detokenize_actions", ids.data_ptr(), n, self.vocab_size, self.config.n_action_bins, q01.data_ptr(), q99.data_ptr(),
+                      mask.data_ptr(), q01.numel(), norm.data_ptr(), act.data_ptr(), _lib.stream())  # fmt: skip
         return norm, act
 
     @torch.no_grad()
@@ -221,7 +222,9 @@ class OpenVLAForActionPrediction:
             input_ids = torch.cat((input_ids, torch.tensor([[29871]], dtype=input_ids.dtype, device=input_ids.device)), dim=1)
         n = self.get_action_dim(unnorm_key)
         kwargs.pop("max_new_tokens", None)
-        generated = self.generate(input_ids, max_new_tokens=n, eos_token_id=None, **kwargs)
+        # EOS stays active exactly as in the reference's `self.generate(...)` call (modeling_prismatic.py:519): a model that emits </s> early
+        # stops there, and `[-n:]` below then reaches back into the prompt ids just as the reference's slice does
+        generated = self.generate(input_ids, max_new_tokens=n, **kwargs)
         _, actions = self.detokenize_on_device(generated[0, -n:], unnorm_key)
         return actions.cpu().numpy()
 
@@ -273,6 +276,10 @@ class OpenVLAForActionPrediction:
         if labels is not None or inputs_embeds is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("training / introspection outputs are outside the accelerated inference path")
         eng = self.engine
+        with torch.cuda.device(eng.device):
+            return self._forward_on_device(eng, input_ids, pixel_values, past_key_values, output_projector_features)
+
+    def _forward_on_device(self, eng: Engine, input_ids, pixel_values, past_key_values, output_projector_features):
         if input_ids.shape[1] == 1 and past_key_values is not None:
             assert input_ids.shape[0] == 1, "Generation is only currently supported for batch size of 1!"
             return self._forward_cached(input_ids)
@@ -289,6 +296,7 @@ class OpenVLAForActionPrediction:
         eng.gemm(normed, eng.lm_head, logits)
         st = eng.d_state
         st[0:1].copy_(ws["first"][0:1]), st[1].fill_(S), st[2].fill_(0), st[3].zero_()
+        self._cached_pos = S  # host mirror of the KV length, for the capacity check of the caller-driven cached loop
         return PrismaticCausalLMOutputWithPast(
             logits=logits.view(B, S, V), past_key_values=eng,
             projector_features=ws["patches"].view(B, -1, H).clone() if output_projector_features else None,
@@ -299,6 +307,12 @@ class OpenVLAForActionPrediction:
 
         eng = self.engine
         V = eng.t.vocab_size
+        pos = getattr(self, "_cached_pos", None)
+        if pos is None:
+            raise ValueError("cached forward() without a preceding multimodal forward(): there is no KV cache to extend")
+        if pos >= eng.max_context:
+            raise ValueError(f"KV cache is full: {pos} positions cached, engine capacity max_context={eng.max_context}")
+        self._cached_pos = pos + 1
         logits = torch.empty((1, 1, V), dtype=torch.float32, device=self.device)
         eng.d_state[0:1].copy_(input_ids.reshape(-1)[:1].to(device=self.device, dtype=torch.int32))
         p = eng._decode_params(0)

@@ -180,10 +180,21 @@ class SyntheticLlamaTokenizer:
 
 
 def load_tokenizer(path: Optional[str]) -> Any:
-    """Real tokenizer if the directory has one, else the synthetic stand-in."""
+    """Real tokenizer if the directory has one. `path=None` (synthetic models) gives the synthetic stand-in; a checkpoint directory
+    WITHOUT tokenizer files also does, but loudly: its vocabulary is not the checkpoint's, so prompts and decoded text are only
+    meaningful for the seeded synthetic weights."""
     if path is not None and os.path.isdir(path):
         if any(os.path.exists(os.path.join(path, f)) for f in ("tokenizer.model", "tokenizer.json")):
             from transformers import AutoTokenizer
 
             return AutoTokenizer.from_pretrained(path, model_max_length=2048, padding_side="right")
+        import warnings
+
+        warnings.warn(
+            f"{path!r} holds no tokenizer.model / tokenizer.json: falling back to the SYNTHETIC Llama-shaped tokenizer. Prompts, decoded "
+            "reasoning text and the Solver round trip will NOT match a real checkpoint's vocabulary - copy the checkpoint's tokenizer files "
+            "into the directory (or pass tokenizer=...) for real weights.",
+            UserWarning,
+            stacklevel=2,
+        )
     return SyntheticLlamaTokenizer()

@@ -142,3 +142,38 @@ def test_decode_row_partition_covers_every_row_once():
         assert max(1, H // 2 // grid + 2) <= 192, "residual pairs of one CTA fit DEC_MAX_RESID"
     b, e = C.c_int(), C.c_int()
     assert lib.emx_decode_phase_rows(10, 3, 0, grid, C.byref(b), C.byref(e)) != 0 and b"emx_decode_phase_rows" in lib.emx_last_error()
+
+
+def test_sparse_text_config_takes_the_transformers_defaults(tmp_path):
+    """A checkpoint's config.json may hold only the keys the HF exporter patches (vocab_size, pad_token_id; convert_openvla_weights_to_hf.py:175-177).
+    The reference then runs `LlamaConfig(**text_config)` (configuration_prismatic.py:119-123), i.e. every other field is the transformers
+    default - rms_norm_eps 1e-6, max_position_embeddings 2048 - and the loader here must resolve to the same numbers."""
+    import json
+
+    from transformers import LlamaConfig
+
+    from emmax_b200 import OpenVLAConfig, emma_x_config
+
+    d = emma_x_config().to_dict()
+    d["text_config"] = {"vocab_size": 32064, "pad_token_id": 32000}
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump(d, f)
+    got = OpenVLAConfig.from_pretrained(str(tmp_path)).text_config
+    want = LlamaConfig(vocab_size=32064, pad_token_id=32000)
+    for k in ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "num_key_value_heads",
+              "rms_norm_eps", "max_position_embeddings", "bos_token_id", "eos_token_id", "pad_token_id"):  # fmt: skip
+        assert getattr(got, k) == getattr(want, k), (k, getattr(got, k), getattr(want, k))
+    assert got.rope_theta == 10000.0
+    # the synthetic / native configuration keeps Llama-2's own 1e-5 (SURVEY.md §8 a7), and a full text_config round-trips unchanged
+    assert emma_x_config().text_config.rms_norm_eps == 1e-5
+    emma_x_config().save_pretrained(str(tmp_path / "full"))
+    assert OpenVLAConfig.from_pretrained(str(tmp_path / "full")).text_config.rms_norm_eps == 1e-5
+
+
+def test_checkpoint_dir_without_tokenizer_warns(tmp_path):
+    from emmax_b200.tokenization import SyntheticLlamaTokenizer, load_tokenizer
+
+    with pytest.warns(UserWarning, match="SYNTHETIC"):
+        tok = load_tokenizer(str(tmp_path))
+    assert isinstance(tok, SyntheticLlamaTokenizer)
+    assert isinstance(load_tokenizer(None), SyntheticLlamaTokenizer)
