@@ -29,30 +29,20 @@
 //     ahead, and only the new token's k/v -> owner split -> head output -> o_proj chain is left on the critical path;
 //   * an L2-prefetch warp keeps HBM busy while the consumers wait for an exchange and the ring is full.
 // Rounding points mirror the torch-eager reference (bf16 after every Linear / norm / residual add / activation).
-#include "common.cuh"
+#include "decode_common.cuh"
 #include "emmax.h"
 
 namespace emx {
 
-constexpr int DEC_CWARPS = 8;                    // consumer warps
-constexpr int DEC_CTHREADS = DEC_CWARPS * 32;    // 256
 constexpr int DEC_PWARPS = 2;                    // producer warps (alternate ring stages)
 constexpr int DEC_AWARPS = 4;                    // attention warps (their own dataflow, concurrent with the consumers)
 constexpr int DEC_ATHREADS = DEC_AWARPS * 32;    // 128
 constexpr int DEC_THREADS = 512;                 // 8 consumer + 4 attention + 2 producer + 1 L2-prefetch warp (+ 1 idle): 128 registers / thread
-constexpr int DEC_GROUP = 16;                    // rows per ring stage == M of the MMA atom
-constexpr int DEC_KC = 2048;                     // K elements per ring stage (4 KB per row segment)
-constexpr int DEC_KW = DEC_KC / DEC_CWARPS;      // 256 columns per consumer warp per stage
-constexpr int DEC_ROWSTRIDE = DEC_KC * 2 + 16;   // padded row stride (bytes): ldmatrix rows land in distinct bank groups
-constexpr int DEC_STAGES = 3;
-constexpr int DEC_STAGE_BYTES = DEC_GROUP * DEC_ROWSTRIDE;  // 65792
 constexpr int DEC_MAX_RESID = 192;               // residual pairs of one CTA staged in shared memory
 constexpr int DEC_XS_BYTES = 22528;                         // activation vector (bf16), up to 11264 elements
 constexpr int DEC_MISC_BYTES = 4096;
-constexpr int DEC_PARTBUFS = 4;                  // partial-sum buffers (a warp is never more than 3 ring stages ahead of warp 0)
 constexpr int DEC_LN_BYTES = 8192;              // norm weights of the NEXT RMSNorm, fetched asynchronously a phase ahead (hidden <= 4096)
 constexpr int DEC_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_XS_BYTES + DEC_MISC_BYTES + 128 + DEC_LN_BYTES;
-constexpr int DEC_HD = 128;  // head_dim supported by the decode kernel (Llama-2)
 constexpr int DEC_MAX_PAGES = 64;  // block-table entries staged in shared memory
 
 // q, k and v rows are three phases of their own, q FIRST: every CTA finishes its share of the q rows a third of the way into the
@@ -73,15 +63,6 @@ struct PhaseTab {
   long layer_stride[7];  // elements between consecutive layers
   int N[7], K[7], r_begin[7], r_end[7];
 };
-
-// [r_begin, r_end) of an n_rows-row phase owned by CTA `cta` of `grid`: contiguous, balanced to one granule (row pairs are one LL unit;
-// gate/up rows come in quads = two SwiGLU outputs = one LL unit), together covering every row exactly once. Host-callable so that the
-// CPU test suite checks the very formula the kernel uses (emx_decode_phase_rows).
-__host__ __device__ __forceinline__ void phase_rows(int n_rows, uint32_t granule, uint32_t cta, uint32_t grid, int& r_begin, int& r_end) {
-  const uint32_t U = static_cast<uint32_t>(n_rows) / granule;  // U * grid < 2^32
-  r_begin = static_cast<int>(U * cta / grid * granule);
-  r_end = static_cast<int>(U * (cta + 1) / grid * granule);
-}
 
 // Rows of a phase owned by this CTA. Row pairs are never split (one LL unit = one row pair); gate/up rows come in groups of
 // four (two SwiGLU outputs = one LL unit).
@@ -104,47 +85,6 @@ __device__ __forceinline__ PhaseDesc phase_desc(const PhaseTab& t, int layer, in
   d.W = t.W[kind] + layer * t.layer_stride[kind];
   d.N = t.N[kind], d.K = t.K[kind], d.kind = kind, d.r_begin = t.r_begin[kind], d.r_end = t.r_end[kind];
   return d;
-}
-
-__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(DEC_CTHREADS) : "memory"); }
-
-// ---- LL units: {32-bit payload | 32-bit tag} in one naturally aligned 64-bit word ---------------------------------------
-// A 64-bit scalar store / load is single-copy atomic, so a reader that sees the expected tag also sees the payload.
-__device__ __forceinline__ void ll_store(uint64_t* unit, uint32_t data, uint32_t tag, bool drop = false) {
-  if (drop) return;
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(unit), "l"((static_cast<uint64_t>(tag) << 32) | data) : "memory");
-}
-__device__ __forceinline__ uint64_t ll_load(const uint64_t* unit) {
-  uint64_t v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(unit) : "memory");
-  return v;
-}
-__device__ __forceinline__ void ll_load2(const uint64_t* unit, uint64_t& a, uint64_t& b) {
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(unit) : "memory");
-}
-// spin until `unit` carries `tag` (check == false: profiling modes whose results are garbage anyway)
-__device__ __forceinline__ uint32_t ll_wait(const uint64_t* unit, uint32_t tag, bool check) {
-  uint64_t v = ll_load(unit);
-  uint32_t spins = 0;
-  while (check && static_cast<uint32_t>(v >> 32) != tag) {
-    v = ll_load(unit);
-    if (++spins > EMX_SPIN_LIMIT) __trap();
-  }
-  return static_cast<uint32_t>(v);
-}
-
-// two units at once: both loads are in flight before the first tag is checked (one L2 round trip instead of two when both are there)
-template <bool BACKOFF = false>
-__device__ __forceinline__ void ll_wait2(const uint64_t* ua, const uint64_t* ub, uint32_t tag, bool check, uint32_t& a, uint32_t& b) {
-  uint64_t va = ll_load(ua), vb = ll_load(ub);
-  uint32_t spins = 0;
-  while (check && (static_cast<uint32_t>(va >> 32) != tag || static_cast<uint32_t>(vb >> 32) != tag)) {
-    if (BACKOFF) __nanosleep(96);  // long waits (tens of us): do not burn issue slots and L2 requests spinning
-    if (static_cast<uint32_t>(va >> 32) != tag) va = ll_load(ua);
-    if (static_cast<uint32_t>(vb >> 32) != tag) vb = ll_load(ub);
-    if (++spins > EMX_SPIN_LIMIT) __trap();
-  }
-  a = static_cast<uint32_t>(va), b = static_cast<uint32_t>(vb);
 }
 
 // Gather a whole vector of `n_units` (even) LL units tagged `tag`: thread t takes the unit pairs t, t + 256, ...; all loads of a
@@ -186,28 +126,6 @@ __device__ __forceinline__ void ll_gather(const uint64_t* buf, int n_units, uint
   }
 }
 
-// NP unit pairs at computed addresses: all loads in flight before the first tag is checked, missing pairs are re-polled.
-template <int NP, typename Addr>
-__device__ __forceinline__ void ll_fetch_pairs(Addr&& addr, uint32_t (&out)[2 * NP], uint32_t tag, bool check) {
-  uint64_t a[NP], b[NP];
-  uint32_t pending = (1u << NP) - 1;
-#pragma unroll
-  for (int i = 0; i < NP; ++i) ll_load2(addr(i), a[i], b[i]);
-  uint32_t spins = 0;
-  while (pending) {
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      if (pending & (1u << i)) {
-        if (!check || (static_cast<uint32_t>(a[i] >> 32) == tag && static_cast<uint32_t>(b[i] >> 32) == tag)) pending &= ~(1u << i);
-        else ll_load2(addr(i), a[i], b[i]);
-      }
-    }
-    if (++spins > EMX_SPIN_LIMIT) __trap();
-  }
-#pragma unroll
-  for (int i = 0; i < NP; ++i) out[2 * i] = static_cast<uint32_t>(a[i]), out[2 * i + 1] = static_cast<uint32_t>(b[i]);
-}
-
 // Block sum over the 8 consumer warps with ONE barrier: per-warp partials go to one of two 8-float buffers (alternating per call, so
 // the next call's writes cannot overtake a slow reader of this call: there is at least one block barrier between two calls), every
 // thread adds the 8 partials itself.
@@ -219,16 +137,6 @@ __device__ __forceinline__ float cblock_sum(float v, float* red, uint32_t parity
   cbar();
   const float4 a = *reinterpret_cast<const float4*>(r), b = *reinterpret_cast<const float4*>(r + 4);
   return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
-}
-
-// Activation vector layout in shared memory: inside every block of 16 words (32 bf16) the 4 x 4 word matrix is transposed.
-// The two B fragments a lane needs for TWO consecutive k-steps of mma.m16n8k16 (words 8j+t, 8j+4+t, 8j+8+t, 8j+12+t,
-// t = lane%4) are then one 16-byte shared load. xs_pos maps a word index of the vector to its position.
-__device__ __forceinline__ int xs_pos(int w) { return (w & ~15) + 4 * (w & 3) + 2 * ((w >> 3) & 1) + ((w >> 2) & 1); }
-
-__device__ __forceinline__ float sumsq2(uint32_t w) {
-  const float a = bf16_lo(w), c = bf16_hi(w);
-  return a * a + c * c;
 }
 
 // The 8 KB norm-weight vectors are streamed once per token, so they are never L2-resident when they are needed, and an
@@ -312,12 +220,6 @@ __device__ __forceinline__ void gather_rmsnorm(const uint64_t* ll, const uint32_
   }
 }
 
-__device__ __forceinline__ long long global_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 // ---- static weight schedule of one CTA: (layer, kind) phases -> 16-row groups ------------------------------------------
 struct SchedIter {
   int layer, kind, r, r_end, layers;
@@ -355,10 +257,6 @@ struct SchedIter {
   __device__ __forceinline__ int nrows() const { return min(DEC_GROUP, r_end - r); }
   __device__ __forceinline__ long group_bytes() const { return static_cast<long>(nrows()) * d.K * 2; }
 };
-
-__device__ __forceinline__ void prefetch_l2(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
 
 // ---- producer warps -------------------------------------------------------------------------------------------------
 // Both producer warps walk the same schedule; warp `pidx` issues the ring stages with it % DEC_PWARPS == pidx.
@@ -483,27 +381,12 @@ __device__ void prefetch_loop(const emx_decode_params& p, int dflags, const Phas
 }
 
 // ---- consumer: tensor-core dot products of one phase ---------------------------------------------------------------------
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
 struct ConsumerState {
   uint32_t it;
   uint32_t group;  // selects the partial-sum buffer / named barrier
   long long waited;        // cycles in mbar_wait(full) (thread 0: warp 0)
   long long t_sync, t_epi;  // cycles warp 0 spent waiting for the other warps' partial sums / in the epilogue
 };
-
-// Hand-off of per-warp partial row sums to warp 0: warps 1..7 arrive and run on, warp 0 waits. One named barrier per
-// partial buffer; a warp can be at most DEC_STAGES ring stages (< DEC_PARTBUFS row groups) ahead of warp 0, so neither a
-// buffer nor a barrier id is reused before warp 0 is done with it.
-__device__ __forceinline__ void part_arrive(uint32_t buf) { asm volatile("bar.arrive %0, %1;" ::"r"(2u + buf), "n"(DEC_CTHREADS) : "memory"); }
-__device__ __forceinline__ void part_sync(uint32_t buf) { asm volatile("bar.sync %0, %1;" ::"r"(2u + buf), "n"(DEC_CTHREADS) : "memory"); }
 
 // epi(row, v0, v1, valid) is called for row pairs (row even) by lanes 0..7 of ONE warp per row group (all eight lanes, converged), rows ascending
 // per lane; valid == false marks lanes beyond the last row of a short group

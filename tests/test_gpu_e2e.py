@@ -291,10 +291,14 @@ def test_full_size_vs_live_oracle(n_new):
 
 
 def test_full_size_unscripted_head_teacher_forced():
-    """Full Emma-X shapes with a plain random lm_head (NO planted script): logits are ~N(0,1), max|logit| ~ 4.5, so the 1e-2-of-max
-    tolerance is ~0.045 absolute - the tight version of the check above, whose scripted rows push max|logit| to ~11. The oracle's own
-    greedy ids are teacher-forced into both paths; every step's logits must agree and the argmax must agree wherever the oracle's top-2
-    margin clears twice the tolerance."""
+    """Full Emma-X shapes with a plain random lm_head (NO planted script): logits are ~N(0,1), max|logit| ~ 5, so the planted rows of
+    the scripted tests (max|logit| ~ 11) no longer widen a relative tolerance. Three runs on the same weights, all teacher-forced with the
+    bf16 oracle's greedy ids: (a) the bf16 oracle (transformers Llama + flash-attn: the reference HF path), (b) the same oracle in FP32
+    (the arithmetic truth), (c) the CUDA path. Accumulated bf16 rounding (65 norms, 64 residual adds, 224 Linears) makes any two bf16
+    implementations with different reduction orders differ by ~0.05-0.08 absolute on these logits; the meaningful bar is therefore
+      * the CUDA path is as close to the fp32 truth as the reference bf16 path is:  err(c, b) <= 1.25 * err(a, b) + 1e-3, max and RMS;
+      * CUDA vs bf16 oracle within 2e-2 * max|logit| at every step (1e-2 holds on the scripted heads, where max|logit| is ~11);
+      * same argmax wherever the fp32 top-2 margin clears the bf16 noise."""
     from emmax_b200 import OpenVLAForActionPrediction, emma_x_config
     from emmax_b200.synthetic import make_state_dict
     from oracle.model import OracleVLA
@@ -303,25 +307,39 @@ def test_full_size_unscripted_head_teacher_forced():
     rng = np.random.default_rng(77)
     input_ids = torch.tensor([[1] + rng.integers(3, 31744, 39).tolist()], dtype=torch.long, device="cuda")
     sd = make_state_dict(cfg, seed=7, device="cuda")
-    oracle = OracleVLA.from_state_dict(cfg, sd, device="cuda", dtype=BF, attn_implementation=_oracle_attn())
     pv = torch.randn((1, 6, 224, 224), generator=torch.Generator(device="cuda").manual_seed(6), device="cuda").to(BF)
     n_new = 32
-    ids_o, logits_o = oracle.generate(input_ids, pv, n_new, eos_token_id=None, return_logits=True)
+    oracle = OracleVLA.from_state_dict(cfg, sd, device="cuda", dtype=BF, attn_implementation=_oracle_attn())
+    ids_o, logits_a = oracle.generate(input_ids, pv, n_new, eos_token_id=None, return_logits=True)
     del oracle
     torch.cuda.empty_cache()
     forced = ids_o[0, input_ids.shape[1] :].tolist()
+    oracle32 = OracleVLA.from_state_dict(cfg, sd, device="cuda", dtype=torch.float32, attn_implementation="sdpa")
+    _, logits_b = oracle32.generate(input_ids, pv.float(), n_new, eos_token_id=None, return_logits=True, forced=forced)
+    del oracle32
+    torch.cuda.empty_cache()
     model = OpenVLAForActionPrediction(cfg, sd).to("cuda")
-    new, logits = model.engine.generate(input_ids, pv, n_new, eos_token_id=None, return_logits=True, forced=forced)
-    assert float(logits_o.abs().max()) < 8.0, "un-scripted logits are expected to be O(1)"
-    err = _rel_err(logits.cpu(), logits_o)
-    assert err < 1e-2, f"un-scripted full-size teacher-forced logits: max|diff| / max|logit| = {err:.4g} (tolerance 1e-2, max|logit| {float(logits_o.abs().max()):.2f})"
-    top2 = logits_o.topk(2, dim=-1).values
+    _, logits_c = model.engine.generate(input_ids, pv, n_new, eos_token_id=None, return_logits=True, forced=forced)
+    logits_c = logits_c.cpu()
+    scale = float(logits_b.abs().max())
+    assert scale < 8.0, "un-scripted logits are expected to be O(1)"
+
+    def errs(x, ref):
+        d = (x.float() - ref.float())
+        return float(d.abs().max()) / scale, float(d.pow(2).mean().sqrt()) / scale
+
+    (ea_max, ea_rms), (ec_max, ec_rms) = errs(logits_a, logits_b), errs(logits_c, logits_b)
+    msg = f"vs fp32 truth (max|logit| {scale:.2f}): bf16 oracle max {ea_max:.4g} rms {ea_rms:.4g} | CUDA path max {ec_max:.4g} rms {ec_rms:.4g}"
+    print(msg)
+    assert ec_max <= 1.25 * ea_max + 1e-3 and ec_rms <= 1.25 * ea_rms + 1e-4, msg
+    err = _rel_err(logits_c, logits_a)
+    assert err < 2e-2, f"CUDA path vs bf16 oracle: max|diff| / max|logit| = {err:.4g} (tolerance 2e-2 on un-scripted O(1) logits)"
+    top2 = logits_b.topk(2, dim=-1).values
     margin = (top2[:, 0] - top2[:, 1]).numpy()
-    tol = 1e-2 * float(logits_o.abs().max())
-    ours = logits.cpu().argmax(-1).numpy()
+    ours = logits_c.argmax(-1).numpy()
     for t in range(n_new):
-        if margin[t] > 2 * tol:
-            assert ours[t] == int(logits_o[t].argmax()), f"step {t}: argmax differs although the oracle margin {margin[t]:.3g} > {2 * tol:.3g}"
+        if margin[t] > 4 * ea_max * scale:
+            assert ours[t] == int(logits_b[t].argmax()), f"step {t}: argmax differs although the fp32 margin {margin[t]:.3g} clears the bf16 noise"
 
 
 def _batched_prefill_check(cfg, sd, B, n_ids, seed, tol):
