@@ -14,6 +14,7 @@ All compute runs in hand-written CUDA kernels (libemmax.so, C ABI in include/emm
 
 from .action_tokenizer import ActionTokenizer
 from .configuration import OpenVLAConfig, PrismaticConfig, emma_x_config, tiny_config
+from .load import load_vla
 from .modeling import AutoConfig, AutoModelForVision2Seq, OpenVLAForActionPrediction, PrismaticCausalLMOutputWithPast
 from .processing import AutoImageProcessor, AutoProcessor, BatchFeature, PrismaticImageProcessor, PrismaticProcessor
 from .prompting import PurePromptBuilder, emma_x_prompt, openvla_prompt
@@ -25,5 +26,5 @@ __all__ = [
     "ActionTokenizer", "AutoConfig", "AutoImageProcessor", "AutoModelForVision2Seq", "AutoProcessor", "BatchFeature",
     "OpenVLAConfig", "OpenVLAForActionPrediction", "OpenVLAInference", "PrismaticCausalLMOutputWithPast", "PrismaticConfig",
     "PrismaticImageProcessor", "PrismaticProcessor", "PurePromptBuilder", "Solver", "SyntheticLlamaTokenizer",
-    "emma_x_config", "emma_x_prompt", "openvla_prompt", "tiny_config",
+    "emma_x_config", "emma_x_prompt", "load_vla", "openvla_prompt", "tiny_config",
 ]  # fmt: skip

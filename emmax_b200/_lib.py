@@ -48,6 +48,33 @@ class DecodeParams(C.Structure):
     ]  # fmt: skip
 
 
+MAX_DECODE_BATCH = 8
+ATT_MAX_SEGMENTS = 16
+
+
+class DecodeBatchState(C.Structure):
+    _fields_ = [
+        ("cur_token", C.c_int32 * 8), ("pos", C.c_int32 * 8), ("n_generated", C.c_int32 * 8), ("finished", C.c_int32 * 8),
+        ("limit", C.c_int32 * 8), ("epoch", C.c_uint32), ("pad_", C.c_uint32 * 7),
+    ]  # fmt: skip
+
+
+class DecodeBatchParams(C.Structure):
+    _fields_ = [
+        ("hidden", C.c_int32), ("inter", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("layers", C.c_int32), ("vocab", C.c_int32), ("rms_eps", C.c_float), ("batch", C.c_int32),
+        ("embed", C.c_void_p), ("w_qkv", C.c_void_p), ("w_o", C.c_void_p), ("w_gateup", C.c_void_p),
+        ("w_down", C.c_void_p), ("ln1", C.c_void_p), ("ln2", C.c_void_p), ("final_norm", C.c_void_p),
+        ("lm_head", C.c_void_p), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
+        ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("block_table", C.c_void_p),
+        ("page_size", C.c_int32), ("n_pages", C.c_int32), ("max_pages", C.c_int32), ("out_stride", C.c_int32),
+        ("x", C.c_void_p), ("xo", C.c_void_p), ("attn", C.c_void_p), ("qkv", C.c_void_p), ("h", C.c_void_p),
+        ("part", C.c_void_p), ("argmax_part", C.c_void_p),
+        ("out_tokens", C.c_void_p), ("logits_out", C.c_void_p), ("state", C.c_void_p), ("dbg", C.c_void_p),
+        ("eos_token", C.c_int32), ("pad_", C.c_int32),
+    ]  # fmt: skip
+
+
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 _SIGNATURES = {
     "emx_last_error": (C.c_char_p, []),
@@ -68,6 +95,8 @@ _SIGNATURES = {
     "emx_gemv_bf16": (_I, [_P, _I, _P, _P, _P, _I, _I, _P]),
     "emx_lmhead_argmax": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P]),
     "emx_decode_step": (_I, [C.POINTER(DecodeParams), _P]),
+    "emx_decode_batch_step": (_I, [C.POINTER(DecodeBatchParams), _P]),
+    "emx_decode_batch_smem": (_I, []),
     "emx_decode_grid": (_I, []),
     "emx_decode_phase_rows": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "emx_detokenize_actions": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P]),

@@ -1,0 +1,834 @@
+// emx_decode_batch_step — one greedy decode step of Llama-2-7B for UP TO 8 SEQUENCES as ONE persistent kernel.
+//
+// The reference cannot do this at all: its cached branch asserts batch size 1
+// (/root/reference/prismatic/extern/hf/modeling_prismatic.py:326, :460-463), so N robots / N simulator environments cost N full
+// passes over the 13.2 GB of weights per token. Single-token decode is HBM-bound and the weight stream is 97 % of its bytes: here
+// one pass over the weights serves 8 sequences (BASELINE.json configs[4]: bs=64 over 8 GPUs = 8 per GPU, mixed 128/512 new tokens).
+//
+// Same skeleton as decode_mega.cu (one CTA per SM, static per-CTA weight schedule streamed by two producer warps through a
+// 3 x 64 KB cp.async.bulk ring, mma.sync.m16n8k16 consumers, no grid barriers: every cross-CTA vector travels as 8-byte LL units),
+// re-thought for a batch:
+//   * the 8 columns of the m16n8k16 B operand — 7 of which are dead weight at batch 1 — are the 8 sequences: thread (g, t) of a
+//     consumer warp feeds column g = sequence g;
+//   * 8 activation vectors (8 x 22 KB for down_proj) do not fit next to the ring in shared memory. They live in TENSOR MEMORY, already
+//     in B-fragment order: a thread gathers exactly the LL units ITS fragments need (the exchange buffers are laid out so that these
+//     are 16-byte runs), normalises them and parks them in its own TMEM lane (tcgen05.st, up to 192 of its 256 columns); the hot loop
+//     pulls 32 columns per ring stage back with one tcgen05.ld. No shared memory, no bank conflicts, no block barrier for the hand-over;
+//   * attention is a phase of the same pipeline: the cached K/V pages of all (sequence, head) rows are one linear list of page-pair
+//     items, split evenly over the CTAs whatever the individual context lengths are (flash-decoding); the producers stream each
+//     CTA's share through the weight ring (16 KB bulk copies straight out of the paged cache), every consumer warp keeps an online-softmax
+//     state for its 16 keys of the stage, and a rotating warp merges the 8 warp states at the end of a row segment and either
+//     publishes the partial (m, l, acc[128]) or — in the CTA that owns the row's last item — folds in the other segments and the
+//     token being decoded (RoPE, KV append, one more online-softmax step) and publishes the head output;
+//   * per-sequence position, block table, RoPE row, token limit and EOS state; sequences that are finished (or slots beyond `batch`)
+//     are inactive: nobody waits for their units, nothing of theirs is stored.
+// Rounding points mirror the torch-eager reference exactly as decode_mega.cu does.
+#include "decode_common.cuh"
+#include "emmax.h"
+
+namespace emx {
+
+constexpr int DB_MAXB = EMX_DECODE_MAX_BATCH;     // sequences per launch == N of the MMA atom
+static_assert(DB_MAXB == 8, "the batch is the N dimension of mma.m16n8k16");
+constexpr int DB_PWARPS = 2;                      // producer warps (alternate ring stages)
+constexpr int DB_THREADS = (DEC_CWARPS + DB_PWARPS) * 32;  // 320
+constexpr int DB_MAX_PAGES = 64;                  // block-table entries per sequence staged in shared memory
+constexpr int DB_MAX_RESID = 64;                  // residual units (row pairs) of this CTA's rows, per sequence
+constexpr int DB_ATT_WSTRIDE = 132;               // floats per warp in an attention partial buffer: acc[128], m, l, pad
+constexpr int DB_PART_FLOATS = 1088;              // one partial buffer: GEMV [8 warps][16 rows][8 seqs] = 1024 | attention 8 x 132 = 1056
+constexpr int DB_MAXSEG = EMX_DECODE_ATT_MAX_SEGMENTS;  // row segments (CTAs) one (sequence, head) row can be split into
+constexpr int DB_LN_BYTES = 8192;                 // norm weights of the next RMSNorm (hidden <= 4096)
+constexpr int DB_PAGE = 64;                       // KV page = 64 tokens (one 16 KB bulk copy per head and page)
+constexpr int DB_PAGE_BYTES = DB_PAGE * DEC_HD * 2;
+constexpr int DB_TMEM_COLS = 512;
+constexpr int DB_PARTU = DEC_HD + 2;              // LL units of one split-KV partial: m, l, acc[128] (fp32 payloads)
+
+constexpr int BPH_STEPS = 7;  // phases per layer
+enum BatchPhase { BPH_Q = 0, BPH_K, BPH_V, BPH_ATT, BPH_O, BPH_GATEUP, BPH_DOWN, BPH_LMHEAD, BPH_KINDS };
+
+struct __align__(16) BatchShared {
+  uint64_t full[DEC_STAGES], empty[DEC_STAGES];
+  float red[2][DEC_CWARPS][DB_MAXB];  // RMSNorm: per-warp sums of squares
+  int tok[DB_MAXB], pos[DB_MAXB], ngen[DB_MAXB];
+  uint32_t active_mask, epoch, tmem_base, pad0;
+  int att_pp[DB_MAXB];       // page pairs (items) per (sequence, head) row
+  int att_off[DB_MAXB + 1];  // first item of sequence i in the linear item list
+  int att_i0, att_i1, att_T;  // this CTA's items [i0, i1) of T
+  const __nv_bfloat16* W[BPH_KINDS];
+  long layer_stride[BPH_KINDS];
+  int N[BPH_KINDS], K[BPH_KINDS], r_begin[BPH_KINDS], r_end[BPH_KINDS];
+  int32_t table[DB_MAXB][DB_MAX_PAGES];
+  uint32_t rope[DB_MAXB][64];  // [32] cos pairs | [32] sin pairs (bf16) of each sequence's position
+  uint32_t resid[DB_MAXB][DB_MAX_RESID];
+};
+constexpr int DB_SMEM = DEC_STAGES * DEC_STAGE_BYTES + DEC_PARTBUFS * DB_PART_FLOATS * 4 + DB_LN_BYTES + static_cast<int>(sizeof(BatchShared));
+static_assert(DB_SMEM <= 232448, "decode_batch_kernel: shared memory exceeds 227 KB");
+
+// Exchange-buffer position of unit u (= bf16 pair u of a vector): inside every block of 16 units the 4 x 4 matrix is transposed, so that
+// the units a thread needs for two consecutive k-steps of mma.m16n8k16 (u = 16 blk + 4 m + t, m = 0..3, t = lane % 4) are the 32-byte run
+// [16 blk + 4 t, 16 blk + 4 t + 4).
+__device__ __forceinline__ int ll_pos(int u) { return (u & ~15) | ((u & 3) << 2) | ((u >> 2) & 3); }
+
+__device__ __forceinline__ bool tag_ok(uint64_t v, uint32_t tag) { return static_cast<uint32_t>(v >> 32) == tag; }
+
+__device__ __forceinline__ void build_phase(const emx_decode_batch_params& p, BatchShared& sh, int kind) {
+  const long H = p.hidden, I = p.inter;
+  const __nv_bfloat16* W = nullptr;
+  long ls = 0;
+  int N = 0, K = 0;
+  switch (kind) {
+    case BPH_Q:
+    case BPH_K:
+    case BPH_V: W = static_cast<const __nv_bfloat16*>(p.w_qkv) + kind * H * H, ls = 3 * H * H, N = H, K = H; break;
+    case BPH_O: W = static_cast<const __nv_bfloat16*>(p.w_o), ls = H * H, N = H, K = H; break;
+    case BPH_GATEUP: W = static_cast<const __nv_bfloat16*>(p.w_gateup), ls = 2 * I * H, N = 2 * I, K = H; break;
+    case BPH_DOWN: W = static_cast<const __nv_bfloat16*>(p.w_down), ls = H * I, N = H, K = I; break;
+    case BPH_LMHEAD: W = static_cast<const __nv_bfloat16*>(p.lm_head), ls = 0, N = p.vocab, K = H; break;
+    default: break;  // BPH_ATT: no weights
+  }
+  sh.W[kind] = W, sh.layer_stride[kind] = ls, sh.N[kind] = N, sh.K[kind] = K;
+  int rb = 0, re = 0;
+  if (N > 0) phase_rows(N, (kind == BPH_GATEUP) ? 4 : 2, blockIdx.x, gridDim.x, rb, re);
+  sh.r_begin[kind] = rb, sh.r_end[kind] = re;
+}
+
+// ---- attention items ---------------------------------------------------------------------------------------------------
+// Item g of the linear list -> (sequence, head, page pair j of that row). att_off is non-decreasing; inactive sequences own no items.
+struct AttItem {
+  int seq, head, j, pp;
+};
+__device__ __forceinline__ AttItem att_item(const BatchShared& sh, int g) {
+  AttItem it;
+  int n = 0;
+#pragma unroll
+  for (int i = 1; i < DB_MAXB; ++i) n += (g >= sh.att_off[i]) ? 1 : 0;
+  it.seq = n, it.pp = sh.att_pp[n];
+  const int rem = g - sh.att_off[n];
+  it.head = rem / it.pp, it.j = rem - it.head * it.pp;
+  return it;
+}
+// element offset of (layer, page, head, slot 0) in the paged cache [layer][page][head][64][128]
+__device__ __forceinline__ long kv_page_off(const emx_decode_batch_params& p, int layer, int page, int head) {
+  return ((static_cast<long>(layer) * p.n_pages + page) * p.heads + head) * (DB_PAGE * DEC_HD);
+}
+
+// ---- producer warps ------------------------------------------------------------------------------------------------------
+// Both walk the same schedule (layer -> q, k, v rows -> this CTA's K/V page pairs -> o, gate/up, down rows; lm_head rows); warp `pidx`
+// issues the ring stages with it % 2 == pidx. They never wait for anything but a free ring slot.
+__device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, const BatchShared& sh, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane,
+                               int pidx) {
+  const uint64_t policy = l2_policy_evict_first();
+  const __nv_bfloat16* kc = static_cast<const __nv_bfloat16*>(p.k_cache);
+  const __nv_bfloat16* vc = static_cast<const __nv_bfloat16*>(p.v_cache);
+  uint32_t it = 0;
+  const int L = p.layers;
+  for (int layer = 0; layer <= L; ++layer) {
+    const int k_first = (layer == L) ? BPH_LMHEAD : BPH_Q, k_last = (layer == L) ? BPH_LMHEAD : BPH_DOWN;
+    for (int kind = k_first; kind <= k_last; ++kind) {
+      if (kind == BPH_ATT) {
+        for (int g = sh.att_i0; g < sh.att_i1; ++g, ++it) {
+          if ((it % DB_PWARPS) != static_cast<uint32_t>(pidx)) continue;
+          const AttItem a = att_item(sh, g);
+          const int pages = (sh.pos[a.seq] + DB_PAGE - 1) / DB_PAGE;
+          const int np = min(2, pages - 2 * a.j);  // pages of this item: K page(s) at [0, 32 K), V page(s) at [32 K, 64 K) of the stage
+          const int slot = it % DEC_STAGES;
+          const uint32_t ph = (it / DEC_STAGES) & 1;
+          if (lane == 0) {
+            mbar_wait(&empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(np) * 2 * DB_PAGE_BYTES);
+          }
+          __syncwarp();
+          if (lane < 2 * np) {
+            const int is_v = lane >= np ? 1 : 0, pg = lane - is_v * np;
+            const long off = kv_page_off(p, layer, sh.table[a.seq][2 * a.j + pg], a.head);
+            bulk_g2s(ring + slot * DEC_STAGE_BYTES + is_v * 2 * DB_PAGE_BYTES + pg * DB_PAGE_BYTES, (is_v ? vc : kc) + off, DB_PAGE_BYTES,
+                     &full[slot], policy);
+          }
+        }
+        continue;
+      }
+      const int K = sh.K[kind], r_end = sh.r_end[kind];
+      const __nv_bfloat16* W = sh.W[kind] + layer * sh.layer_stride[kind];
+      for (int r = sh.r_begin[kind]; r < r_end; r += DEC_GROUP) {
+        const int nrows = min(DEC_GROUP, r_end - r);
+        for (int k0 = 0; k0 < K; k0 += DEC_KC, ++it) {
+          if ((it % DB_PWARPS) != static_cast<uint32_t>(pidx)) continue;
+          const int klen = min(DEC_KC, K - k0);
+          const int slot = it % DEC_STAGES;
+          const uint32_t ph = (it / DEC_STAGES) & 1;
+          if (lane == 0) {
+            mbar_wait(&empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(nrows) * klen * 2);
+          }
+          __syncwarp();
+          if (lane < nrows)
+            bulk_g2s(ring + slot * DEC_STAGE_BYTES + lane * DEC_ROWSTRIDE, W + static_cast<long>(r + lane) * K + k0, klen * 2, &full[slot], policy);
+        }
+      }
+    }
+  }
+}
+
+// ---- gathers: LL exchange buffer -> this thread's B fragments -> tensor memory ----------------------------------------------
+// Thread (warp w, lane = 4 g + t) feeds sequence g. For ring-stage chunk c (2048 columns) warp w multiplies columns
+// [2048 c + 256 w, + 256): 16 k-steps, i.e. 8 blocks of 32 columns = 16 units each, of which this thread needs units 4 m + t (m = 0..3):
+// one 32-byte run per block in ll_pos order, fetched as two 16-byte loads ("pairs"; pair i belongs to k-step i). The 32 payload words of a
+// chunk are TMEM columns [32 c, 32 c + 32) of the thread's lane, in the order the hot loop wants them: word 2 i = b0, 2 i + 1 = b1 of k-step i.
+// The gathers work in HALF chunks (8 k-steps, 8 pairs, 16 TMEM columns), two in flight.
+struct GRaw {
+  uint64_t a[8], b[8];
+};
+__device__ __forceinline__ int chunk_ksteps(int K, int c, int warp) { return max(0, min(DEC_KW / 16, (K - c * DEC_KC - warp * DEC_KW) / 16)); }
+__device__ __forceinline__ int half_ksteps(int K, int hc, int warp) { return max(0, min(8, chunk_ksteps(K, hc >> 1, warp) - 8 * (hc & 1))); }
+__device__ __forceinline__ const uint64_t* g_base(const uint64_t* src, int hc, int warp, int t) {
+  return src + 16 * (64 * (hc >> 1) + 8 * warp + 4 * (hc & 1)) + 4 * t;
+}
+__device__ __forceinline__ uint32_t g_issue(const uint64_t* src, int hc, int warp, int t, int ks, bool act, GRaw& raw) {
+  const uint64_t* base = g_base(src, hc, warp, t);
+  uint32_t pending = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    raw.a[i] = 0, raw.b[i] = 0;
+    if (act && i < ks) {
+      ll_load2(base + 16 * (i >> 1) + 2 * (i & 1), raw.a[i], raw.b[i]);
+      pending |= 1u << i;
+    }
+  }
+  return pending;
+}
+__device__ __forceinline__ void g_poll(const uint64_t* src, int hc, int warp, int t, uint32_t pending, uint32_t tag, GRaw& raw) {
+  const uint64_t* base = g_base(src, hc, warp, t);
+  uint32_t spins = 0;
+  while (pending) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (pending & (1u << i)) {
+        if (tag_ok(raw.a[i], tag) && tag_ok(raw.b[i], tag)) pending &= ~(1u << i);
+        else ll_load2(base + 16 * (i >> 1) + 2 * (i & 1), raw.a[i], raw.b[i]);
+      }
+    }
+    if (++spins > EMX_SPIN_LIMIT) __trap();
+  }
+}
+// natural unit index of payload word q (0..15) of half chunk hc for (warp, t)
+__device__ __forceinline__ int g_unit(int hc, int warp, int t, int q) { return 16 * (64 * (hc >> 1) + 8 * warp + 4 * (hc & 1) + (q >> 2)) + 4 * (q & 3) + t; }
+
+// Walk the half chunks of a K-element vector with two fetches in flight; take(hc, raw, ks) sees every half chunk this warp owns.
+template <typename Take>
+__device__ __forceinline__ void g_walk(const uint64_t* src, int K, int warp, int t, bool act, uint32_t tag, Take&& take) {
+  const int nh = 2 * ((K + DEC_KC - 1) / DEC_KC);
+  GRaw A, B;
+  uint32_t pa = g_issue(src, 0, warp, t, half_ksteps(K, 0, warp), act, A), pb = 0;
+#pragma unroll 1
+  for (int hc = 0; hc < nh; hc += 2) {
+    pb = g_issue(src, hc + 1, warp, t, half_ksteps(K, hc + 1, warp), act, B);
+    g_poll(src, hc, warp, t, pa, tag, A);
+    take(hc, A, half_ksteps(K, hc, warp));
+    if (hc + 2 < nh) pa = g_issue(src, hc + 2, warp, t, half_ksteps(K, hc + 2, warp), act, A);
+    g_poll(src, hc + 1, warp, t, pb, tag, B);
+    take(hc + 1, B, half_ksteps(K, hc + 1, warp));
+  }
+}
+
+// A plain vector per sequence (attention output for o_proj, SwiGLU output for down_proj): gather -> TMEM.
+__device__ __noinline__ void gather_plain_b(const uint64_t* buf, long seq_stride, int K, uint32_t tag, uint32_t tm, uint32_t active_mask, int warp, int lane) {
+  const int n = lane >> 2, t = lane & 3;
+  g_walk(buf + n * seq_stride, K, warp, t, (active_mask >> n) & 1, tag, [&](int hc, const GRaw& raw, int ks) {
+    if (ks > 0) {  // warp-uniform
+      uint32_t r[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[2 * i] = static_cast<uint32_t>(raw.a[i]), r[2 * i + 1] = static_cast<uint32_t>(raw.b[i]);
+      tmem_st_32x16(tm + 16 * hc, r);
+    }
+  });
+  tmem_st_wait();
+}
+
+__device__ __forceinline__ void ln_fetch_async_b(const __nv_bfloat16* w, uint32_t* ln_s, int H) {
+  for (int i = threadIdx.x; i < (H >> 3); i += DEC_CTHREADS)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ln_s + 4 * i)), "l"(reinterpret_cast<const uint4*>(w) + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Residual stream in (LL units, or the embedding rows for layer 0) -> LlamaRMSNorm -> TMEM:  y = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))
+// Pass 1 parks the raw words in TMEM while summing squares, pass 2 normalises them in place. The CTA's own rows of the residual stream
+// are kept in shared memory for the residual add of the next o_proj / down_proj epilogue.
+__device__ __noinline__ void gather_rmsnorm_b(const uint64_t* buf, long seq_stride, const __nv_bfloat16* embed, int H, uint32_t tag, uint32_t tm, BatchShared& sh,
+                                              const uint32_t* ln_s, float eps, uint32_t parity, int rb2, int re2, int warp, int lane) {
+  const int n = lane >> 2, t = lane & 3;
+  const bool act = (sh.active_mask >> n) & 1;
+  const int nh = 2 * ((H + DEC_KC - 1) / DEC_KC);
+  float ss = 0.f;
+  auto park = [&](int hc, const uint32_t (&r)[16], int ks) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if ((q >> 1) < ks) {
+        ss += sumsq2(r[q]);
+        const int u = g_unit(hc, warp, t, q);
+        if (act && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
+      }
+    }
+    tmem_st_32x16(tm + 16 * hc, r);
+  };
+  if (embed) {  // layer 0: plain bf16 rows of the embedding table
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(embed + static_cast<long>(sh.tok[n]) * H);
+#pragma unroll 1
+    for (int hc = 0; hc < nh; ++hc) {
+      const int ks = half_ksteps(H, hc, warp);
+      if (ks > 0) {
+        uint32_t r[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) r[q] = (act && (q >> 1) < ks) ? __ldg(row + g_unit(hc, warp, t, q)) : 0u;
+        park(hc, r, ks);
+      }
+    }
+  } else {
+    g_walk(buf + n * seq_stride, H, warp, t, act, tag, [&](int hc, const GRaw& raw, int ks) {
+      if (ks > 0) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[2 * i] = static_cast<uint32_t>(raw.a[i]), r[2 * i + 1] = static_cast<uint32_t>(raw.b[i]);
+        park(hc, r, ks);
+      }
+    });
+  }
+  // sum of squares of sequence n: the 4 lanes of a quad, then the 8 warps
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  if (t == 0) sh.red[parity & 1][warp][n] = ss;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's share of the norm weights has landed
+  tmem_st_wait();
+  cbar();  // partial sums and everybody's norm weights are visible
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < DEC_CWARPS; ++w) tot += sh.red[parity & 1][w][n];
+  const float rs = 1.0f / sqrtf(tot / H + eps);
+#pragma unroll 1
+  for (int hc = 0; hc < nh; ++hc) {
+    const int ks = half_ksteps(H, hc, warp);
+    if (ks > 0) {
+      uint32_t r[16];
+      tmem_ld_32x16(tm + 16 * hc, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        if ((q >> 1) < ks) {
+          const uint32_t g = ln_s[g_unit(hc, warp, t, q)], v = r[q];
+          r[q] = pack_bf16(bf16_lo(g) * bf16_round(bf16_lo(v) * rs), bf16_hi(g) * bf16_round(bf16_hi(v) * rs));
+        }
+      }
+      tmem_st_32x16(tm + 16 * hc, r);
+    }
+  }
+  tmem_st_wait();
+  cbar();  // everybody is done with ln_s: the next norm's weights may be fetched into it
+}
+
+// ---- consumer: tensor-core dot products of one weight phase, 8 sequences at once ---------------------------------------------
+struct BCons {
+  uint32_t it;     // ring stage counter
+  uint32_t group;  // row groups / attention flushes so far: selects the partial buffer, its named barrier and the rotating warp
+};
+
+// epi(row, v[4], n) is called by all 32 lanes of ONE warp per row group: lane = 8 a + n handles rows row .. row + 3 (row = r0 + 4 a) of
+// sequence n; rows >= r_end (short last group) must be ignored by the callee.
+template <typename Epi>
+__device__ __forceinline__ void consume_phase_b(int K, int r_begin, int r_end, const uint8_t* ring, uint64_t* full, uint64_t* empty, BCons& cs, uint32_t tm,
+                                                float* part, int warp, int lane, Epi&& epi) {
+  const uint32_t a_lane_off = ((lane & 7) + ((lane >> 3) & 1) * 8) * DEC_ROWSTRIDE + (lane >> 4) * 16;
+  const int kbeg = warp * DEC_KW;
+  for (int r0 = r_begin; r0 < r_end; r0 += DEC_GROUP) {
+    float c[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = c[q][2] = c[q][3] = 0.f;
+    int chunk = 0;
+    for (int k0 = 0; k0 < K; k0 += DEC_KC, ++chunk) {
+      const int klen = min(DEC_KC, K - k0);
+      const int slot = cs.it % DEC_STAGES;
+      const uint32_t ph = (cs.it / DEC_STAGES) & 1;
+      const int ksteps = min(DEC_KW / 16, (klen - kbeg) / 16);  // <= 0: this warp's slice is past the K tail
+      uint32_t b[32];
+      if (ksteps > 0) tmem_ld_32x32(tm + 32 * chunk, b);  // in flight while the stage lands
+      mbar_wait(&full[slot], ph);
+      if (ksteps > 0) {
+        tmem_ld_wait();
+        const uint32_t a_base = smem_u32(ring + slot * DEC_STAGE_BYTES) + a_lane_off + kbeg * 2;
+        if (ksteps == DEC_KW / 16) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {  // two batches of 8 k-steps: 8 ldmatrix in flight, then 8 HMMA on four accumulator chains
+            uint32_t a[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ldmatrix_x4(a_base + (h * 8 + j) * 32, a[j][0], a[j][1], a[j][2], a[j][3]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_bf16_16816(c[j & 3], a[j][0], a[j][1], a[j][2], a[j][3], b[2 * (h * 8 + j)], b[2 * (h * 8 + j) + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < DEC_KW / 16; ++j) {
+            if (j < ksteps) {
+              uint32_t a0, a1, a2, a3;
+              ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
+              mma_bf16_16816(c[j & 3], a0, a1, a2, a3, b[2 * j], b[2 * j + 1]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+      ++cs.it;
+    }
+    // accumulator tile: c[.][0..1] -> row lane/4, sequences 2 t, 2 t + 1; c[.][2..3] -> row lane/4 + 8
+    const uint32_t buf = cs.group % DEC_PARTBUFS;
+    float* pb = part + buf * DB_PART_FLOATS;
+    {
+      const int g = lane >> 2, t = lane & 3;
+      *reinterpret_cast<float2*>(pb + warp * 128 + g * 8 + 2 * t) = make_float2((c[0][0] + c[1][0]) + (c[2][0] + c[3][0]), (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]));
+      *reinterpret_cast<float2*>(pb + warp * 128 + (g + 8) * 8 + 2 * t) =
+          make_float2((c[0][2] + c[1][2]) + (c[2][2] + c[3][2]), (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]));
+    }
+    if (warp == static_cast<int>(cs.group % DEC_CWARPS)) {  // rotating epilogue duty (see decode_mega.cu)
+      part_sync(buf);
+      const int n = lane & 7, a = lane >> 3;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int w = 0; w < DEC_CWARPS; ++w) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += pb[w * 128 + (4 * a + i) * 8 + n];
+      }
+      epi(r0 + 4 * a, v, n);
+      __syncwarp();
+    } else {
+      part_arrive(buf);
+    }
+    ++cs.group;
+  }
+}
+
+// ---- attention phase -----------------------------------------------------------------------------------------------------
+struct AttState {
+  float m, l, acc[4], q[4];
+  int row;  // (sequence * heads + head) the state and q belong to, -1: none
+};
+
+// 4 consecutive elements (4 lane .. 4 lane + 3) of a 128-wide head vector out of LL units, optionally through RoPE (rotate_half form:
+// the partner element d +- 64 lives in lane ^ 16). x_embed = bf16(bf16(x cos) + bf16(rotate_half(x) sin)), tables are bf16.
+__device__ __forceinline__ void load_head4(const uint64_t* units, const uint32_t* rope, int lane, uint32_t tag, float (&out)[4]) {
+  uint32_t w[2];
+  ll_fetch_pairs<1>([&](int) { return units + 2 * lane; }, w, tag, true);
+  const float x[4] = {bf16_lo(w[0]), bf16_hi(w[0]), bf16_lo(w[1]), bf16_hi(w[1])};
+  if (!rope) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = x[e];
+    return;
+  }
+  const int ci = (2 * lane) & 31;
+  const uint32_t cw[2] = {rope[ci], rope[ci + 1]}, sw[2] = {rope[32 + ci], rope[32 + ci + 1]};
+  const float sgn = (lane < 16) ? -1.f : 1.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float pr = __shfl_xor_sync(0xffffffffu, x[e], 16);
+    const float cs = (e & 1) ? bf16_hi(cw[e >> 1]) : bf16_lo(cw[e >> 1]), sn = (e & 1) ? bf16_hi(sw[e >> 1]) : bf16_lo(sw[e >> 1]);
+    out[e] = bf16_round(bf16_round(x[e] * cs) + bf16_round(sgn * pr * sn));
+  }
+}
+
+// One online-softmax step of this warp over its 16 keys of the stage (keys 16 warp .. 16 warp + 15 of the item's 128; K rows at
+// [page][row][128] from byte 0, V rows from byte 32 K). Lane l owns head elements 4 l .. 4 l + 3 of q, K, V and the accumulator.
+__device__ __forceinline__ void att_block(const uint8_t* stage, int warp, int lane, int nvalid, float scale, AttState& s) {
+  const uint8_t* kb = stage + (warp >> 2) * DB_PAGE_BYTES + (warp & 3) * 16 * (DEC_HD * 2) + lane * 8;
+  const uint8_t* vb = kb + 2 * DB_PAGE_BYTES;
+  float pr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint2 kw = *reinterpret_cast<const uint2*>(kb + i * (DEC_HD * 2));
+    pr[i] = fmaf(s.q[3], bf16_hi(kw.y), fmaf(s.q[2], bf16_lo(kw.y), fmaf(s.q[1], bf16_hi(kw.x), s.q[0] * bf16_lo(kw.x))));
+  }
+  // transposing butterfly: 16 partial dot products per lane -> the complete score of key (lane >> 1) in every lane
+  float v8[8], v4[4], v2[2], sc;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = (up ? pr[i + 8] : pr[i]) + __shfl_xor_sync(0xffffffffu, up ? pr[i] : pr[i + 8], 16);
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v4[i] = (up ? v8[i + 4] : v8[i]) + __shfl_xor_sync(0xffffffffu, up ? v8[i] : v8[i + 4], 8);
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) v2[i] = (up ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, up ? v4[i] : v4[i + 2], 4);
+  }
+  {
+    const bool up = lane & 2;
+    sc = (up ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, up ? v2[0] : v2[1], 2);
+  }
+  sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+  const bool valid = (lane >> 1) < nvalid;
+  sc = valid ? sc * scale : -INFINITY;
+  const float m_new = fmaxf(s.m, warp_max(sc));  // finite: nvalid >= 1
+  const float pk = valid ? __expf(sc - m_new) : 0.f;
+  const float lsum = warp_sum((lane & 1) ? 0.f : pk);  // every key sits in two lanes
+  const float corr = __expf(s.m - m_new);              // exp(-inf) = 0 on the first block
+  s.l = s.l * corr + lsum, s.m = m_new;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) s.acc[e] *= corr;
+  const float pb = bf16_round(pk);  // flash-attn: P is bf16 for the PV product, the row sum stays fp32
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float pi = __shfl_sync(0xffffffffu, pb, 2 * i);
+    if (i < nvalid) {  // rows beyond the valid keys may hold anything
+      const uint2 vw = *reinterpret_cast<const uint2*>(vb + i * (DEC_HD * 2));
+      s.acc[0] = fmaf(pi, bf16_lo(vw.x), s.acc[0]), s.acc[1] = fmaf(pi, bf16_hi(vw.x), s.acc[1]);
+      s.acc[2] = fmaf(pi, bf16_lo(vw.y), s.acc[2]), s.acc[3] = fmaf(pi, bf16_hi(vw.y), s.acc[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void att_merge(float& M, float& den, float (&num)[4], float m2, float l2, const float (&a2)[4]) {
+  if (l2 > 0.f) {
+    const float Mn = fmaxf(M, m2);
+    const float wo = (M == -INFINITY) ? 0.f : __expf(M - Mn), wn = __expf(m2 - Mn);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) num[e] = num[e] * wo + a2[e] * wn;
+    den = den * wo + l2 * wn, M = Mn;
+  }
+}
+
+// End of a row segment, run by the rotating warp once all 8 warp states are in `pb`: merge them; if the row goes on in the next CTA
+// publish the partial, otherwise (this CTA owns the row's last item) fold in the segments of the CTAs before us and the token being
+// decoded, append its K/V to the cache and publish the head output in o_proj's exchange order.
+__device__ void att_finish(const emx_decode_batch_params& p, const BatchShared& sh, const float* pb, int lane, const AttItem& it, int g, int layer,
+                           uint32_t tag, const float (&q)[4], float scale) {
+  float M = -INFINITY, den = 0.f, num[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int w = 0; w < DEC_CWARPS; ++w) {
+    const float4 a = *reinterpret_cast<const float4*>(pb + w * DB_ATT_WSTRIDE + 4 * lane);
+    const float a4[4] = {a.x, a.y, a.z, a.w};
+    att_merge(M, den, num, pb[w * DB_ATT_WSTRIDE + DEC_HD], pb[w * DB_ATT_WSTRIDE + DEC_HD + 1], a4);
+  }
+  const int n = it.seq, H = p.hidden;
+  const int row_start = sh.att_off[n] + it.head * it.pp;
+  const int seg_start = max(sh.att_i0, row_start);
+  uint64_t* rowpart = static_cast<uint64_t*>(p.part) + (static_cast<long>(n) * p.heads + it.head) * (DB_MAXSEG * DB_PARTU);
+  if (it.j != it.pp - 1) {  // (then g is the last item of this CTA)
+    uint64_t* dst = rowpart + (seg_start - row_start) * DB_PARTU;
+    if (lane == 0) ll_store(dst, __float_as_uint(M), tag), ll_store(dst + 1, __float_as_uint(den), tag);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ll_store(dst + 2 + 4 * lane + e, __float_as_uint(num[e]), tag);
+    return;
+  }
+  // ---- segments of the CTAs before this one (owner(g) = the CTA c with T c / G <= g < T (c + 1) / G)
+  const long T = sh.att_T, G = gridDim.x;
+  for (int gc = row_start; gc < seg_start;) {
+    const long c = ((gc + 1) * G - 1) / T;
+    const uint64_t* src = rowpart + (gc - row_start) * DB_PARTU;
+    uint32_t w[6];
+    ll_fetch_pairs<3>([&](int i) -> const uint64_t* { return i == 0 ? src : src + 2 + 4 * lane + 2 * (i - 1); }, w, tag, true);
+    const float a4[4] = {__uint_as_float(w[2]), __uint_as_float(w[3]), __uint_as_float(w[4]), __uint_as_float(w[5])};
+    att_merge(M, den, num, __uint_as_float(w[0]), __uint_as_float(w[1]), a4);
+    gc = static_cast<int>(T * (c + 1) / G);
+  }
+  // ---- the token being decoded: k (RoPE) and v arrive from the projection phases of this layer
+  const uint64_t* qkv = static_cast<const uint64_t*>(p.qkv) + static_cast<long>(n) * (3 * H / 2);
+  const int pos = sh.pos[n];
+  float kr[4], vn[4];
+  load_head4(qkv + H / 2 + it.head * (DEC_HD / 2), sh.rope[n], lane, tag, kr);
+  load_head4(qkv + H + it.head * (DEC_HD / 2), nullptr, lane, tag, vn);
+  const long dst = kv_page_off(p, layer, sh.table[n][pos / DB_PAGE], it.head) + (pos % DB_PAGE) * DEC_HD + 4 * lane;
+  *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.k_cache) + dst) = make_uint2(pack_bf16(kr[0], kr[1]), pack_bf16(kr[2], kr[3]));
+  *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.v_cache) + dst) = make_uint2(pack_bf16(vn[0], vn[1]), pack_bf16(vn[2], vn[3]));
+  const float s_new = warp_sum(fmaf(q[3], kr[3], fmaf(q[2], kr[2], fmaf(q[1], kr[1], q[0] * kr[0])))) * scale;
+  const float Mn = fmaxf(M, s_new);
+  const float wo = (M == -INFINITY) ? 0.f : __expf(M - Mn), pn = __expf(s_new - Mn), pnb = bf16_round(pn);
+  den = den * wo + pn;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) num[e] = (num[e] * wo + pnb * vn[e]) / den;
+  uint64_t* attn = static_cast<uint64_t*>(p.attn) + static_cast<long>(n) * ((H / 2 + 15) & ~15);
+  const int u = it.head * (DEC_HD / 2) + 2 * lane;
+  ll_store(attn + ll_pos(u), pack_bf16(num[0], num[1]), tag);
+  ll_store(attn + ll_pos(u + 1), pack_bf16(num[2], num[3]), tag);
+}
+
+__device__ __noinline__ void attention_phase_b(const emx_decode_batch_params& p, const BatchShared& sh, const uint8_t* ring, uint64_t* full, uint64_t* empty, BCons& cs,
+                                  float* part, int layer, uint32_t tag, int warp, int lane) {
+  const float scale = rsqrtf(static_cast<float>(DEC_HD));
+  const int i0 = sh.att_i0, i1 = sh.att_i1;
+  AttState s;
+  s.row = -1, s.m = -INFINITY, s.l = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) s.acc[e] = 0.f, s.q[e] = 0.f;
+#pragma unroll 1
+  for (int g = i0; g < i1; ++g) {
+    const AttItem it = att_item(sh, g);
+    const int row = it.seq * p.heads + it.head;
+    if (row != s.row) {  // new row: q of (sequence, head) — projected two phases ago, long there
+      s.row = row, s.m = -INFINITY, s.l = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s.acc[e] = 0.f;
+      load_head4(static_cast<const uint64_t*>(p.qkv) + static_cast<long>(it.seq) * (3 * p.hidden / 2) + it.head * (DEC_HD / 2), sh.rope[it.seq], lane, tag, s.q);
+    }
+    const int slot = cs.it % DEC_STAGES;
+    const uint32_t ph = (cs.it / DEC_STAGES) & 1;
+    mbar_wait(&full[slot], ph);
+    const int nvalid = min(16, sh.pos[it.seq] - (128 * it.j + 16 * warp));  // cached keys are positions 0 .. pos - 1
+    if (nvalid > 0) att_block(ring + slot * DEC_STAGE_BYTES, warp, lane, nvalid, scale, s);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+    ++cs.it;
+    if (it.j == it.pp - 1 || g == i1 - 1) {  // end of the row, or of this CTA's share of it
+      const uint32_t buf = cs.group % DEC_PARTBUFS;
+      float* pb = part + buf * DB_PART_FLOATS;
+      *reinterpret_cast<float4*>(pb + warp * DB_ATT_WSTRIDE + 4 * lane) = make_float4(s.acc[0], s.acc[1], s.acc[2], s.acc[3]);
+      if (lane == 0) pb[warp * DB_ATT_WSTRIDE + DEC_HD] = s.m, pb[warp * DB_ATT_WSTRIDE + DEC_HD + 1] = s.l;
+      if (warp == static_cast<int>(cs.group % DEC_CWARPS)) {
+        part_sync(buf);
+        att_finish(p, sh, pb, lane, it, g, layer, tag, s.q, scale);
+        __syncwarp();
+      } else {
+        part_arrive(buf);
+      }
+      ++cs.group;
+      s.row = -1;  // (a new segment of the same row cannot follow inside one CTA, but the state must restart)
+    }
+  }
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------------
+template <bool PROF>
+__global__ void __maxnreg__(200) decode_batch_kernel(const emx_decode_batch_params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* ring = smem;
+  float* part = reinterpret_cast<float*>(smem + DEC_STAGES * DEC_STAGE_BYTES);
+  uint32_t* ln_s = reinterpret_cast<uint32_t*>(part + DEC_PARTBUFS * DB_PART_FLOATS);
+  BatchShared& sh = *reinterpret_cast<BatchShared*>(reinterpret_cast<uint8_t*>(ln_s) + DB_LN_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  emx_decode_batch_state* st = p.state;
+
+  if (tid < DB_MAXB) {
+    const int n = tid;
+    const int tok = static_cast<int>(ldg_cg_u32(&st->cur_token[n])), pos = static_cast<int>(ldg_cg_u32(&st->pos[n]));
+    const int ngen = static_cast<int>(ldg_cg_u32(&st->n_generated[n])), fin = static_cast<int>(ldg_cg_u32(&st->finished[n]));
+    const int lim = static_cast<int>(ldg_cg_u32(&st->limit[n]));
+    // active: a live sequence with room for one more token (KV cache, RoPE tables and out_tokens all end at these limits) and at
+    // least one cached key (a prefill always leaves some)
+    const bool act = n < p.batch && !fin && ngen < lim && ngen < p.out_stride && pos >= 1 && pos < p.max_pages * DB_PAGE;
+    sh.tok[n] = min(max(tok, 0), p.vocab - 1), sh.pos[n] = act ? pos : 0, sh.ngen[n] = ngen;
+    const uint32_t m = __ballot_sync(0xffu, act);
+    if (tid == 0) sh.active_mask = m, sh.epoch = ldg_cg_u32(&st->epoch);
+  }
+  if (tid >= 32 && tid < 32 + BPH_KINDS) build_phase(p, sh, tid - 32);
+  if (tid == 64) {
+    for (int s = 0; s < DEC_STAGES; ++s) {
+      mbar_init(&sh.full[s], 1);
+      mbar_init(&sh.empty[s], DEC_CWARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint32_t active_mask = sh.active_mask;
+  if (!active_mask) return;  // every sequence is finished: nothing to do, uniformly
+  for (int i = tid; i < DB_MAXB * p.max_pages; i += DB_THREADS) {
+    const int n = i / p.max_pages, pg = i - n * p.max_pages;
+    sh.table[n][pg] = ((active_mask >> n) & 1) ? __ldg(p.block_table + i) : 0;
+  }
+  for (int i = tid; i < DB_MAXB * 64; i += DB_THREADS) {
+    const int n = i >> 6, j = i & 63;
+    const uint32_t* tabp = reinterpret_cast<const uint32_t*>(j < 32 ? p.cos_tab : p.sin_tab);
+    sh.rope[n][j] = ((active_mask >> n) & 1) ? __ldg(tabp + static_cast<long>(sh.pos[n]) * (DEC_HD / 4) + (j & 31)) : 0u;
+  }
+  if (tid == 0) {
+    int T = 0;
+    for (int n = 0; n < DB_MAXB; ++n) {
+      const int pages = (sh.pos[n] + DB_PAGE - 1) / DB_PAGE;  // 0 for inactive sequences
+      sh.att_pp[n] = (pages + 1) / 2, sh.att_off[n] = T;
+      T += sh.att_pp[n] * p.heads;
+    }
+    sh.att_off[DB_MAXB] = T, sh.att_T = T;
+    sh.att_i0 = static_cast<int>(static_cast<long>(T) * blockIdx.x / gridDim.x);
+    sh.att_i1 = static_cast<int>(static_cast<long>(T) * (blockIdx.x + 1) / gridDim.x);
+  }
+  if (warp == 0) tmem_alloc(&sh.tmem_base, DB_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp >= DEC_CWARPS) {
+    batch_producer(p, sh, ring, sh.full, sh.empty, lane, warp - DEC_CWARPS);
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  const int L = p.layers, H = p.hidden, I = p.inter;
+  const long sH = (H / 2 + 15) & ~15, sI = (I / 2 + 15) & ~15;  // per-sequence strides (units) of the ll_pos-ordered buffers
+  const uint32_t tag0 = sh.epoch * static_cast<uint32_t>(L + 2) + 1u;  // tag0 + l: layer l; + L: final norm; + L + 1: argmax candidates
+  // this thread's TMEM lane and its half of the 512 columns (two consumer warps share a lane quarter)
+  const uint32_t tm = sh.tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) * 256);
+  uint64_t* xd = static_cast<uint64_t*>(p.x);
+  uint64_t* xo = static_cast<uint64_t*>(p.xo);
+  uint64_t* qkv = static_cast<uint64_t*>(p.qkv);
+  uint64_t* attn = static_cast<uint64_t*>(p.attn);
+  uint64_t* hbuf = static_cast<uint64_t*>(p.h);
+  const int rb = sh.r_begin[BPH_O], rb2 = rb >> 1, re2 = sh.r_end[BPH_O] >> 1;
+  long long* dbg = (PROF && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
+
+  BCons cs{0, 0};
+  float best = -INFINITY;  // lm_head: this lane's best logit of ITS sequence (lane & 7)
+  int best_i = 0x7fffffff;
+
+  ln_fetch_async_b(static_cast<const __nv_bfloat16*>(p.ln1), ln_s, H);
+  const int n_steps = BPH_STEPS * L + 1;
+  int layer = 0, kind = BPH_Q;
+#pragma unroll 1
+  for (int step = 0; step < n_steps; ++step) {
+    const uint32_t tag = tag0 + layer;  // (the lm_head step has layer == L)
+    if (PROF && dbg) dbg[2 * step] = global_ns();
+    if (kind == BPH_Q || kind == BPH_GATEUP || kind == BPH_LMHEAD) {
+      gather_rmsnorm_b(kind == BPH_GATEUP ? xo : xd, sH, step == 0 ? static_cast<const __nv_bfloat16*>(p.embed) : nullptr, H, tag, tm, sh, ln_s, p.rms_eps,
+                       kind == BPH_GATEUP ? 1u : 0u, rb2, re2, warp, lane);
+      if (kind != BPH_LMHEAD) {
+        const __nv_bfloat16* next_w = (kind == BPH_Q)    ? static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H
+                                      : (layer + 1 < L) ? static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer + 1) * H
+                                                        : static_cast<const __nv_bfloat16*>(p.final_norm);
+        ln_fetch_async_b(next_w, ln_s, H);
+      }
+    } else if (kind == BPH_O || kind == BPH_DOWN) {  // a plain vector in: the attention output for o_proj, the SwiGLU output for down_proj
+      const bool o = (kind == BPH_O);
+      gather_plain_b(o ? attn : hbuf, o ? sH : sI, o ? H : I, tag, tm, active_mask, warp, lane);
+    }
+    if (PROF && dbg) dbg[2 * step + 1] = global_ns();
+    if (kind == BPH_ATT) {
+      attention_phase_b(p, sh, ring, sh.full, sh.empty, cs, part, layer, tag, warp, lane);
+    } else {
+      consume_phase_b(sh.K[kind], sh.r_begin[kind], sh.r_end[kind], ring, sh.full, sh.empty, cs, tm, part, warp, lane,
+                      [&](int row, const float (&v)[4], int n) {
+                        const int r_end = sh.r_end[kind];
+                        if (!((active_mask >> n) & 1) || row >= r_end) return;
+                        const bool two = row + 2 < r_end;  // rows row + 2, row + 3 exist (always, for gate/up quads)
+                        if (kind <= BPH_V) {
+                          uint64_t* dst = qkv + static_cast<long>(n) * (3 * H / 2) + kind * (H >> 1) + (row >> 1);
+                          ll_store(dst, pack_bf16(v[0], v[1]), tag);
+                          if (two) ll_store(dst + 1, pack_bf16(v[2], v[3]), tag);
+                        } else if (kind == BPH_GATEUP) {
+                          // rows (gate_i, up_i, gate_i+1, up_i+1): two SwiGLU outputs = one unit
+                          const float h0 = bf16_round(bf16_round(silu(bf16_round(v[0]))) * bf16_round(v[1]));
+                          const float h1 = bf16_round(bf16_round(silu(bf16_round(v[2]))) * bf16_round(v[3]));
+                          ll_store(hbuf + n * sI + ll_pos(row >> 2), pack_bf16(h0, h1), tag);
+                        } else if (kind == BPH_LMHEAD) {
+#pragma unroll
+                          for (int i = 0; i < 4; ++i) {
+                            if (row + i < r_end) {
+                              const float lv = bf16_round(v[i]);
+                              if (p.logits_out) p.logits_out[static_cast<long>(n) * p.vocab + row + i] = lv;
+                              if (lv > best) best = lv, best_i = row + i;  // rows ascend per thread: strict '>' keeps the lowest index
+                            }
+                          }
+                        } else {  // o_proj / down_proj: + residual; down_proj feeds the NEXT layer (tag + 1)
+                          uint64_t* dst = (kind == BPH_O ? xo : xd) + n * sH;
+                          const uint32_t t2 = (kind == BPH_O) ? tag : tag + 1;
+                          const int u = row >> 1;
+                          const uint32_t r0 = sh.resid[n][u - rb2];
+                          ll_store(dst + ll_pos(u), pack_bf16(bf16_lo(r0) + bf16_round(v[0]), bf16_hi(r0) + bf16_round(v[1])), t2);
+                          if (two) {
+                            const uint32_t r1 = sh.resid[n][u + 1 - rb2];
+                            ll_store(dst + ll_pos(u + 1), pack_bf16(bf16_lo(r1) + bf16_round(v[2]), bf16_hi(r1) + bf16_round(v[3])), t2);
+                          }
+                        }
+                      });
+    }
+    if (++kind == BPH_LMHEAD) {
+      kind = BPH_Q;
+      if (++layer == L) kind = BPH_LMHEAD;
+    }
+  }
+  if (PROF && dbg) dbg[2 * n_steps] = global_ns();
+
+  // ---- greedy argmax per sequence: lanes -> CTA -> grid (lowest index wins ties, as torch.argmax) ----
+  cbar();  // every epilogue is done: the partial buffers are free
+  float* s_bv = part;
+  int* s_bi = reinterpret_cast<int*>(part + DEC_CTHREADS);
+  s_bv[tid] = best, s_bi[tid] = best_i;
+  cbar();
+  const uint32_t tag_a = tag0 + L + 1;
+  uint64_t* cand = static_cast<uint64_t*>(p.argmax_part);  // [grid][8][2] units: value bits, index
+  if (tid < DB_MAXB) {
+    float b = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int k = 0; k < DEC_CTHREADS / DB_MAXB; ++k) {  // lanes with lane % 8 == tid of every warp
+      const float v = s_bv[8 * k + tid];
+      const int i = s_bi[8 * k + tid];
+      if (v > b || (v == b && i < bi)) b = v, bi = i;
+    }
+    ll_store(cand + (blockIdx.x * DB_MAXB + tid) * 2, __float_as_uint(b), tag_a);
+    ll_store(cand + (blockIdx.x * DB_MAXB + tid) * 2 + 1, static_cast<uint32_t>(bi), tag_a);
+  }
+  if (blockIdx.x == 0) {
+    const int n = warp;  // consumer warp n of CTA 0 finishes sequence n
+    if ((active_mask >> n) & 1) {
+      float b = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < static_cast<int>(gridDim.x); c += 32) {
+        const float v = __uint_as_float(ll_wait(cand + (c * DB_MAXB + n) * 2, tag_a, true));
+        const int i = static_cast<int>(ll_wait(cand + (c * DB_MAXB + n) * 2 + 1, tag_a, true));
+        if (v > b || (v == b && i < bi)) b = v, bi = i;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, b, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > b || (ob == b && oi < bi)) b = ob, bi = oi;
+      }
+      if (lane == 0) {
+        const int ng = sh.ngen[n];
+        p.out_tokens[static_cast<long>(n) * p.out_stride + ng] = bi;
+        st->cur_token[n] = bi;
+        st->pos[n] = sh.pos[n] + 1;
+        st->n_generated[n] = ng + 1;
+        if (p.eos_token >= 0 && bi == p.eos_token) st->finished[n] = 1;
+      }
+    }
+    if (tid == 0) st->epoch = sh.epoch + 1u;
+  }
+  tc_fence_before();
+  cbar();
+  if (warp == 0) tmem_dealloc(sh.tmem_base, DB_TMEM_COLS);
+}
+
+}  // namespace emx
+
+extern "C" int emx_decode_batch_step(const emx_decode_batch_params* params, cudaStream_t stream) {
+  using namespace emx;
+  const emx_decode_batch_params& p = *params;
+  EMX_REQUIRE(p.head_dim == DEC_HD, "emx_decode_batch_step: head_dim %d not supported (128)", p.head_dim);
+  EMX_REQUIRE(p.batch >= 1 && p.batch <= DB_MAXB, "emx_decode_batch_step: batch %d not in 1..%d", p.batch, DB_MAXB);
+  EMX_REQUIRE(p.hidden % 16 == 0 && p.inter % 16 == 0 && p.vocab % 2 == 0, "emx_decode_batch_step: hidden/inter must be multiples of 16, vocab even");
+  EMX_REQUIRE(p.heads * DEC_HD == p.hidden, "emx_decode_batch_step: heads x head_dim must equal hidden");
+  EMX_REQUIRE(p.x && p.xo && p.qkv && p.attn && p.h && p.part && p.argmax_part && p.state && p.out_tokens && p.block_table,
+              "emx_decode_batch_step: null pointer");
+  EMX_REQUIRE(p.hidden * 2 <= DB_LN_BYTES, "emx_decode_batch_step: hidden > %d not supported by the fused gather + RMSNorm", DB_LN_BYTES / 2);
+  EMX_REQUIRE(p.inter <= 8 * DEC_KC && p.hidden <= 8 * DEC_KC, "emx_decode_batch_step: activation vector exceeds the 256 TMEM columns of a thread");
+  EMX_REQUIRE(p.page_size == DB_PAGE, "emx_decode_batch_step: page_size must be %d", DB_PAGE);
+  EMX_REQUIRE(p.max_pages >= 1 && p.max_pages <= DB_MAX_PAGES && p.max_pages <= 2 * DB_MAXSEG,
+              "emx_decode_batch_step: block table of %d pages exceeds %d", p.max_pages, 2 * DB_MAXSEG);
+  EMX_REQUIRE(p.out_stride >= 1, "emx_decode_batch_step: out_stride");
+  int dev = 0;
+  const int grid = device_sms(&dev);
+  bool* attr_set = device_attr_flag(ATTR_DECODE_BATCH);
+  if (grid < 0 || !attr_set) return -2;
+  if (!*attr_set) {
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(decode_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM));
+    int per_sm = 0;
+    EMX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_batch_kernel<true>, DB_THREADS, DB_SMEM));
+    EMX_REQUIRE(per_sm >= 1, "emx_decode_batch_step: kernel does not fit on an SM (smem %d)", DB_SMEM);
+    *attr_set = true;
+  }
+  EMX_REQUIRE(p.hidden / 2 / grid + 2 <= DB_MAX_RESID, "emx_decode_batch_step: hidden too large for the residual staging buffer");
+  void* args[] = {const_cast<emx_decode_batch_params*>(params)};
+  void* fn = p.dbg ? reinterpret_cast<void*>(decode_batch_kernel<true>) : reinterpret_cast<void*>(decode_batch_kernel<false>);
+  EMX_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(DB_THREADS), args, DB_SMEM, stream));
+  return 0;
+}
+
+extern "C" int emx_decode_batch_smem(void) { return emx::DB_SMEM; }

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import EPI_GELU, EPI_SWIGLU, DecodeParams, DecodeState, call, ptr, stream
+from ._lib import ATT_MAX_SEGMENTS, EPI_GELU, EPI_SWIGLU, MAX_DECODE_BATCH, DecodeBatchParams, DecodeBatchState, DecodeParams, DecodeState, call, ptr, stream
 from .configuration import OpenVLAConfig, ViTDims
 
 BF16 = torch.bfloat16
@@ -65,7 +65,7 @@ class Engine:
         self.max_batch, self.kv_splits = max_batch, kv_splits
         self.l2_lookahead_kb = int(os.environ.get("EMX_L2_LOOKAHEAD_KB", "256"))  # idle-triggered L2 prefetch window per CTA
         self.max_context = _ceil_to(max_context, self.PAGE)
-        self._graphs: Dict[Tuple[int, int], Tuple[torch.cuda.CUDAGraph, int]] = {}
+        self._graphs: Dict[Tuple[int, int, int], Tuple[torch.cuda.CUDAGraph, int]] = {}
         self.last_decode = None
         self._side: Optional[torch.cuda.Stream] = None  # second vision tower at small batch
         with torch.cuda.device(device):
@@ -246,8 +246,9 @@ class Engine:
     def _layer_cache(self, cache: torch.Tensor, layer: int) -> int:
         return cache.data_ptr() + layer * self.layer_cache_bytes
 
-    def _llm_prefill(self, ws: dict, B: int, n_ids: int) -> None:
-        """multimodal assembly + full-sequence Llama forward, KV written to the paged cache (modeling_prismatic.py:380-415)"""
+    def _llm_prefill(self, ws: dict, B: int, n_ids: int, slot: int = 0) -> None:
+        """multimodal assembly + full-sequence Llama forward, KV written to the paged cache of sequences slot .. slot + B - 1
+        (modeling_prismatic.py:380-415)"""
         t, cfg = self.t, self.config
         H, I, L, S = t.hidden_size, t.intermediate_size, t.num_hidden_layers, ws["S"]
         heads, hd = t.num_attention_heads, t.head_dim
@@ -256,7 +257,7 @@ class Engine:
             call("emx_rmsnorm", ptr(ws["x"]), ptr(self.ln1[l]), ptr(ws["n"]), B * S, H, t.rms_norm_eps, stream())
             self.gemm(ws["n"], self.w_qkv[l], ws["qkv"])
             call("emx_rope_kvstore", ptr(ws["qkv"]), B, S, heads, hd, ptr(self.cos_tab), ptr(self.sin_tab), 0,
-                 self._layer_cache(self.k_cache, l), self._layer_cache(self.v_cache, l), ptr(self.block_table),
+                 self._layer_cache(self.k_cache, l), self._layer_cache(self.v_cache, l), self.block_table[slot].data_ptr(),
                  self.pages_per_seq, self.PAGE, stream())  # fmt: skip
             call("emx_attn_fwd", ptr(ws["qkv"]), ptr(ws["att"]), B, S, heads, hd, 1, hd**-0.5, stream())
             self.gemm(ws["att"], self.w_o[l], ws["x"], resid=ws["x"])
@@ -270,19 +271,20 @@ class Engine:
             call("emx_lmhead_argmax", ptr(self.lm_head), H, ptr(ws["last_n"][b]), t.vocab_size, H, ptr(ws["logits"][b]),
                  ptr(ws["first"][b : b + 1]), None, stream())  # fmt: skip
 
-    def _prefill_body(self, ws: dict, B: int, n_ids: int) -> None:
+    def _prefill_body(self, ws: dict, B: int, n_ids: int, slot: int = 0) -> None:
         self._vision(ws, B)
         self._projector(ws)
-        self._llm_prefill(ws, B, n_ids)
+        self._llm_prefill(ws, B, n_ids, slot)
 
     # ------------------------------------------------------------------------------------------------------------
     @_on_engine_device
     @torch.no_grad()
-    def prefill(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, use_graph: bool = True) -> dict:
-        """Vision + projector + LLM prefill for B same-length prompts. Returns the workspace (first tokens, logits, features)."""
+    def prefill(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, use_graph: bool = True, slot: int = 0) -> dict:
+        """Vision + projector + LLM prefill for B same-length prompts, into the KV pages of sequences slot .. slot + B - 1.
+        Returns the workspace (first tokens, logits, features)."""
         B, n_ids = input_ids.shape
-        if B > self.max_batch:
-            raise ValueError(f"batch {B} exceeds engine capacity {self.max_batch}")
+        if slot < 0 or slot + B > self.max_batch:
+            raise ValueError(f"batch {B} at slot {slot} exceeds engine capacity {self.max_batch}")
         S = n_ids + self.config.num_patches
         if S + 1 > self.max_context:
             raise ValueError(f"prompt of {S} positions does not fit max_context={self.max_context}")
@@ -290,17 +292,17 @@ class Engine:
         ws["ids"].copy_(input_ids, non_blocking=True)
         ws["pixels"].copy_(pixel_values, non_blocking=True)
         if not use_graph:
-            self._prefill_body(ws, B, n_ids)
+            self._prefill_body(ws, B, n_ids, slot)
             return ws
-        key = (B, n_ids)
+        key = (B, n_ids, slot)
         if key not in self._graphs:
             # warm-up once outside capture (sets func attributes / driver entry points), then capture
-            self._prefill_body(ws, B, n_ids)
+            self._prefill_body(ws, B, n_ids, slot)
             torch.cuda.current_stream().synchronize()
             before = _lib.launch_count
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._prefill_body(ws, B, n_ids)
+                self._prefill_body(ws, B, n_ids, slot)
             self._graphs[key] = (g, _lib.launch_count - before)
             _lib.count_launches(before - _lib.launch_count)  # capture enqueued nothing
         g, n_kernels = self._graphs[key]
@@ -381,3 +383,125 @@ class Engine:
         self.last_decode = (ev0, ev1, n_launched, S)  # bench.py: average decode-step duration on this stream
         n = int(st[2].item())  # device -> host sync point (the reference syncs every token)
         return self.d_out_tokens[:n].clone(), (logits[:n] if return_logits else None)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # batched decode: up to 8 sequences share one pass over the weights per token (emx_decode_batch_step)
+    # ------------------------------------------------------------------------------------------------------------
+    def _alloc_batch(self) -> None:
+        if getattr(self, "b_state", None) is not None:
+            return
+        dev, t = self.device, self.t
+        H, I = t.hidden_size, t.intermediate_size
+        R = lambda n: _ceil_to(n, 16)  # noqa: E731
+        ll = lambda n: torch.zeros(n, dtype=torch.int64, device=dev)  # noqa: E731
+        MB = MAX_DECODE_BATCH
+        grid = _lib.load().emx_decode_grid()
+        self.b_x, self.b_xo, self.b_attn = ll(MB * R(H // 2)), ll(MB * R(H // 2)), ll(MB * R(H // 2))
+        self.b_qkv, self.b_h = ll(MB * 3 * H // 2), ll(MB * R(I // 2))
+        self.b_part = ll(MB * t.num_attention_heads * ATT_MAX_SEGMENTS * (t.head_dim + 2))
+        self.b_argmax = ll(grid * MB * 2)
+        self.b_state = torch.zeros(C.sizeof(DecodeBatchState) // 4, dtype=torch.int32, device=dev)
+        self.b_out = torch.zeros((MB, self.max_new), dtype=torch.int32, device=dev)
+        self.h_bflag = torch.zeros(C.sizeof(DecodeBatchState) // 4, dtype=torch.int32).pin_memory()
+
+    def _decode_batch_params(self, B: int) -> DecodeBatchParams:
+        t = self.t
+        p = DecodeBatchParams()
+        p.hidden, p.inter, p.heads, p.head_dim = t.hidden_size, t.intermediate_size, t.num_attention_heads, t.head_dim
+        p.layers, p.vocab, p.rms_eps, p.batch = t.num_hidden_layers, t.vocab_size, t.rms_norm_eps, B
+        p.embed, p.w_qkv, p.w_o, p.w_gateup, p.w_down = ptr(self.embed), ptr(self.w_qkv), ptr(self.w_o), ptr(self.w_gateup), ptr(self.w_down)
+        p.ln1, p.ln2, p.final_norm, p.lm_head = ptr(self.ln1), ptr(self.ln2), ptr(self.final_norm), ptr(self.lm_head)
+        p.cos_tab, p.sin_tab = ptr(self.cos_tab), ptr(self.sin_tab)
+        p.k_cache, p.v_cache, p.block_table = ptr(self.k_cache), ptr(self.v_cache), ptr(self.block_table)
+        p.page_size, p.n_pages, p.max_pages, p.out_stride = self.PAGE, self.n_pages, self.pages_per_seq, self.b_out.shape[1]
+        p.x, p.xo, p.attn, p.qkv, p.h = ptr(self.b_x), ptr(self.b_xo), ptr(self.b_attn), ptr(self.b_qkv), ptr(self.b_h)
+        p.part, p.argmax_part = ptr(self.b_part), ptr(self.b_argmax)
+        p.out_tokens, p.logits_out, p.state, p.dbg = ptr(self.b_out), None, ptr(self.b_state), None
+        p.eos_token = -1
+        return p
+
+    @_on_engine_device
+    @torch.no_grad()
+    def generate_batch(self, input_ids, pixel_values: torch.Tensor, max_new_tokens, eos_token_id: Optional[int] = 2,
+                       return_logits: bool = False, forced: Optional[List[List[int]]] = None, use_graph: bool = True,
+                       poll_every: int = 32) -> Tuple[List[torch.Tensor], Optional[torch.Tensor]]:  # fmt: skip
+        """Greedy decode of B <= 8 sequences at once — what the reference refuses to do (bs == 1 asserts, modeling_prismatic.py:326,
+        :460-463). `input_ids`: [B, n_ids] tensor (one batched prefill) or a list of B [1, n_i] tensors of different lengths (prefilled one
+        by one into their KV slots); `max_new_tokens`: int or one int per sequence (BASELINE.json configs[4]: mixed 128 / 512).
+        Returns (list of B int32 id tensors, optional logits [steps, 8, vocab])."""
+        same_len = isinstance(input_ids, torch.Tensor)
+        B = input_ids.shape[0] if same_len else len(input_ids)
+        if not 1 <= B <= min(MAX_DECODE_BATCH, self.max_batch):
+            raise ValueError(f"batch {B} not in 1..{min(MAX_DECODE_BATCH, self.max_batch)} (engine max_batch={self.max_batch})")
+        if self.pages_per_seq > 2 * ATT_MAX_SEGMENTS:
+            raise ValueError(f"batched decode supports contexts up to {2 * ATT_MAX_SEGMENTS * self.PAGE} (max_context={self.max_context})")
+        limits = [int(max_new_tokens)] * B if isinstance(max_new_tokens, int) else [int(x) for x in max_new_tokens]
+        if len(limits) != B or min(limits) < 1:
+            raise ValueError("max_new_tokens: one positive int, or one per sequence")
+        P = self.config.num_patches
+        lens = [input_ids.shape[1]] * B if same_len else [int(x.shape[1]) for x in input_ids]
+        for b in range(B):
+            if lens[b] + P + limits[b] > self.max_context:
+                raise ValueError(f"sequence {b}: {lens[b] + P} prompt positions + {limits[b]} new tokens exceed max_context={self.max_context}")
+        self._alloc_batch()
+        V, dev = self.t.vocab_size, self.device
+        T = max(limits)
+        MB = MAX_DECODE_BATCH
+        logits = torch.zeros((T, MB, V), dtype=torch.float32, device=dev) if return_logits else None
+        first = torch.empty(B, dtype=torch.int32, device=dev)
+        if same_len:
+            ws = self.prefill(input_ids, pixel_values, use_graph=use_graph)
+            first.copy_(ws["first"][:B])
+            if return_logits:
+                logits[0, :B].copy_(ws["logits"][:B])
+        else:
+            for b in range(B):
+                ws = self.prefill(input_ids[b], pixel_values[b : b + 1], use_graph=use_graph, slot=b)
+                first[b : b + 1].copy_(ws["first"][0:1])
+                if return_logits:
+                    logits[0, b].copy_(ws["logits"][0])
+        st = self.b_state.view(-1)
+        st[: 5 * MB].zero_()  # (the kernel-private epoch word stays)
+        cur = first if forced is None else torch.tensor([f[0] for f in forced], dtype=torch.int32, device=dev)
+        st[0:B].copy_(cur)
+        st[MB : MB + B].copy_(torch.tensor([n + P for n in lens], dtype=torch.int32, device=dev))
+        st[2 * MB : 2 * MB + B].fill_(1)
+        use_eos = eos_token_id is not None and forced is None
+        if use_eos:
+            st[3 * MB : 3 * MB + B].copy_((first == eos_token_id).to(torch.int32))
+        st[4 * MB : 4 * MB + B].copy_(torch.tensor(limits, dtype=torch.int32, device=dev))
+        self.b_out[:B, 0].copy_(first)
+        p = self._decode_batch_params(B)
+        p.eos_token = int(eos_token_id) if use_eos else -1
+        lib = _lib.load()
+        s = stream()
+        pending = None
+        forced_t = None
+        if forced is not None:  # teacher forcing: row `step` of [T, B] overwrites the tokens the next launch embeds
+            forced_t = torch.zeros((T, B), dtype=torch.int32, device=dev)
+            for b, f in enumerate(forced):
+                forced_t[: len(f), b] = torch.tensor(f, dtype=torch.int32, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        n_launched = 0
+        for step in range(1, T):
+            if return_logits:
+                p.logits_out = logits[step].data_ptr()
+            _lib.check(lib.emx_decode_batch_step(C.byref(p), s))
+            n_launched += 1
+            if forced_t is not None:
+                st[0:B].copy_(forced_t[step])
+            if use_eos and step % poll_every == 0:
+                # lagging, non-blocking poll: stop once every sequence is finished or at its limit (state copied one chunk ago)
+                if pending is not None and pending.query():
+                    hf = self.h_bflag
+                    if all(int(hf[3 * MB + b]) != 0 or int(hf[2 * MB + b]) >= limits[b] for b in range(B)):
+                        break
+                self.h_bflag.copy_(st, non_blocking=True)
+                pending = torch.cuda.Event()
+                pending.record()
+        ev1.record()
+        _lib.count_launches(n_launched)
+        self.last_decode_batch = (ev0, ev1, n_launched, [n + P for n in lens], limits)
+        n_gen = st[2 * MB : 2 * MB + B].tolist()  # device -> host sync point
+        return [self.b_out[b, : n_gen[b]].clone() for b in range(B)], logits

@@ -18,7 +18,7 @@ import json
 import os
 from collections.abc import Mapping
 from dataclasses import dataclass
-from typing import Any, Dict, List, Optional, Tuple, Union
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -67,6 +67,10 @@ def _load_checkpoint_tensors(path: str) -> Dict[str, torch.Tensor]:
             raise FileNotFoundError(f"no weights under {path}")
         sd = torch.load(os.path.join(path, pts[0]), map_location="cpu")
         sd = sd.get("model", sd)
+        if isinstance(sd.get("llm_backbone"), dict):  # a native Prismatic checkpoint (component dicts): apply the converter's name map
+            from .load import remap_native_state_dict
+
+            sd = remap_native_state_dict(sd)
     return sd
 
 
@@ -132,8 +136,10 @@ class OpenVLAForActionPrediction:
         for a in args:
             if isinstance(a, (str, torch.device)):
                 device = a
-            elif isinstance(a, torch.dtype) and a != torch.bfloat16:
-                raise NotImplementedError("emmax_b200 computes in bf16")
+            elif isinstance(a, torch.dtype):
+                self._check_dtype(a)
+        if isinstance(kwargs.get("dtype"), torch.dtype):
+            self._check_dtype(kwargs["dtype"])
         if device is None:
             return self
         device = torch.device(device)
@@ -147,6 +153,16 @@ class OpenVLAForActionPrediction:
         elif self._engine.device != device:
             raise NotImplementedError("moving a materialised engine between devices is not supported; build a replica instead")
         return self
+
+    @staticmethod
+    def _check_dtype(dtype: torch.dtype) -> None:
+        if dtype == torch.float16:
+            # experiments/robot/robot_utils.py:42 moves the natively loaded model with `.to(device, dtype=torch.float16)`
+            import warnings
+
+            warnings.warn("emmax_b200 computes in bf16 (the reference HF path's dtype, openvla_utils.py:46); the float16 request is ignored", stacklevel=3)
+        elif dtype != torch.bfloat16:
+            raise NotImplementedError("emmax_b200 computes in bf16")
 
     def cuda(self, device: Optional[int] = None) -> "OpenVLAForActionPrediction":
         return self.to(torch.device("cuda", device if device is not None else torch.cuda.current_device()))
@@ -250,8 +266,49 @@ class OpenVLAForActionPrediction:
         pixel_values = self.vision_backbone.image_transform(image)[None, ...]
         return self._generate_actions_ids(input_ids, pixel_values, tok, kind, **kwargs)
 
+    # ---- batched requests: an extension over the reference, whose cached generation asserts batch size 1 --------------
+    @torch.no_grad()
+    def generate_batch(self, input_ids: Sequence[torch.Tensor], pixel_values: Sequence[torch.Tensor], max_new_tokens: Union[int, Sequence[int]] = 512,
+                       eos_token_id: Union[int, None, str] = "default") -> List[torch.Tensor]:  # fmt: skip
+        """N independent requests (prompt ids [1, n_i], pixel_values [1, 6, h, w] each; N robots or N simulator environments) decoded
+        8 at a time with ONE pass over the weights per token for the whole group (Engine.generate_batch / emx_decode_batch_step) - where
+        the reference raises "Generation with batch size > 1 is not currently supported!" (modeling_prismatic.py:460-463) and a caller
+        has to loop. Every request's result is what its own bs=1 `generate` returns: [1, n_i + T_i] ids."""
+        N = len(input_ids)
+        limits = [int(max_new_tokens)] * N if isinstance(max_new_tokens, int) else [int(x) for x in max_new_tokens]
+        eos = self.config.text_config.eos_token_id if eos_token_id == "default" else eos_token_id
+        eng, dev = self.engine, self.device
+        group = min(_lib.MAX_DECODE_BATCH, eng.max_batch)
+        out: List[torch.Tensor] = []
+        for g0 in range(0, N, group):
+            ids = [x.to(dev) for x in input_ids[g0 : g0 + group]]
+            pv = torch.cat([x.to(dev, torch.bfloat16) for x in pixel_values[g0 : g0 + group]], dim=0)
+            same = len({x.shape[1] for x in ids}) == 1
+            new, _ = eng.generate_batch(torch.cat(ids, dim=0) if same else ids, pv, limits[g0 : g0 + group], eos_token_id=eos)
+            out += [torch.cat([ids[b], new[b].to(torch.long)[None]], dim=1) for b in range(len(ids))]
+        return out
+
+    @torch.no_grad()
+    def generate_actions_batch(self, inputs: Sequence[Mapping], tokenizer: Any = None, type: str = "act",  # noqa: A002
+                               max_new_tokens: Union[int, Sequence[int]] = 512, do_sample: bool = False) -> List[Tuple[Any, str]]:
+        """`generate_actions(inputs, tokenizer, ...)` (README.md:44-47) for a list of processor outputs at once: one (action[7], reasoning)
+        per request, each identical to its own bs=1 call."""
+        if do_sample:
+            raise NotImplementedError("only greedy decoding (do_sample=False) is implemented, as used by the reference callers")
+        tokenizer = tokenizer if tokenizer is not None else self._tokenizer
+        gen = self.generate_batch([i["input_ids"] for i in inputs], [i["pixel_values"] for i in inputs], max_new_tokens)
+        res = []
+        for i, g in zip(inputs, gen):
+            acts, text = self._parse_generated(g, i["input_ids"].shape[1], tokenizer, type)
+            res.append((acts[0] if type == "act" else acts, text))
+        return res
+
     def _generate_actions_ids(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, tokenizer: Any, kind: str, **gen_kwargs: Any):
         generated = self.generate(input_ids=input_ids, pixel_values=pixel_values, **gen_kwargs)
+        return self._parse_generated(generated, input_ids.shape[1], tokenizer, kind)
+
+    def _parse_generated(self, generated: torch.Tensor, n_prompt: int, tokenizer: Any, kind: str):
+        input_ids = generated[:, :n_prompt]
         text = tokenizer.decode(generated[0, input_ids.shape[1] :], skip_special_tokens=True).strip()
         solver = self.solver if tokenizer is self._tokenizer else Solver(ActionTokenizer(tokenizer), verbose=False)
         if kind == "act":

@@ -171,6 +171,67 @@ int emx_decode_grid(void);
  * (granule 2 = row pairs; 4 = gate/up quads). Runs on the host; used by the CPU tests. */
 int emx_decode_phase_rows(int n_rows, int granule, int cta, int grid, int* r_begin, int* r_end);
 
+/* ---- persistent decode step, up to 8 sequences per launch ------------------------------------------------------
+ * ONE launch = one new token for EACH active sequence of a batch of <= 8 (BASELINE.json configs[4]: bs=64 over 8 GPUs = 8 per GPU,
+ * mixed max_new_tokens). The reference has no counterpart: its cached branch asserts batch size 1 (modeling_prismatic.py:326,
+ * :460-463), i.e. N requests cost N passes over the 13.2 GB of weights per token; here one pass serves 8 sequences (they are the 8
+ * columns of the mma.m16n8k16 B operand). Same machinery as emx_decode_step (weight ring, LL exchanges, no grid barriers), plus:
+ * activation vectors of all sequences parked in tensor memory in B-fragment order; attention over a linear list of K/V page-pair items
+ * split evenly over the CTAs for any mix of context lengths, the pages streamed through the weight ring. page_size must be 64,
+ * contexts up to 2048. Per sequence i: state->cur_token[i], pos[i], n_generated[i], finished[i] as in emx_decode_state, plus
+ * limit[i] = the sequence's max_new_tokens (it goes inactive when n_generated[i] reaches it). Inactive sequences (i >= batch, finished,
+ * at their limit, out of cache) cost nothing and nothing of theirs is written. */
+#define EMX_DECODE_MAX_BATCH 8
+#define EMX_DECODE_ATT_MAX_SEGMENTS 16
+typedef struct emx_decode_batch_state {
+  int32_t cur_token[EMX_DECODE_MAX_BATCH];
+  int32_t pos[EMX_DECODE_MAX_BATCH];
+  int32_t n_generated[EMX_DECODE_MAX_BATCH];
+  int32_t finished[EMX_DECODE_MAX_BATCH];
+  int32_t limit[EMX_DECODE_MAX_BATCH];
+  uint32_t epoch; /* kernel-private: completed launches; zero once at allocation */
+  uint32_t pad_[7];
+} emx_decode_batch_state;
+
+typedef struct emx_decode_batch_params {
+  int32_t hidden, inter, heads, head_dim, layers, vocab;
+  float rms_eps;
+  int32_t batch;         /* sequences in use, 1..8 */
+  const void* embed;     /* weights: layouts as in emx_decode_params */
+  const void* w_qkv;
+  const void* w_o;
+  const void* w_gateup;
+  const void* w_down;
+  const void* ln1;
+  const void* ln2;
+  const void* final_norm;
+  const void* lm_head;
+  const void* cos_tab;
+  const void* sin_tab;
+  void* k_cache;         /* [layers][n_pages][heads][64][head_dim] */
+  void* v_cache;
+  const int32_t* block_table; /* [batch][max_pages] */
+  int32_t page_size, n_pages, max_pages, out_stride;
+  /* exchange buffers (8-byte LL units, zeroed once at allocation, then owned by the kernel); R(n) = n rounded up to a multiple of 16 */
+  void* x;        /* [8][R(hidden/2)]: residual stream after down_proj */
+  void* xo;       /* [8][R(hidden/2)]: residual stream after o_proj */
+  void* attn;     /* [8][R(hidden/2)] */
+  void* qkv;      /* [8][3*hidden/2] */
+  void* h;        /* [8][R(inter/2)]: SwiGLU output */
+  void* part;     /* [8][heads][EMX_DECODE_ATT_MAX_SEGMENTS][head_dim + 2]: split-KV partials (fp32 payloads) */
+  void* argmax_part; /* [grid][8][2] */
+  int32_t* out_tokens;  /* out_tokens[i * out_stride + n_generated[i]] = new token of sequence i */
+  float* logits_out;    /* optional [8][vocab] fp32 (bf16-rounded values), for parity tests */
+  emx_decode_batch_state* state;
+  int64_t* dbg;         /* optional (>= 2 * (7 * layers + 1) + 1 int64): CTA 0 stores %globaltimer before / after every phase's gather; selects the instrumented twin */
+  int32_t eos_token;    /* -1 disables EOS handling */
+  int32_t pad_;
+} emx_decode_batch_params;
+
+int emx_decode_batch_step(const emx_decode_batch_params* params, emx_stream_t stream);
+/* dynamic shared memory of the batched decode kernel (host-side query, no CUDA call) */
+int emx_decode_batch_smem(void);
+
 /* ---- action de-tokeniser (device twin of ActionTokenizer.decode_token_ids_to_actions + un-normalise) ---------
  * ids [n] int32 -> normalized[n], actions[n] fp64:  k = clip(vocab - id - 1, 0, n_bins-2); c = centres[k];
  * actions = mask ? 0.5*(c+1)*(q99-q01)+q01 : c.   action_tokenizer.py:49-68; modeling_prismatic.py:522-535.

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [s for s in sorted(declared) if not hasattr(handle, s)]
     assert not missing, missing
     assert set(lib.EXPORTS) == declared, set(lib.EXPORTS) ^ declared
-    assert handle.emx_arch() == b"sm_100a" and handle.emx_abi_version() == 2 and handle.emx_decode_grid() == 148
+    assert handle.emx_arch() == b"sm_100a" and handle.emx_abi_version() == 3 and handle.emx_decode_grid() == 148
 
 
 def test_ctypes_structs_match_c_layout(lib):
@@ -177,3 +177,60 @@ def test_checkpoint_dir_without_tokenizer_warns(tmp_path):
         tok = load_tokenizer(str(tmp_path))
     assert isinstance(tok, SyntheticLlamaTokenizer)
     assert isinstance(load_tokenizer(None), SyntheticLlamaTokenizer)
+
+
+def test_native_run_dir_loader_name_map(tmp_path):
+    """`load_vla(<run>/checkpoints/x.pt)` (prismatic/models/load.py:122-228): the native component dicts are renamed exactly as
+    convert_openvla_weights_to_hf.py:74-116 does (projector.{0,2,4} -> fc{1,2,3}, llm. -> language_model., dino_/siglip_featurizer. ->
+    vision_backbone.(fused_)featurizer., .gamma -> .scale_factor), statistics and proprio stats are attached, and the reference's own
+    path validation applies."""
+    import json
+
+    from emmax_b200 import load_vla, tiny_config
+    from emmax_b200.load import BASE_VLM_REGISTRY, remap_native_state_dict, to_native_state_dict
+    from emmax_b200.synthetic import make_state_dict
+
+    cfg = tiny_config()
+    sd = make_state_dict(cfg, seed=5)
+    native = to_native_state_dict(sd)
+    assert set(native) == {"vision_backbone", "projector", "llm_backbone"}
+    assert "projector.0.weight" in native["projector"] and "projector.4.bias" in native["projector"]
+    assert "llm.model.embed_tokens.weight" in native["llm_backbone"] and "llm.lm_head.weight" in native["llm_backbone"]
+    assert "dino_featurizer.blocks.0.ls1.gamma" in native["vision_backbone"] and "siglip_featurizer.pos_embed" in native["vision_backbone"]
+    assert not any("scale_factor" in k for k in native["vision_backbone"])
+    back = remap_native_state_dict(native)
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+
+    run = tmp_path / "run-1"
+    (run / "checkpoints").mkdir(parents=True)
+    torch.save({"model": native}, run / "checkpoints" / "latest-checkpoint.pt")
+    stats = {"bridge_orig": {"action": {"q01": [-1.0] * 7, "q99": [1.0] * 7, "mask": [True] * 6 + [False]}}}
+    with pytest.raises(AssertionError):  # config.json missing
+        load_vla(run / "checkpoints" / "latest-checkpoint.pt")
+    with open(run / "config.json", "w") as f:
+        json.dump({"vla": {"base_vlm": "prism-dinosiglip-224px+7b", "vla_id": "emma-x"}}, f)
+    with open(run / "dataset_statistics.json", "w") as f:
+        json.dump(stats, f)
+    with pytest.warns(UserWarning, match="SYNTHETIC"):  # no tokenizer files in the run dir
+        vla = load_vla(run / "checkpoints" / "latest-checkpoint.pt", proprio_norm_stats={"Q1": [0.0] * 7, "Q99": [1.0] * 7}, config=cfg)
+    assert set(vla._sd) == set(sd) and all(torch.equal(vla._sd[k], sd[k]) for k in sd)
+    assert vla.norm_stats == stats and vla.get_action_dim() == 7 and vla.get_proprio_stats()["Q99"] == [1.0] * 7
+    # registry lookup (no override): the Emma-X base VLM resolves to the accelerated backbone pair at full Llama-2-7B size
+    with pytest.warns(UserWarning, match="SYNTHETIC"):
+        full = load_vla(str(run / "checkpoints" / "latest-checkpoint.pt"))
+    assert full.config.vision_backbone_id == "dinosiglip-vit-so-224px" and full.config.text_config.hidden_size == 4096
+    assert full.config.text_config.rms_norm_eps == 1e-5 and BASE_VLM_REGISTRY["prism-dinosiglip-224px+7b"]["image_resize_strategy"] == "resize-naive"
+    # reference validation: wrong location / hub ids
+    bad = tmp_path / "x.pt"
+    torch.save({"model": native}, bad)
+    with pytest.raises(AssertionError, match="Invalid checkpoint"):
+        load_vla(bad)
+    with pytest.raises(ValueError, match="Couldn't find valid HF Hub Path"):
+        load_vla("emma-x-7b")
+    # the HF-style directory loader accepts the same native file too
+    from emmax_b200.modeling import _load_checkpoint_tensors
+
+    assert set(_load_checkpoint_tensors(str(run / "checkpoints"))) == set(sd)
+    # experiments/robot/robot_utils.py:42 asks for float16; the engine stays bf16 and says so
+    with pytest.warns(UserWarning, match="bf16"):
+        vla._check_dtype(torch.float16)

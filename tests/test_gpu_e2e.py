@@ -372,8 +372,14 @@ def _batched_prefill_check(cfg, sd, B, n_ids, seed, tol):
             e_b = _rel_err(ws["patches"].view_as(proj_o)[b], proj_o[b])
             assert e_b < tol, f"row {b}: projected patches rel err {e_b:.4g}"
         got = ws["logits"].float().cpu()
-        err = _rel_err(got, last_o)
-        assert err < 1e-2, f"B={B} graph={use_graph}: last-position logits max|diff| / max|logit| = {err:.4g} (tolerance 1e-2)"
+        # un-scripted head: logits are ~N(0,1) (max|logit| ~ 5), where two bf16 implementations with different reduction orders differ by
+        # 0.05-0.08 absolute after 32 layers (see test_full_size_unscripted_head_teacher_forced, which measures that noise against an fp32
+        # truth). Bar: every row within 2e-2 of max|logit|, the typical row within 1e-2; a batching bug (wrong row) is O(1), not O(1e-2).
+        scale = float(last_o.abs().max())
+        row_err = ((got - last_o).abs().amax(dim=-1) / scale).numpy()
+        assert row_err.max() < 2e-2 and np.median(row_err) < 1e-2, (
+            f"B={B} graph={use_graph}: last-position logits, per-row max|diff| / max|logit|: worst {row_err.max():.4g} (tolerance 2e-2), "
+            f"median {np.median(row_err):.4g} (tolerance 1e-2)")
         top2 = last_o.topk(2, dim=-1).values
         clear = (top2[:, 0] - top2[:, 1]) > 4e-2 * float(last_o.abs().max())
         first = ws["first"].cpu().long()
