@@ -597,7 +597,7 @@ __device__ __noinline__ void attention_phase_b(const emx_decode_batch_params& p,
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 template <bool PROF>
-__global__ void __maxnreg__(200) decode_batch_kernel(const emx_decode_batch_params p) {
+__global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_decode_batch_params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ring = smem;
   float* part = reinterpret_cast<float*>(smem + DEC_STAGES * DEC_STAGE_BYTES);
