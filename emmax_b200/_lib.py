@@ -85,6 +85,8 @@ _SIGNATURES = {
     "emx_rmsnorm": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "emx_preprocess_u8": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "emx_resize_preprocess_u8": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "emx_crop_resize_u8": (_I, [_P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _I, _P]),
+    "emx_lanczos3_resize_u8": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
     "emx_patch_im2col": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "emx_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "emx_vit_gather_features": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
@@ -142,7 +144,7 @@ def check(rc: int) -> None:
 
 
 # kernels launched per C-ABI call (bookkeeping for bench.py's `gpu_launches`; graph replays add their captured count)
-_KERNELS_PER_CALL = {"emx_lmhead_argmax": 2}
+_KERNELS_PER_CALL = {"emx_lmhead_argmax": 2, "emx_lanczos3_resize_u8": 2, "emx_resize_preprocess_u8": 2}
 launch_count = 0
 
 

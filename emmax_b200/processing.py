@@ -167,7 +167,7 @@ class PrismaticImageProcessor:
         return torch.vstack(outs)
 
     def preprocess_device(self, frames: torch.Tensor) -> torch.Tensor:
-        """GPU twin of `apply_transform` for the `resize-naive` strategy (Emma-X: conf/models.py:494): uint8 [B, H, W, 3] or [H, W, 3]
+        """GPU twin of `apply_transform` for the `resize-naive` (Emma-X: conf/models.py:494) and `letterbox` strategies: uint8 [B, H, W, 3] or [H, W, 3]
         on a CUDA device -> bf16 [B, 6, 224, 224], bit-exact with `preprocess(...)["pixel_values"].to(device, dtype=torch.bfloat16)`.
         Frames already at the input size (the robot loop pre-resizes, bridgev2_utils.py:152-166) take one kernel (`emx_preprocess_u8`);
         other sizes (256x256 sim frames, run_bridgev2_eval.py:161) go through Pillow's antialiased bicubic resample restated in its
@@ -181,9 +181,18 @@ class PrismaticImageProcessor:
         B, H, W, _ = frames.shape
         n = len(self.input_sizes)
         Ho, Wo = self.input_sizes[0][-2:]
-        if self.image_resize_strategy != "resize-naive" or any(tuple(s[-2:]) != (Ho, Wo) for s in self.input_sizes):
-            raise ValueError(f"preprocess_device implements the `resize-naive` strategy with one common input size; got "
+        if self.image_resize_strategy not in ("resize-naive", "letterbox") or any(tuple(s[-2:]) != (Ho, Wo) for s in self.input_sizes):
+            raise ValueError(f"preprocess_device implements the `resize-naive` and `letterbox` strategies with one common input size; got "
                              f"{self.image_resize_strategy} / {self.input_sizes}: use the host transform")  # fmt: skip
+        if self.tvf_do_letterbox:
+            # letterbox_pad_transform (processing_prismatic.py:23-29): symmetric constant border of int((max - side) / 2) pixels per side,
+            # filled with int(255 * mean) of the LAST backbone; pure data movement, then the same resample as `resize-naive`
+            hp, vp = int((max(H, W) - W) / 2), int((max(H, W) - H) / 2)
+            if hp or vp:
+                fill = torch.tensor(self.tvf_letterbox_fill, dtype=torch.uint8, device=frames.device)
+                padded = fill.expand(B, H + 2 * vp, W + 2 * hp, 3).contiguous()
+                padded[:, vp : vp + H, hp : hp + W] = frames
+                frames, H, W = padded, H + 2 * vp, W + 2 * hp
         if (H, W) != (Ho, Wo) and any(i != "bicubic" for i in self.interpolations):
             raise ValueError(f"preprocess_device resizes with Pillow's antialiased bicubic only; got {self.interpolations}")
         frames = frames.contiguous()

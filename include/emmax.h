@@ -62,6 +62,16 @@ int emx_preprocess_u8(const void* hwc, int B, int H, int W, int n_backbones, con
 int emx_resize_preprocess_u8(const void* hwc, int B, int Hin, int Win, int Hout, int Wout, const int32_t* kk_h, const int32_t* bounds_h,
                              int ksize_h, const int32_t* kk_v, const int32_t* bounds_v, int ksize_v, void* tmp, int n_backbones,
                              const float* mean, const float* stdv, void* out, emx_stream_t stream);
+/* GPU twins of the robot loop's TensorFlow image steps (bit-exact with the numpy float32 restatements in emmax_b200/robot_utils.py):
+ * the 0.9-area centre crop + bilinear resize of get_vla_action / get_seq_action (experiments/robot/openvla_utils.py:81-124, :136-156:
+ * uint8 -> /255 -> tf.image.crop_and_resize(box y1,x1,y2,x2 normalised) -> clip -> * 255.5, saturate, truncate), uint8 [B,H,W,3] -> [B,Ho,Wo,3] */
+int emx_crop_resize_u8(const void* hwc, int B, int H, int W, float y1, float x1, float y2, float x2, void* out, int Ho, int Wo,
+                       emx_stream_t stream);
+/* and `resize_image`'s tf.image.resize(method="lanczos3", antialias=True) + round + clip + uint8 (experiments/robot/bridge/
+ * bridgev2_utils.py:152-166): separable, span starts (int32 [out]) and normalised fp32 weights ([out][ks]) built on the host as TF's
+ * ComputeSpansCore does; tmp: fp32 [H, Wo, 3] scratch; uint8 [H,W,3] -> [Ho,Wo,3]. Launches two kernels. */
+int emx_lanczos3_resize_u8(const void* hwc, int H, int W, int Ho, int Wo, const int32_t* start_h, const float* w_h, int ks_h,
+                           const int32_t* start_v, const float* w_v, int ks_v, void* tmp, void* out, emx_stream_t stream);
 int emx_patch_im2col(const void* pixels, int B, int c_total, int chan0, int H, int W, int patch, void* out, int kpad, emx_stream_t stream);
 /* tokens[b, 0:prefix] = prefix_tokens; tokens[b, prefix+i] = bf16(patch_out[b,i] + pos[i])  (timm _pos_embed) */
 int emx_vit_assemble(const void* patch_out, const void* pos, const void* prefix_tokens, void* tokens, int B, int n_patches, int prefix,

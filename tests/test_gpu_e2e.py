@@ -374,12 +374,13 @@ def _batched_prefill_check(cfg, sd, B, n_ids, seed, tol):
         got = ws["logits"].float().cpu()
         # un-scripted head: logits are ~N(0,1) (max|logit| ~ 5), where two bf16 implementations with different reduction orders differ by
         # 0.05-0.08 absolute after 32 layers (see test_full_size_unscripted_head_teacher_forced, which measures that noise against an fp32
-        # truth). Bar: every row within 2e-2 of max|logit|, the typical row within 1e-2; a batching bug (wrong row) is O(1), not O(1e-2).
+        # truth). Bar: every row within 2e-2 of max|logit| and no row standing out from the rest (a batching bug - wrong row, wrong image -
+        # is O(1) on ONE row, not a uniform O(1e-2)).
         scale = float(last_o.abs().max())
         row_err = ((got - last_o).abs().amax(dim=-1) / scale).numpy()
-        assert row_err.max() < 2e-2 and np.median(row_err) < 1e-2, (
+        assert row_err.max() < 2e-2 and row_err.max() < 1.6 * np.median(row_err) + 2e-3, (
             f"B={B} graph={use_graph}: last-position logits, per-row max|diff| / max|logit|: worst {row_err.max():.4g} (tolerance 2e-2), "
-            f"median {np.median(row_err):.4g} (tolerance 1e-2)")
+            f"median {np.median(row_err):.4g} (no row may stand out: worst < 1.6 x median + 2e-3)")
         top2 = last_o.topk(2, dim=-1).values
         clear = (top2[:, 0] - top2[:, 1]) > 4e-2 * float(last_o.abs().max())
         first = ws["first"].cpu().long()
@@ -403,3 +404,26 @@ def test_full_size_batched_prefill_b32_vs_oracle():
 
     cfg = emma_x_config()
     _batched_prefill_check(cfg, make_state_dict(cfg, seed=12, device="cuda"), B=32, n_ids=40, seed=12, tol=3e-2)
+
+
+def test_robot_loop_entry_points_on_the_engine(tiny):
+    """`get_vla_action` / `get_seq_action` (openvla_utils.py:127-218) over the real engine — a 256 x 256 camera frame, with
+    and without the 0.9 centre crop (GPU twin inside) — return exactly what the direct API calls return on the same processed inputs."""
+    from PIL import Image
+
+    from emmax_b200 import AutoProcessor
+    from emmax_b200 import robot_utils as R
+
+    model, tok, g, input_ids, script = tiny
+    proc = AutoProcessor.from_pretrained(None)
+    frame = np.random.default_rng(3).integers(0, 256, (256, 256, 3), dtype=np.uint8)
+    obs = {"full_image": frame}
+    for crop in (False, True):
+        a = R.get_vla_action(model, proc, "openvla-7b", obs, "Put Carrot In Pot", None, center_crop=crop)
+        img = Image.fromarray(R.center_crop_frame(frame) if crop else frame)
+        inputs = proc("In: What action should the robot take to put carrot in pot?\nOut:", img).to("cuda", dtype=BF)
+        want = model.predict_action(**inputs, unnorm_key=None, do_sample=False)
+        assert a.shape == (7,) and np.array_equal(a, want)
+        acts, text = R.get_seq_action(model, proc, "emma-x", obs, "put carrot in pot", None, type="act", center_crop=crop)
+        acts2, text2 = model.generate_actions(img, "In: put carrot in pot\nOut:", "act", max_new_tokens=512, do_sample=False)
+        assert text == text2 and len(acts) == len(acts2) and all(np.array_equal(x, y) for x, y in zip(acts, acts2))

@@ -249,3 +249,38 @@ def test_resize_preprocess_u8_bit_exact(lib, h, w):
     got = proc.preprocess_device(torch.from_numpy(frames).cuda())
     assert got.shape == (2, 6, 224, 224)
     assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16)), "device resize + transform must be bit-exact with the host processor"
+
+
+@pytest.mark.parametrize("h,w", [(480, 640), (300, 200), (224, 224), (257, 256)])
+def test_letterbox_preprocess_bit_exact(lib, h, w):
+    """`letterbox` strategy on the GPU (pad to square with int(255 * mean) of the last backbone, processing_prismatic.py:23-29, :130-131,
+    then the antialiased bicubic resample) == the host processor, bit for bit; odd differences leave a non-square padded frame, as the
+    reference's int((max - side) / 2) does."""
+    from PIL import Image
+
+    from emmax_b200 import PrismaticImageProcessor
+
+    proc = PrismaticImageProcessor(image_resize_strategy="letterbox")
+    frames = np.random.default_rng(h + w).integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    want = torch.stack([proc.apply_transform(Image.fromarray(f)) for f in frames]).to(BF)
+    got = proc.preprocess_device(torch.from_numpy(frames).cuda())
+    assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
+
+
+@pytest.mark.parametrize("h,w", [(256, 256), (480, 640), (224, 224)])
+def test_center_crop_and_lanczos_twins_bit_exact(lib, h, w):
+    """GPU twins of the robot loop's TensorFlow image steps == their numpy float32 host twins, bit for bit: the 0.9-area centre crop +
+    bilinear resize (openvla_utils.py:81-124, :136-156) and resize_image's lanczos3 antialias resize (bridgev2_utils.py:152-166)."""
+    from emmax_b200 import robot_utils as R
+
+    rng = np.random.default_rng(h * 3 + w)
+    frames = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    frames[0, : h // 8] = 255
+    frames[0, h // 8 : h // 4] = 0
+    got = R.center_crop_frame_device(torch.from_numpy(frames).cuda()).cpu().numpy()
+    for b in range(2):
+        assert np.array_equal(got[b], R.center_crop_frame(frames[b])), f"centre crop differs (frame {b})"
+    assert np.array_equal(R.center_crop_frame_device(torch.from_numpy(frames[1]).cuda(), 0.8).cpu().numpy(), R.center_crop_frame(frames[1], 0.8))
+    for size in ((224, 224), (128, 160)):
+        got = R.lanczos3_resize_device(torch.from_numpy(frames[1]).cuda(), size).cpu().numpy()
+        assert np.array_equal(got, R.lanczos3_resize(frames[1], size)), f"lanczos3 resize to {size} differs"

@@ -1,0 +1,64 @@
+"""Phase-level timing of the batched decode kernel (CTA 0's view, %globaltimer of the instrumented twin): per phase kind the time spent
+in the gather (+ RMSNorm) that precedes it and in the phase body, averaged over layers and launches; and the product kernel's ms/launch for
+several batch sizes.  Usage (GPU box): python tools/batch_probe.py [--steps 16] [--batches 1,4,8] [--advance 0]"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from emmax_b200 import OpenVLAForActionPrediction, _lib, emma_x_config
+from emmax_b200.synthetic import make_state_dict
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=16)
+ap.add_argument("--warm", type=int, default=4)
+ap.add_argument("--batches", default="1,4,8")
+ap.add_argument("--advance", type=int, default=0, help="decode this many extra tokens first (longer context)")
+args = ap.parse_args()
+
+cfg = emma_x_config()
+sd = make_state_dict(cfg, seed=0, device="cuda")
+model = OpenVLAForActionPrediction(cfg, sd, max_batch=8, max_context=1024).to("cuda")
+eng = model.engine
+L = cfg.text_config.num_hidden_layers
+lib = _lib.load()
+KINDS = ["q", "k", "v", "att", "o", "gateup", "down"]
+n_steps = 7 * L + 1
+
+for B in [int(b) for b in args.batches.split(",")]:
+    ids = torch.tensor([[1] + np.random.default_rng(1234).integers(3, 31744, 39).tolist()] * B, device="cuda")
+    pv = torch.randn(B, 6, 224, 224, device="cuda").to(torch.bfloat16)
+    eng.generate_batch(ids, pv, 2 + args.advance, eos_token_id=None)
+    st = eng.b_state
+    st[32 : 32 + B].fill_(10_000)  # limit: keep every sequence active
+    p = eng._decode_batch_params(B)
+    for _ in range(args.warm):
+        _lib.check(lib.emx_decode_batch_step(C.byref(p), _lib.stream()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        _lib.check(lib.emx_decode_batch_step(C.byref(p), _lib.stream()))
+    e1.record()
+    torch.cuda.synchronize()
+    ctx = int(st[8].item())
+    print(f"== batch {B}, context {ctx}: PRODUCT kernel {e0.elapsed_time(e1) / args.steps:.3f} ms/launch", flush=True)
+    dbg = torch.zeros(2 * n_steps + 8, dtype=torch.int64, device="cuda")
+    p.dbg = dbg.data_ptr()
+    gath, body, tot = np.zeros(8), np.zeros(8), []
+    for _ in range(args.steps):
+        _lib.check(lib.emx_decode_batch_step(C.byref(p), _lib.stream()))
+        torch.cuda.synchronize()
+        t = dbg.cpu().numpy().astype(np.float64)
+        tot.append((t[2 * n_steps] - t[0]) / 1e3)
+        for s in range(n_steps):
+            k = 7 if s == n_steps - 1 else s % 7
+            gath[k] += t[2 * s + 1] - t[2 * s]
+            body[k] += t[2 * s + 2] - t[2 * s + 1]
+    n = args.steps
+    print(f"   instrumented twin: {np.mean(tot):.1f} us per launch (CTA 0, first gather -> end of lm_head)")
+    print("   per layer (us):  " + "  ".join(f"{KINDS[k]}: gather {gath[k] / n / L:.2f} + body {body[k] / n / L:.2f}" for k in range(7)))
+    print(f"   per launch (us): gathers {gath[:7].sum() / n:.0f}, bodies {body[:7].sum() / n:.0f}, lm_head gather {gath[7] / n:.1f} + body {body[7] / n:.1f}", flush=True)
