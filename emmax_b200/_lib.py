@@ -71,7 +71,7 @@ class DecodeBatchParams(C.Structure):
         ("x", C.c_void_p), ("xo", C.c_void_p), ("attn", C.c_void_p), ("qkv", C.c_void_p), ("h", C.c_void_p),
         ("part", C.c_void_p), ("argmax_part", C.c_void_p),
         ("out_tokens", C.c_void_p), ("logits_out", C.c_void_p), ("state", C.c_void_p), ("dbg", C.c_void_p),
-        ("eos_token", C.c_int32), ("pad_", C.c_int32),
+        ("eos_token", C.c_int32), ("l2_lookahead_stages", C.c_int32),
     ]  # fmt: skip
 
 

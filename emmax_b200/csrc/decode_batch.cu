@@ -18,7 +18,7 @@
 //     items, split evenly over the CTAs whatever the individual context lengths are (flash-decoding); the producers stream each
 //     CTA's share through the weight ring (16 KB bulk copies straight out of the paged cache), every consumer warp keeps an online-softmax
 //     state for its 16 keys of the stage, and a rotating warp merges the 8 warp states at the end of a row segment and either
-//     publishes the partial (m, l, acc[128]) or — in the CTA that owns the row's last item — folds in the other segments and the
+//     publishes the partial (m, l, acc[128]) or — in the CTA that owns the row's FIRST item — folds in the other segments and the
 //     token being decoded (RoPE, KV append, one more online-softmax step) and publishes the head output;
 //   * per-sequence position, block table, RoPE row, token limit and EOS state; sequences that are finished (or slots beyond `batch`)
 //     are inactive: nobody waits for their units, nothing of theirs is stored.
@@ -31,7 +31,7 @@ namespace emx {
 constexpr int DB_MAXB = EMX_DECODE_MAX_BATCH;     // sequences per launch == N of the MMA atom
 static_assert(DB_MAXB == 8, "the batch is the N dimension of mma.m16n8k16");
 constexpr int DB_PWARPS = 2;                      // producer warps (alternate ring stages)
-constexpr int DB_THREADS = (DEC_CWARPS + DB_PWARPS) * 32;  // 320
+constexpr int DB_THREADS = (DEC_CWARPS + DB_PWARPS + 1) * 32;  // 352: 8 consumer + 2 producer + 1 L2-prefetch warp
 constexpr int DB_MAX_PAGES = 64;                  // block-table entries per sequence staged in shared memory
 constexpr int DB_MAX_RESID = 64;                  // residual units (row pairs) of this CTA's rows, per sequence
 constexpr int DB_ATT_WSTRIDE = 132;               // floats per warp in an attention partial buffer: acc[128], m, l, pad
@@ -51,6 +51,7 @@ struct __align__(16) BatchShared {
   float red[2][DEC_CWARPS][DB_MAXB];  // RMSNorm: per-warp sums of squares
   int tok[DB_MAXB], pos[DB_MAXB], ngen[DB_MAXB];
   uint32_t active_mask, epoch, tmem_base, pad0;
+  uint32_t issued[2], pad1[2];  // producers -> L2-prefetch warp: ring stages issued so far
   int att_pp[DB_MAXB];       // page pairs (items) per (sequence, head) row
   int att_off[DB_MAXB + 1];  // first item of sequence i in the linear item list
   int att_i0, att_i1, att_T;  // this CTA's items [i0, i1) of T
@@ -112,14 +113,44 @@ __device__ __forceinline__ long kv_page_off(const emx_decode_batch_params& p, in
   return ((static_cast<long>(layer) * p.n_pages + page) * p.heads + head) * (DB_PAGE * DEC_HD);
 }
 
-// ---- producer warps ------------------------------------------------------------------------------------------------------
-// Both walk the same schedule (layer -> q, k, v rows -> this CTA's K/V page pairs -> o, gate/up, down rows; lm_head rows); warp `pidx`
-// issues the ring stages with it % 2 == pidx. They never wait for anything but a free ring slot.
+// ---- producer warps, L2-prefetch warp ----------------------------------------------------------------------------------------
+// All walk the same schedule (layer -> q, k, v rows -> this CTA's K/V page pairs -> o, gate/up, down rows; lm_head rows).
+// PREFETCH == false: producer warp `pidx` issues the ring stages with it % 2 == pidx; it never waits for anything but a free ring slot.
+// PREFETCH == true: the ring only covers ~4 us of a saturated HBM, so whenever the consumers stall (an exchange, a gather) the ring fills,
+// no new copy can be issued and HBM idles. This warp watches for exactly that — the newest ring copy of this CTA has LANDED, i.e. nothing
+// of ours is in flight — and then pulls the next stages of the schedule HBM -> L2 (cp.async.bulk.prefetch.L2), paced at about twice the
+// SM's fair share of HBM, at most `l2_lookahead_stages` ahead of the ring. In the HBM-bound steady state it never triggers.
+struct PfGate {
+  volatile uint32_t* issued;  // [2] ring stages issued so far by the two producer warps
+  uint64_t* full;
+  uint32_t lookahead;
+  // true: prefetch stage `it` now; false: the ring got there first, skip it
+  __device__ __forceinline__ bool admit(uint32_t it) const {
+    uint32_t spins = 0;
+    for (;;) {
+      const uint32_t iss = max(issued[0], issued[1]);
+      if (it < iss) return false;
+      if (iss > 0 && it < iss + lookahead) {
+        const uint32_t last = iss - 1;
+        if (mbar_try_wait(&full[last % DEC_STAGES], (last / DEC_STAGES) & 1)) return true;
+      }
+      __nanosleep(200);
+      if (++spins > EMX_SPIN_LIMIT) __trap();
+    }
+  }
+};
+__device__ __forceinline__ void pf_pace(long long t0, int bytes) {
+  const long long wait_ns = 700LL * bytes / (64 * 1024);
+  while (global_ns() - t0 < wait_ns) __nanosleep(100);
+}
+
+template <bool PREFETCH>
 __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, const BatchShared& sh, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane,
-                               int pidx) {
+                                            int pidx, volatile uint32_t* s_issued) {
   const uint64_t policy = l2_policy_evict_first();
   const __nv_bfloat16* kc = static_cast<const __nv_bfloat16*>(p.k_cache);
   const __nv_bfloat16* vc = static_cast<const __nv_bfloat16*>(p.v_cache);
+  const PfGate gate{s_issued, full, static_cast<uint32_t>(max(p.l2_lookahead_stages, 0))};
   uint32_t it = 0;
   const int L = p.layers;
   for (int layer = 0; layer <= L; ++layer) {
@@ -127,10 +158,19 @@ __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, co
     for (int kind = k_first; kind <= k_last; ++kind) {
       if (kind == BPH_ATT) {
         for (int g = sh.att_i0; g < sh.att_i1; ++g, ++it) {
-          if ((it % DB_PWARPS) != static_cast<uint32_t>(pidx)) continue;
+          if (!PREFETCH && (it % DB_PWARPS) != static_cast<uint32_t>(pidx)) continue;
+          if (PREFETCH && !gate.admit(it)) continue;
           const AttItem a = att_item(sh, g);
           const int pages = (sh.pos[a.seq] + DB_PAGE - 1) / DB_PAGE;
           const int np = min(2, pages - 2 * a.j);  // pages of this item: K page(s) at [0, 32 K), V page(s) at [32 K, 64 K) of the stage
+          const int is_v = lane >= np ? 1 : 0, pg = lane - is_v * np;
+          const long off = (lane < 2 * np) ? kv_page_off(p, layer, sh.table[a.seq][2 * a.j + pg], a.head) : 0;
+          if (PREFETCH) {
+            const long long t0 = global_ns();
+            if (lane < 2 * np) prefetch_l2((is_v ? vc : kc) + off, DB_PAGE_BYTES);
+            pf_pace(t0, 2 * np * DB_PAGE_BYTES);
+            continue;
+          }
           const int slot = it % DEC_STAGES;
           const uint32_t ph = (it / DEC_STAGES) & 1;
           if (lane == 0) {
@@ -138,12 +178,9 @@ __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, co
             mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(np) * 2 * DB_PAGE_BYTES);
           }
           __syncwarp();
-          if (lane < 2 * np) {
-            const int is_v = lane >= np ? 1 : 0, pg = lane - is_v * np;
-            const long off = kv_page_off(p, layer, sh.table[a.seq][2 * a.j + pg], a.head);
-            bulk_g2s(ring + slot * DEC_STAGE_BYTES + is_v * 2 * DB_PAGE_BYTES + pg * DB_PAGE_BYTES, (is_v ? vc : kc) + off, DB_PAGE_BYTES,
-                     &full[slot], policy);
-          }
+          if (lane < 2 * np)
+            bulk_g2s(ring + slot * DEC_STAGE_BYTES + is_v * 2 * DB_PAGE_BYTES + pg * DB_PAGE_BYTES, (is_v ? vc : kc) + off, DB_PAGE_BYTES, &full[slot], policy);
+          if (lane == 0) s_issued[pidx] = it + 1;
         }
         continue;
       }
@@ -152,8 +189,16 @@ __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, co
       for (int r = sh.r_begin[kind]; r < r_end; r += DEC_GROUP) {
         const int nrows = min(DEC_GROUP, r_end - r);
         for (int k0 = 0; k0 < K; k0 += DEC_KC, ++it) {
-          if ((it % DB_PWARPS) != static_cast<uint32_t>(pidx)) continue;
+          if (!PREFETCH && (it % DB_PWARPS) != static_cast<uint32_t>(pidx)) continue;
+          if (PREFETCH && !gate.admit(it)) continue;
           const int klen = min(DEC_KC, K - k0);
+          const __nv_bfloat16* src = W + static_cast<long>(r + lane) * K + k0;
+          if (PREFETCH) {
+            const long long t0 = global_ns();
+            if (lane < nrows) prefetch_l2(src, klen * 2);
+            pf_pace(t0, nrows * klen * 2);
+            continue;
+          }
           const int slot = it % DEC_STAGES;
           const uint32_t ph = (it / DEC_STAGES) & 1;
           if (lane == 0) {
@@ -161,8 +206,8 @@ __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, co
             mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(nrows) * klen * 2);
           }
           __syncwarp();
-          if (lane < nrows)
-            bulk_g2s(ring + slot * DEC_STAGE_BYTES + lane * DEC_ROWSTRIDE, W + static_cast<long>(r + lane) * K + k0, klen * 2, &full[slot], policy);
+          if (lane < nrows) bulk_g2s(ring + slot * DEC_STAGE_BYTES + lane * DEC_ROWSTRIDE, src, klen * 2, &full[slot], policy);
+          if (lane == 0) s_issued[pidx] = it + 1;
         }
       }
     }
@@ -213,20 +258,30 @@ __device__ __forceinline__ void g_poll(const uint64_t* src, int hc, int warp, in
 // natural unit index of payload word q (0..15) of half chunk hc for (warp, t)
 __device__ __forceinline__ int g_unit(int hc, int warp, int t, int q) { return 16 * (64 * (hc >> 1) + 8 * warp + 4 * (hc & 1) + (q >> 2)) + 4 * (q & 3) + t; }
 
-// Walk the half chunks of a K-element vector with two fetches in flight; take(hc, raw, ks) sees every half chunk this warp owns.
+// Walk the half chunks of a K-element vector with THREE fetches in flight (each poll is one L2 round trip of ~2 us while the weight stream
+// saturates the memory system, so the number of sequential round trips is what a gather costs); take(hc, raw, ks) sees every half chunk.
 template <typename Take>
 __device__ __forceinline__ void g_walk(const uint64_t* src, int K, int warp, int t, bool act, uint32_t tag, Take&& take) {
   const int nh = 2 * ((K + DEC_KC - 1) / DEC_KC);
-  GRaw A, B;
-  uint32_t pa = g_issue(src, 0, warp, t, half_ksteps(K, 0, warp), act, A), pb = 0;
+  GRaw A, B, C;
+  uint32_t pa = g_issue(src, 0, warp, t, half_ksteps(K, 0, warp), act, A);
+  uint32_t pb = g_issue(src, 1, warp, t, half_ksteps(K, 1, warp), act, B);  // nh >= 2
+  uint32_t pc = 0;
 #pragma unroll 1
-  for (int hc = 0; hc < nh; hc += 2) {
-    pb = g_issue(src, hc + 1, warp, t, half_ksteps(K, hc + 1, warp), act, B);
+  for (int hc = 0; hc < nh; hc += 3) {
+    if (hc + 2 < nh) pc = g_issue(src, hc + 2, warp, t, half_ksteps(K, hc + 2, warp), act, C);
     g_poll(src, hc, warp, t, pa, tag, A);
     take(hc, A, half_ksteps(K, hc, warp));
-    if (hc + 2 < nh) pa = g_issue(src, hc + 2, warp, t, half_ksteps(K, hc + 2, warp), act, A);
-    g_poll(src, hc + 1, warp, t, pb, tag, B);
-    take(hc + 1, B, half_ksteps(K, hc + 1, warp));
+    if (hc + 3 < nh) pa = g_issue(src, hc + 3, warp, t, half_ksteps(K, hc + 3, warp), act, A);
+    if (hc + 1 < nh) {
+      g_poll(src, hc + 1, warp, t, pb, tag, B);
+      take(hc + 1, B, half_ksteps(K, hc + 1, warp));
+    }
+    if (hc + 4 < nh) pb = g_issue(src, hc + 4, warp, t, half_ksteps(K, hc + 4, warp), act, B);
+    if (hc + 2 < nh) {
+      g_poll(src, hc + 2, warp, t, pc, tag, C);
+      take(hc + 2, C, half_ksteps(K, hc + 2, warp));
+    }
   }
 }
 
@@ -410,27 +465,40 @@ struct AttState {
   int row;  // (sequence * heads + head) the state and q belong to, -1: none
 };
 
-// 4 consecutive elements (4 lane .. 4 lane + 3) of a 128-wide head vector out of LL units, optionally through RoPE (rotate_half form:
-// the partner element d +- 64 lives in lane ^ 16). x_embed = bf16(bf16(x cos) + bf16(rotate_half(x) sin)), tables are bf16.
-__device__ __forceinline__ void load_head4(const uint64_t* units, const uint32_t* rope, int lane, uint32_t tag, float (&out)[4]) {
-  uint32_t w[2];
-  ll_fetch_pairs<1>([&](int) { return units + 2 * lane; }, w, tag, true);
-  const float x[4] = {bf16_lo(w[0]), bf16_hi(w[0]), bf16_lo(w[1]), bf16_hi(w[1])};
-  if (!rope) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) out[e] = x[e];
-    return;
+// 4 consecutive elements (4 lane .. 4 lane + 3) of a 128-wide head vector out of two LL units (one 16-byte load per lane, issued early and
+// polled when the values are needed), optionally through RoPE (rotate_half form: the partner element d +- 64 lives in lane ^ 16).
+// x_embed = bf16(bf16(x cos) + bf16(rotate_half(x) sin)), tables are bf16.
+struct Head4 {
+  const uint64_t* src;
+  uint64_t a, b;
+  __device__ __forceinline__ void issue(const uint64_t* units, int lane) {
+    src = units + 2 * lane;
+    ll_load2(src, a, b);
   }
-  const int ci = (2 * lane) & 31;
-  const uint32_t cw[2] = {rope[ci], rope[ci + 1]}, sw[2] = {rope[32 + ci], rope[32 + ci + 1]};
-  const float sgn = (lane < 16) ? -1.f : 1.f;
+  __device__ __forceinline__ void finish(const uint32_t* rope, int lane, uint32_t tag, float (&out)[4]) {
+    uint32_t spins = 0;
+    while (!(tag_ok(a, tag) && tag_ok(b, tag))) {
+      ll_load2(src, a, b);
+      if (++spins > EMX_SPIN_LIMIT) __trap();
+    }
+    const uint32_t w0 = static_cast<uint32_t>(a), w1 = static_cast<uint32_t>(b);
+    const float x[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
+    if (!rope) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float pr = __shfl_xor_sync(0xffffffffu, x[e], 16);
-    const float cs = (e & 1) ? bf16_hi(cw[e >> 1]) : bf16_lo(cw[e >> 1]), sn = (e & 1) ? bf16_hi(sw[e >> 1]) : bf16_lo(sw[e >> 1]);
-    out[e] = bf16_round(bf16_round(x[e] * cs) + bf16_round(sgn * pr * sn));
+      for (int e = 0; e < 4; ++e) out[e] = x[e];
+      return;
+    }
+    const int ci = (2 * lane) & 31;
+    const uint32_t cw[2] = {rope[ci], rope[ci + 1]}, sw[2] = {rope[32 + ci], rope[32 + ci + 1]};
+    const float sgn = (lane < 16) ? -1.f : 1.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float pr = __shfl_xor_sync(0xffffffffu, x[e], 16);
+      const float cs = (e & 1) ? bf16_hi(cw[e >> 1]) : bf16_lo(cw[e >> 1]), sn = (e & 1) ? bf16_hi(sw[e >> 1]) : bf16_lo(sw[e >> 1]);
+      out[e] = bf16_round(bf16_round(x[e] * cs) + bf16_round(sgn * pr * sn));
+    }
   }
-}
+};
 
 // One online-softmax step of this warp over its 16 keys of the stage (keys 16 warp .. 16 warp + 15 of the item's 128; K rows at
 // [page][row][128] from byte 0, V rows from byte 32 K). Lane l owns head elements 4 l .. 4 l + 3 of q, K, V and the accumulator.
@@ -496,11 +564,23 @@ __device__ __forceinline__ void att_merge(float& M, float& den, float (&num)[4],
   }
 }
 
-// End of a row segment, run by the rotating warp once all 8 warp states are in `pb`: merge them; if the row goes on in the next CTA
-// publish the partial, otherwise (this CTA owns the row's last item) fold in the segments of the CTAs before us and the token being
-// decoded, append its K/V to the cache and publish the head output in o_proj's exchange order.
+// End of a row segment, run by the rotating warp once all 8 warp states are in `pb`: merge them. The CTA that owns the row's FIRST item
+// combines: it folds in the segments of the CTAs after it and the token being decoded (RoPE, KV append, one more online-softmax step)
+// and publishes the head output in o_proj's exchange order; every other segment is published as a partial. Publishers never wait, and a
+// combiner only waits for segments that were started at the same time as its own, so no CTA ever waits for another one's WHOLE share
+// (the mirror-image choice — combining in the CTA that owns the row's last item — chains every CTA behind its predecessor).
 __device__ void att_finish(const emx_decode_batch_params& p, const BatchShared& sh, const float* pb, int lane, const AttItem& it, int g, int layer,
                            uint32_t tag, const float (&q)[4], float scale) {
+  const int n = it.seq, H = p.hidden;
+  const int row_start = sh.att_off[n] + it.head * it.pp, row_last = row_start + it.pp - 1;
+  const int seg_start = max(sh.att_i0, row_start);
+  const bool combiner = (seg_start == row_start);
+  const uint64_t* qkv = static_cast<const uint64_t*>(p.qkv) + static_cast<long>(n) * (3 * H / 2);
+  Head4 hk, hv;
+  if (combiner) {  // k and v of the token being decoded: in flight while the partials are merged
+    hk.issue(qkv + H / 2 + it.head * (DEC_HD / 2), lane);
+    hv.issue(qkv + H + it.head * (DEC_HD / 2), lane);
+  }
   float M = -INFINITY, den = 0.f, num[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int w = 0; w < DEC_CWARPS; ++w) {
@@ -508,20 +588,17 @@ __device__ void att_finish(const emx_decode_batch_params& p, const BatchShared& 
     const float a4[4] = {a.x, a.y, a.z, a.w};
     att_merge(M, den, num, pb[w * DB_ATT_WSTRIDE + DEC_HD], pb[w * DB_ATT_WSTRIDE + DEC_HD + 1], a4);
   }
-  const int n = it.seq, H = p.hidden;
-  const int row_start = sh.att_off[n] + it.head * it.pp;
-  const int seg_start = max(sh.att_i0, row_start);
   uint64_t* rowpart = static_cast<uint64_t*>(p.part) + (static_cast<long>(n) * p.heads + it.head) * (DB_MAXSEG * DB_PARTU);
-  if (it.j != it.pp - 1) {  // (then g is the last item of this CTA)
+  if (!combiner) {
     uint64_t* dst = rowpart + (seg_start - row_start) * DB_PARTU;
     if (lane == 0) ll_store(dst, __float_as_uint(M), tag), ll_store(dst + 1, __float_as_uint(den), tag);
 #pragma unroll
     for (int e = 0; e < 4; ++e) ll_store(dst + 2 + 4 * lane + e, __float_as_uint(num[e]), tag);
     return;
   }
-  // ---- segments of the CTAs before this one (owner(g) = the CTA c with T c / G <= g < T (c + 1) / G)
+  // ---- segments of the CTAs after this one (owner(g) = the CTA c with T c / G <= g < T (c + 1) / G); g is the last item of ours
   const long T = sh.att_T, G = gridDim.x;
-  for (int gc = row_start; gc < seg_start;) {
+  for (int gc = g + 1; gc <= row_last;) {
     const long c = ((gc + 1) * G - 1) / T;
     const uint64_t* src = rowpart + (gc - row_start) * DB_PARTU;
     uint32_t w[6];
@@ -531,11 +608,10 @@ __device__ void att_finish(const emx_decode_batch_params& p, const BatchShared& 
     gc = static_cast<int>(T * (c + 1) / G);
   }
   // ---- the token being decoded: k (RoPE) and v arrive from the projection phases of this layer
-  const uint64_t* qkv = static_cast<const uint64_t*>(p.qkv) + static_cast<long>(n) * (3 * H / 2);
   const int pos = sh.pos[n];
   float kr[4], vn[4];
-  load_head4(qkv + H / 2 + it.head * (DEC_HD / 2), sh.rope[n], lane, tag, kr);
-  load_head4(qkv + H + it.head * (DEC_HD / 2), nullptr, lane, tag, vn);
+  hk.finish(sh.rope[n], lane, tag, kr);
+  hv.finish(nullptr, lane, tag, vn);
   const long dst = kv_page_off(p, layer, sh.table[n][pos / DB_PAGE], it.head) + (pos % DB_PAGE) * DEC_HD + 4 * lane;
   *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.k_cache) + dst) = make_uint2(pack_bf16(kr[0], kr[1]), pack_bf16(kr[2], kr[3]));
   *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.v_cache) + dst) = make_uint2(pack_bf16(vn[0], vn[1]), pack_bf16(vn[2], vn[3]));
@@ -563,15 +639,19 @@ __device__ __noinline__ void attention_phase_b(const emx_decode_batch_params& p,
   for (int g = i0; g < i1; ++g) {
     const AttItem it = att_item(sh, g);
     const int row = it.seq * p.heads + it.head;
-    if (row != s.row) {  // new row: q of (sequence, head) — projected two phases ago, long there
-      s.row = row, s.m = -INFINITY, s.l = 0.f;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s.acc[e] = 0.f;
-      load_head4(static_cast<const uint64_t*>(p.qkv) + static_cast<long>(it.seq) * (3 * p.hidden / 2) + it.head * (DEC_HD / 2), sh.rope[it.seq], lane, tag, s.q);
-    }
+    const bool new_row = row != s.row;
+    Head4 hq;
+    if (new_row)  // q of (sequence, head) — projected two phases ago, long there: its L2 round trip overlaps the wait for the stage
+      hq.issue(static_cast<const uint64_t*>(p.qkv) + static_cast<long>(it.seq) * (3 * p.hidden / 2) + it.head * (DEC_HD / 2), lane);
     const int slot = cs.it % DEC_STAGES;
     const uint32_t ph = (cs.it / DEC_STAGES) & 1;
     mbar_wait(&full[slot], ph);
+    if (new_row) {
+      s.row = row, s.m = -INFINITY, s.l = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s.acc[e] = 0.f;
+      hq.finish(sh.rope[it.seq], lane, tag, s.q);
+    }
     const int nvalid = min(16, sh.pos[it.seq] - (128 * it.j + 16 * warp));  // cached keys are positions 0 .. pos - 1
     if (nvalid > 0) att_block(ring + slot * DEC_STAGE_BYTES, warp, lane, nvalid, scale, s);
     __syncwarp();
@@ -616,7 +696,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
     const bool act = n < p.batch && !fin && ngen < lim && ngen < p.out_stride && pos >= 1 && pos < p.max_pages * DB_PAGE;
     sh.tok[n] = min(max(tok, 0), p.vocab - 1), sh.pos[n] = act ? pos : 0, sh.ngen[n] = ngen;
     const uint32_t m = __ballot_sync(0xffu, act);
-    if (tid == 0) sh.active_mask = m, sh.epoch = ldg_cg_u32(&st->epoch);
+    if (tid == 0) sh.active_mask = m, sh.epoch = ldg_cg_u32(&st->epoch), sh.issued[0] = 0, sh.issued[1] = 0;
   }
   if (tid >= 32 && tid < 32 + BPH_KINDS) build_phase(p, sh, tid - 32);
   if (tid == 64) {
@@ -654,8 +734,12 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
   __syncthreads();
   tc_fence_after();
 
+  if (warp >= DEC_CWARPS + DB_PWARPS) {
+    if (p.l2_lookahead_stages > 0) batch_producer<true>(p, sh, ring, sh.full, sh.empty, lane, 0, sh.issued);
+    return;
+  }
   if (warp >= DEC_CWARPS) {
-    batch_producer(p, sh, ring, sh.full, sh.empty, lane, warp - DEC_CWARPS);
+    batch_producer<false>(p, sh, ring, sh.full, sh.empty, lane, warp - DEC_CWARPS, sh.issued);
     return;
   }
 
@@ -684,6 +768,10 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
   for (int step = 0; step < n_steps; ++step) {
     const uint32_t tag = tag0 + layer;  // (the lm_head step has layer == L)
     if (PROF && dbg) dbg[2 * step] = global_ns();
+    // every CTA: entry / exit times of the four gathers of layer 1 (skew of the exchanges)
+    const int gslot = (kind == BPH_Q) ? 0 : (kind == BPH_O) ? 1 : (kind == BPH_GATEUP) ? 2 : (kind == BPH_DOWN) ? 3 : -1;
+    long long* gdbg = (PROF && p.dbg && tid == 0 && layer == 1 && gslot >= 0) ? reinterpret_cast<long long*>(p.dbg) + 2 * n_steps + 8 + 8 * blockIdx.x + 2 * gslot : nullptr;
+    if (PROF && gdbg) gdbg[0] = global_ns();
     if (kind == BPH_Q || kind == BPH_GATEUP || kind == BPH_LMHEAD) {
       gather_rmsnorm_b(kind == BPH_GATEUP ? xo : xd, sH, step == 0 ? static_cast<const __nv_bfloat16*>(p.embed) : nullptr, H, tag, tm, sh, ln_s, p.rms_eps,
                        kind == BPH_GATEUP ? 1u : 0u, rb2, re2, warp, lane);
@@ -698,6 +786,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
       gather_plain_b(o ? attn : hbuf, o ? sH : sI, o ? H : I, tag, tm, active_mask, warp, lane);
     }
     if (PROF && dbg) dbg[2 * step + 1] = global_ns();
+    if (PROF && gdbg) gdbg[1] = global_ns();
     if (kind == BPH_ATT) {
       attention_phase_b(p, sh, ring, sh.full, sh.empty, cs, part, layer, tag, warp, lane);
     } else {

@@ -418,6 +418,7 @@ class Engine:
         p.part, p.argmax_part = ptr(self.b_part), ptr(self.b_argmax)
         p.out_tokens, p.logits_out, p.state, p.dbg = ptr(self.b_out), None, ptr(self.b_state), None
         p.eos_token = -1
+        p.l2_lookahead_stages = int(os.environ.get("EMX_BATCH_L2_LOOKAHEAD_STAGES", "6"))
         return p
 
     @_on_engine_device

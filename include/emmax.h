@@ -233,9 +233,11 @@ typedef struct emx_decode_batch_params {
   int32_t* out_tokens;  /* out_tokens[i * out_stride + n_generated[i]] = new token of sequence i */
   float* logits_out;    /* optional [8][vocab] fp32 (bf16-rounded values), for parity tests */
   emx_decode_batch_state* state;
-  int64_t* dbg;         /* optional (>= 2 * (7 * layers + 1) + 1 int64): CTA 0 stores %globaltimer before / after every phase's gather; selects the instrumented twin */
+  int64_t* dbg;         /* optional (>= 2 * (7 * layers + 1) + 8 + 8 * grid int64): CTA 0 stores %globaltimer before / after every phase's gather,
+                         * every CTA the entry / exit times of layer 1's four gathers; selects the instrumented twin */
   int32_t eos_token;    /* -1 disables EOS handling */
-  int32_t pad_;
+  /* look-ahead (ring stages of 64 KB) of the idle-triggered cp.async.bulk.prefetch.L2 warp beyond the shared-memory ring; 0 disables */
+  int32_t l2_lookahead_stages;
 } emx_decode_batch_params;
 
 int emx_decode_batch_step(const emx_decode_batch_params* params, emx_stream_t stream);

@@ -45,6 +45,10 @@ def test_ctypes_structs_match_c_layout(lib):
       printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(emx_decode_state), offsetof(emx_decode_state, head_ticket),
              sizeof(emx_decode_params), offsetof(emx_decode_params, embed), offsetof(emx_decode_params, page_size),
              offsetof(emx_decode_params, out_tokens), offsetof(emx_decode_params, state), offsetof(emx_decode_params, debug_flags));
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(emx_decode_batch_state), offsetof(emx_decode_batch_state, limit),
+             offsetof(emx_decode_batch_state, epoch), sizeof(emx_decode_batch_params), offsetof(emx_decode_batch_params, embed),
+             offsetof(emx_decode_batch_params, page_size), offsetof(emx_decode_batch_params, x), offsetof(emx_decode_batch_params, out_tokens),
+             offsetof(emx_decode_batch_params, state), offsetof(emx_decode_batch_params, l2_lookahead_stages));
       return 0;
     }"""
     with tempfile.TemporaryDirectory() as d:
@@ -55,7 +59,11 @@ def test_ctypes_structs_match_c_layout(lib):
     S, P = lib.DecodeState, lib.DecodeParams
     want = [C.sizeof(S), S.head_ticket.offset, C.sizeof(P), P.embed.offset, P.page_size.offset, P.out_tokens.offset, P.state.offset,
             P.debug_flags.offset]  # fmt: skip
-    assert got == want, (got, want)
+    assert got[:8] == want, (got, want)
+    BS, BP = lib.DecodeBatchState, lib.DecodeBatchParams
+    want_b = [C.sizeof(BS), BS.limit.offset, BS.epoch.offset, C.sizeof(BP), BP.embed.offset, BP.page_size.offset, BP.x.offset, BP.out_tokens.offset,
+              BP.state.offset, BP.l2_lookahead_stages.offset]  # fmt: skip
+    assert got[8:] == want_b, (got[8:], want_b)
 
 
 def test_argument_validation_without_gpu(lib):

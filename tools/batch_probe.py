@@ -18,6 +18,7 @@ ap.add_argument("--steps", type=int, default=16)
 ap.add_argument("--warm", type=int, default=4)
 ap.add_argument("--batches", default="1,4,8")
 ap.add_argument("--advance", type=int, default=0, help="decode this many extra tokens first (longer context)")
+ap.add_argument("--lookahead", default="6", help="comma list of l2_lookahead_stages values to try")
 args = ap.parse_args()
 
 cfg = emma_x_config()
@@ -29,13 +30,15 @@ lib = _lib.load()
 KINDS = ["q", "k", "v", "att", "o", "gateup", "down"]
 n_steps = 7 * L + 1
 
-for B in [int(b) for b in args.batches.split(",")]:
+GRID = lib.emx_decode_grid()
+for B, LA in [(int(b), int(la)) for b in args.batches.split(",") for la in args.lookahead.split(",")]:
     ids = torch.tensor([[1] + np.random.default_rng(1234).integers(3, 31744, 39).tolist()] * B, device="cuda")
     pv = torch.randn(B, 6, 224, 224, device="cuda").to(torch.bfloat16)
     eng.generate_batch(ids, pv, 2 + args.advance, eos_token_id=None)
     st = eng.b_state
     st[32 : 32 + B].fill_(10_000)  # limit: keep every sequence active
     p = eng._decode_batch_params(B)
+    p.l2_lookahead_stages = LA
     for _ in range(args.warm):
         _lib.check(lib.emx_decode_batch_step(C.byref(p), _lib.stream()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,20 +48,25 @@ for B in [int(b) for b in args.batches.split(",")]:
     e1.record()
     torch.cuda.synchronize()
     ctx = int(st[8].item())
-    print(f"== batch {B}, context {ctx}: PRODUCT kernel {e0.elapsed_time(e1) / args.steps:.3f} ms/launch", flush=True)
-    dbg = torch.zeros(2 * n_steps + 8, dtype=torch.int64, device="cuda")
+    print(f"== batch {B}, L2 look-ahead {LA} stages, context {ctx}: PRODUCT kernel {e0.elapsed_time(e1) / args.steps:.3f} ms/launch", flush=True)
+    dbg = torch.zeros(2 * n_steps + 8 + 8 * GRID, dtype=torch.int64, device="cuda")
     p.dbg = dbg.data_ptr()
-    gath, body, tot = np.zeros(8), np.zeros(8), []
+    gath, body, tot, skew = np.zeros(8), np.zeros(8), [], []
     for _ in range(args.steps):
         _lib.check(lib.emx_decode_batch_step(C.byref(p), _lib.stream()))
         torch.cuda.synchronize()
         t = dbg.cpu().numpy().astype(np.float64)
         tot.append((t[2 * n_steps] - t[0]) / 1e3)
+        g = t[2 * n_steps + 8 :].reshape(GRID, 4, 2)
+        skew.append([(g[:, k, 0].max() - g[:, k, 0].min(), g[:, k, 1].max() - g[:, k, 1].min(), np.median(g[:, k, 1] - g[:, k, 0]), (g[:, k, 1] - g[:, k, 0]).min()) for k in range(4)])
         for s in range(n_steps):
             k = 7 if s == n_steps - 1 else s % 7
             gath[k] += t[2 * s + 1] - t[2 * s]
             body[k] += t[2 * s + 2] - t[2 * s + 1]
     n = args.steps
     print(f"   instrumented twin: {np.mean(tot):.1f} us per launch (CTA 0, first gather -> end of lm_head)")
-    print("   per layer (us):  " + "  ".join(f"{KINDS[k]}: gather {gath[k] / n / L:.2f} + body {body[k] / n / L:.2f}" for k in range(7)))
-    print(f"   per launch (us): gathers {gath[:7].sum() / n:.0f}, bodies {body[:7].sum() / n:.0f}, lm_head gather {gath[7] / n:.1f} + body {body[7] / n:.1f}", flush=True)
+    print("   per layer (us):  " + "  ".join(f"{KINDS[k]}: gather {gath[k] / n / L / 1e3:.2f} + body {body[k] / n / L / 1e3:.2f}" for k in range(7)))
+    print(f"   per launch (us): gathers {gath[:7].sum() / n / 1e3:.0f}, bodies {body[:7].sum() / n / 1e3:.0f}, lm_head gather {gath[7] / n / 1e3:.1f} + body {body[7] / n / 1e3:.1f}")
+    sk = np.mean(np.array(skew), axis=0) / 1e3
+    print("   layer 1, all CTAs (us): " + "  ".join(f"{nm}: entry spread {sk[k, 0]:.1f}, exit spread {sk[k, 1]:.1f}, gather median {sk[k, 2]:.1f} / min {sk[k, 3]:.1f}"
+                                                    for k, nm in enumerate(["q", "o", "gateup", "down"])), flush=True)
