@@ -18,12 +18,12 @@ from .load import load_vla
 from .modeling import AutoConfig, AutoModelForVision2Seq, OpenVLAForActionPrediction, PrismaticCausalLMOutputWithPast
 from .processing import AutoImageProcessor, AutoProcessor, BatchFeature, PrismaticImageProcessor, PrismaticProcessor
 from .prompting import PurePromptBuilder, emma_x_prompt, openvla_prompt
-from .simpler_policy import OpenVLAInference
+from .simpler_policy import BatchedOpenVLAInference, OpenVLAInference
 from .solver import Solver
 from .tokenization import SyntheticLlamaTokenizer
 
 __all__ = [
-    "ActionTokenizer", "AutoConfig", "AutoImageProcessor", "AutoModelForVision2Seq", "AutoProcessor", "BatchFeature",
+    "ActionTokenizer", "AutoConfig", "BatchedOpenVLAInference", "AutoImageProcessor", "AutoModelForVision2Seq", "AutoProcessor", "BatchFeature",
     "OpenVLAConfig", "OpenVLAForActionPrediction", "OpenVLAInference", "PrismaticCausalLMOutputWithPast", "PrismaticConfig",
     "PrismaticImageProcessor", "PrismaticProcessor", "PurePromptBuilder", "Solver", "SyntheticLlamaTokenizer",
     "emma_x_config", "emma_x_prompt", "load_vla", "openvla_prompt", "tiny_config",

@@ -48,6 +48,7 @@ enum BatchPhase { BPH_Q = 0, BPH_K, BPH_V, BPH_ATT, BPH_O, BPH_GATEUP, BPH_DOWN,
 
 struct __align__(16) BatchShared {
   uint64_t full[DEC_STAGES], empty[DEC_STAGES];
+  uint64_t gbar, pad2;  // completion barrier of the gathers' bulk copies
   float red[2][DEC_CWARPS][DB_MAXB];  // RMSNorm: per-warp sums of squares
   int tok[DB_MAXB], pos[DB_MAXB], ngen[DB_MAXB];
   uint32_t active_mask, epoch, tmem_base, pad0;
@@ -112,6 +113,9 @@ __device__ __forceinline__ AttItem att_item(const BatchShared& sh, int g) {
 __device__ __forceinline__ long kv_page_off(const emx_decode_batch_params& p, int layer, int page, int head) {
   return ((static_cast<long>(layer) * p.n_pages + page) * p.heads + head) * (DB_PAGE * DEC_HD);
 }
+
+// virtual ring stages the gather of a K-element vector occupies (see "gathers" below; producers and the prefetch warp skip them)
+__host__ __device__ __forceinline__ int gather_stages(int K) { return (K + DEC_KC - 1) / DEC_KC; }
 
 // ---- producer warps, L2-prefetch warp ----------------------------------------------------------------------------------------
 // All walk the same schedule (layer -> q, k, v rows -> this CTA's K/V page pairs -> o, gate/up, down rows; lm_head rows).
@@ -185,6 +189,8 @@ __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, co
         continue;
       }
       const int K = sh.K[kind], r_end = sh.r_end[kind];
+      // the gather in front of this phase occupies ring slots of its own (none for k / v rows, and none for the embedding rows of layer 0)
+      if (kind != BPH_K && kind != BPH_V && !(layer == 0 && kind == BPH_Q)) it += gather_stages(K);
       const __nv_bfloat16* W = sh.W[kind] + layer * sh.layer_stride[kind];
       for (int r = sh.r_begin[kind]; r < r_end; r += DEC_GROUP) {
         const int nrows = min(DEC_GROUP, r_end - r);
@@ -214,89 +220,38 @@ __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, co
   }
 }
 
-// ---- gathers: LL exchange buffer -> this thread's B fragments -> tensor memory ----------------------------------------------
+// ---- gathers: LL exchange buffer -> ring slots (TMA) -> this thread's B fragments -> tensor memory ---------------------------------
 // Thread (warp w, lane = 4 g + t) feeds sequence g. For ring-stage chunk c (2048 columns) warp w multiplies columns
 // [2048 c + 256 w, + 256): 16 k-steps, i.e. 8 blocks of 32 columns = 16 units each, of which this thread needs units 4 m + t (m = 0..3):
-// one 32-byte run per block in ll_pos order, fetched as two 16-byte loads ("pairs"; pair i belongs to k-step i). The 32 payload words of a
-// chunk are TMEM columns [32 c, 32 c + 32) of the thread's lane, in the order the hot loop wants them: word 2 i = b0, 2 i + 1 = b1 of k-step i.
-// The gathers work in HALF chunks (8 k-steps, 8 pairs, 16 TMEM columns), two in flight.
-struct GRaw {
-  uint64_t a[8], b[8];
-};
+// one 32-byte run per block in ll_pos order ("pairs" of units; pair i belongs to k-step i). The 32 payload words of a chunk are TMEM
+// columns [32 c, 32 c + 32) of the thread's lane, in the order the hot loop wants them: word 2 i = b0, 2 i + 1 = b1 of k-step i.
+//
+// 8 sequences make a gather 128 KB (hidden) to 344 KB (intermediate) of LL units per CTA: polled from registers that is many dependent
+// L2 round trips (~2 us each under the weight stream) and a large unrolled instruction footprint (an instruction-cache miss costs as
+// much as a data miss here). Instead the vector travels like the weights: consumer thread 0 points the TMA engine at the LL buffers
+// (one cp.async.bulk per sequence and chunk, 8 KB) and lands them in the NEXT RING SLOTS — every byte in flight at once, no registers, a
+// few instructions. The producers skip these "virtual" stages of the schedule. Threads then read their own units from shared memory
+// (conflict-free: sequences are skewed by 16 bytes), check the tags, and a block-wide vote (bar.red.or) decides: if any unit of the round
+// was not published yet, the round is copied again — one L2 round trip after the last unit lands, everybody has everything.
+constexpr int DB_GSEQ_STRIDE = 1024 * 8 + 16;  // bytes between sequences inside a ring slot: one chunk = 1024 units, + 16 B bank skew
+static_assert(DB_MAXB * DB_GSEQ_STRIDE <= DEC_STAGE_BYTES, "a gather chunk of 8 sequences must fit one ring stage");
+
 __device__ __forceinline__ int chunk_ksteps(int K, int c, int warp) { return max(0, min(DEC_KW / 16, (K - c * DEC_KC - warp * DEC_KW) / 16)); }
 __device__ __forceinline__ int half_ksteps(int K, int hc, int warp) { return max(0, min(8, chunk_ksteps(K, hc >> 1, warp) - 8 * (hc & 1))); }
-__device__ __forceinline__ const uint64_t* g_base(const uint64_t* src, int hc, int warp, int t) {
-  return src + 16 * (64 * (hc >> 1) + 8 * warp + 4 * (hc & 1)) + 4 * t;
-}
-__device__ __forceinline__ uint32_t g_issue(const uint64_t* src, int hc, int warp, int t, int ks, bool act, GRaw& raw) {
-  const uint64_t* base = g_base(src, hc, warp, t);
-  uint32_t pending = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    raw.a[i] = 0, raw.b[i] = 0;
-    if (act && i < ks) {
-      ll_load2(base + 16 * (i >> 1) + 2 * (i & 1), raw.a[i], raw.b[i]);
-      pending |= 1u << i;
-    }
-  }
-  return pending;
-}
-__device__ __forceinline__ void g_poll(const uint64_t* src, int hc, int warp, int t, uint32_t pending, uint32_t tag, GRaw& raw) {
-  const uint64_t* base = g_base(src, hc, warp, t);
-  uint32_t spins = 0;
-  while (pending) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (pending & (1u << i)) {
-        if (tag_ok(raw.a[i], tag) && tag_ok(raw.b[i], tag)) pending &= ~(1u << i);
-        else ll_load2(base + 16 * (i >> 1) + 2 * (i & 1), raw.a[i], raw.b[i]);
-      }
-    }
-    if (++spins > EMX_SPIN_LIMIT) __trap();
-  }
-}
 // natural unit index of payload word q (0..15) of half chunk hc for (warp, t)
 __device__ __forceinline__ int g_unit(int hc, int warp, int t, int q) { return 16 * (64 * (hc >> 1) + 8 * warp + 4 * (hc & 1) + (q >> 2)) + 4 * (q & 3) + t; }
 
-// Walk the half chunks of a K-element vector with THREE fetches in flight (each poll is one L2 round trip of ~2 us while the weight stream
-// saturates the memory system, so the number of sequential round trips is what a gather costs); take(hc, raw, ks) sees every half chunk.
-template <typename Take>
-__device__ __forceinline__ void g_walk(const uint64_t* src, int K, int warp, int t, bool act, uint32_t tag, Take&& take) {
-  const int nh = 2 * ((K + DEC_KC - 1) / DEC_KC);
-  GRaw A, B, C;
-  uint32_t pa = g_issue(src, 0, warp, t, half_ksteps(K, 0, warp), act, A);
-  uint32_t pb = g_issue(src, 1, warp, t, half_ksteps(K, 1, warp), act, B);  // nh >= 2
-  uint32_t pc = 0;
-#pragma unroll 1
-  for (int hc = 0; hc < nh; hc += 3) {
-    if (hc + 2 < nh) pc = g_issue(src, hc + 2, warp, t, half_ksteps(K, hc + 2, warp), act, C);
-    g_poll(src, hc, warp, t, pa, tag, A);
-    take(hc, A, half_ksteps(K, hc, warp));
-    if (hc + 3 < nh) pa = g_issue(src, hc + 3, warp, t, half_ksteps(K, hc + 3, warp), act, A);
-    if (hc + 1 < nh) {
-      g_poll(src, hc + 1, warp, t, pb, tag, B);
-      take(hc + 1, B, half_ksteps(K, hc + 1, warp));
-    }
-    if (hc + 4 < nh) pb = g_issue(src, hc + 4, warp, t, half_ksteps(K, hc + 4, warp), act, B);
-    if (hc + 2 < nh) {
-      g_poll(src, hc + 2, warp, t, pc, tag, C);
-      take(hc + 2, C, half_ksteps(K, hc + 2, warp));
-    }
-  }
-}
-
-// A plain vector per sequence (attention output for o_proj, SwiGLU output for down_proj): gather -> TMEM.
-__device__ __noinline__ void gather_plain_b(const uint64_t* buf, long seq_stride, int K, uint32_t tag, uint32_t tm, uint32_t active_mask, int warp, int lane) {
-  const int n = lane >> 2, t = lane & 3;
-  g_walk(buf + n * seq_stride, K, warp, t, (active_mask >> n) & 1, tag, [&](int hc, const GRaw& raw, int ks) {
-    if (ks > 0) {  // warp-uniform
-      uint32_t r[16];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r[2 * i] = static_cast<uint32_t>(raw.a[i]), r[2 * i + 1] = static_cast<uint32_t>(raw.b[i]);
-      tmem_st_32x16(tm + 16 * hc, r);
-    }
-  });
-  tmem_st_wait();
+__device__ __forceinline__ bool vote_any(bool pred) {  // OR over the 256 consumer threads (named barrier 1, as cbar)
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "bar.red.or.pred p, 1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(pred)), "n"(DEC_CTHREADS)
+      : "memory");
+  return out != 0;
 }
 
 __device__ __forceinline__ void ln_fetch_async_b(const __nv_bfloat16* w, uint32_t* ln_s, int H) {
@@ -305,47 +260,109 @@ __device__ __forceinline__ void ln_fetch_async_b(const __nv_bfloat16* w, uint32_
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// Residual stream in (LL units, or the embedding rows for layer 0) -> LlamaRMSNorm -> TMEM:  y = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))
-// Pass 1 parks the raw words in TMEM while summing squares, pass 2 normalises them in place. The CTA's own rows of the residual stream
-// are kept in shared memory for the residual add of the next o_proj / down_proj epilogue.
-__device__ __noinline__ void gather_rmsnorm_b(const uint64_t* buf, long seq_stride, const __nv_bfloat16* embed, int H, uint32_t tag, uint32_t tm, BatchShared& sh,
-                                              const uint32_t* ln_s, float eps, uint32_t parity, int rb2, int re2, int warp, int lane) {
+struct BCons {
+  uint32_t it;     // ring stage counter (weight stages, K/V items and the virtual stages of the gathers)
+  uint32_t group;  // row groups / attention flushes so far: selects the partial buffer, its named barrier and the rotating warp
+  uint32_t gph;    // completed phases of the gather mbarrier
+};
+
+// One gather: K-element vectors of all sequences (LL units at buf + n * seq_stride, ll_pos order) -> TMEM. norm: LlamaRMSNorm on the way,
+//   y = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))   (pass 1 parks the raw words in TMEM while summing squares, pass 2 normalises in place)
+// and the CTA's own rows of the residual stream are kept in shared memory for the residual add of the next o_proj / down_proj epilogue.
+// embed != nullptr (layer 0): the vectors are plain bf16 rows of the embedding table, no exchange, no ring slots.
+__device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int K, bool norm, const __nv_bfloat16* embed, uint32_t tag, uint32_t tm, BatchShared& sh,
+                                      uint8_t* ring, BCons& cs, const uint32_t* ln_s, float eps, uint32_t parity, int rb2, int re2, int warp, int lane) {
   const int n = lane >> 2, t = lane & 3;
   const bool act = (sh.active_mask >> n) & 1;
-  const int nh = 2 * ((H + DEC_KC - 1) / DEC_KC);
+  const int nc = gather_stages(K);
   float ss = 0.f;
-  auto park = [&](int hc, const uint32_t (&r)[16], int ks) {
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      if ((q >> 1) < ks) {
-        ss += sumsq2(r[q]);
-        const int u = g_unit(hc, warp, t, q);
-        if (act && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
-      }
-    }
-    tmem_st_32x16(tm + 16 * hc, r);
-  };
-  if (embed) {  // layer 0: plain bf16 rows of the embedding table
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(embed + static_cast<long>(sh.tok[n]) * H);
+  if (embed) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(embed + static_cast<long>(sh.tok[n]) * K);
 #pragma unroll 1
-    for (int hc = 0; hc < nh; ++hc) {
-      const int ks = half_ksteps(H, hc, warp);
+    for (int hc = 0; hc < 2 * nc; ++hc) {
+      const int ks = half_ksteps(K, hc, warp);
       if (ks > 0) {
         uint32_t r[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) r[q] = (act && (q >> 1) < ks) ? __ldg(row + g_unit(hc, warp, t, q)) : 0u;
-        park(hc, r, ks);
+        for (int q = 0; q < 16; ++q) {
+          r[q] = (act && (q >> 1) < ks) ? __ldg(row + g_unit(hc, warp, t, q)) : 0u;
+          ss += sumsq2(r[q]);
+          const int u = g_unit(hc, warp, t, q);
+          if (act && (q >> 1) < ks && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
+        }
+        tmem_st_32x16(tm + 16 * hc, r);
       }
     }
   } else {
-    g_walk(buf + n * seq_stride, H, warp, t, act, tag, [&](int hc, const GRaw& raw, int ks) {
-      if (ks > 0) {
-        uint32_t r[16];
+    const int units = static_cast<int>(seq_stride);  // per sequence, a multiple of 16
+#pragma unroll 1
+    for (int c0 = 0; c0 < nc; c0 += DEC_STAGES) {  // rounds of up to 3 chunks = 3 ring slots
+      const int nr = min(DEC_STAGES, nc - c0);
+      bool first = true;
+      float ss_try;
+      for (;;) {
+        if (threadIdx.x == 0) {
+          uint32_t bytes = 0;
+          for (int j = 0; j < nr; ++j) {
+            const uint32_t it = cs.it + j, slot = it % DEC_STAGES;
+            if (first) {  // the slot is ours once its previous stage has been released; advance its `full` phase (nobody waits on it)
+              mbar_wait(&sh.empty[slot], ((it / DEC_STAGES) & 1) ^ 1);
+              mbar_arrive(&sh.full[slot]);
+            }
+            bytes += static_cast<uint32_t>(__popc(sh.active_mask)) * static_cast<uint32_t>(min(1024, units - 1024 * (c0 + j)) * 8);
+          }
+          mbar_arrive_expect_tx(&sh.gbar, bytes);
+          const uint64_t policy = l2_policy_evict_last();
+          for (int j = 0; j < nr; ++j) {
+            const uint32_t slot = (cs.it + j) % DEC_STAGES;
+            const uint32_t cbytes = static_cast<uint32_t>(min(1024, units - 1024 * (c0 + j)) * 8);
+            for (int q = 0; q < DB_MAXB; ++q)
+              if ((sh.active_mask >> q) & 1)
+                bulk_g2s(ring + slot * DEC_STAGE_BYTES + q * DB_GSEQ_STRIDE, buf + q * seq_stride + 1024 * (c0 + j), cbytes, &sh.gbar, policy);
+          }
+        }
+        mbar_wait(&sh.gbar, cs.gph & 1);
+        ++cs.gph;
+        ss_try = 0.f;
+        bool bad = false;
+#pragma unroll 1
+        for (int hh = 0; hh < 2 * nr; ++hh) {
+          const int hc = 2 * c0 + hh;
+          const int ks = half_ksteps(K, hc, warp);
+          if (ks > 0) {  // warp-uniform
+            const uint8_t* base = ring + ((cs.it + (hh >> 1)) % DEC_STAGES) * DEC_STAGE_BYTES + n * DB_GSEQ_STRIDE + 128 * (8 * warp + 4 * (hh & 1)) + 32 * t;
+            uint32_t r[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[2 * i] = static_cast<uint32_t>(raw.a[i]), r[2 * i + 1] = static_cast<uint32_t>(raw.b[i]);
-        park(hc, r, ks);
+            for (int i = 0; i < 8; ++i) {
+              uint4 v = make_uint4(0u, tag, 0u, tag);
+              if (act && i < ks) v = *reinterpret_cast<const uint4*>(base + 128 * (i >> 1) + 16 * (i & 1));  // {payload, tag, payload, tag}
+              bad |= (v.y != tag) | (v.w != tag);
+              r[2 * i] = v.x, r[2 * i + 1] = v.z;
+            }
+            if (norm) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                ss_try += sumsq2(r[q]);
+                const int u = g_unit(hc, warp, t, q);
+                if (act && (q >> 1) < ks && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
+              }
+            }
+            tmem_st_32x16(tm + 16 * hc, r);
+          }
+        }
+        if (!vote_any(bad)) break;  // (also: everybody is done reading the slots, they may be overwritten)
+        first = false;
       }
-    });
+      ss += ss_try;
+      __syncwarp();
+      if (lane == 0)
+        for (int j = 0; j < nr; ++j) mbar_arrive(&sh.empty[(cs.it + j) % DEC_STAGES]);
+      cs.it += nr;
+    }
+  }
+  if (!norm) {
+    tmem_st_wait();
+    return;
   }
   // sum of squares of sequence n: the 4 lanes of a quad, then the 8 warps
   ss += __shfl_xor_sync(0xffffffffu, ss, 1);
@@ -357,10 +374,10 @@ __device__ __noinline__ void gather_rmsnorm_b(const uint64_t* buf, long seq_stri
   float tot = 0.f;
 #pragma unroll
   for (int w = 0; w < DEC_CWARPS; ++w) tot += sh.red[parity & 1][w][n];
-  const float rs = 1.0f / sqrtf(tot / H + eps);
+  const float rs = 1.0f / sqrtf(tot / K + eps);
 #pragma unroll 1
-  for (int hc = 0; hc < nh; ++hc) {
-    const int ks = half_ksteps(H, hc, warp);
+  for (int hc = 0; hc < 2 * nc; ++hc) {
+    const int ks = half_ksteps(K, hc, warp);
     if (ks > 0) {
       uint32_t r[16];
       tmem_ld_32x16(tm + 16 * hc, r);
@@ -380,11 +397,6 @@ __device__ __noinline__ void gather_rmsnorm_b(const uint64_t* buf, long seq_stri
 }
 
 // ---- consumer: tensor-core dot products of one weight phase, 8 sequences at once ---------------------------------------------
-struct BCons {
-  uint32_t it;     // ring stage counter
-  uint32_t group;  // row groups / attention flushes so far: selects the partial buffer, its named barrier and the rotating warp
-};
-
 // epi(row, v[4], n) is called by all 32 lanes of ONE warp per row group: lane = 8 a + n handles rows row .. row + 3 (row = r0 + 4 a) of
 // sequence n; rows >= r_end (short last group) must be ignored by the callee.
 template <typename Epi>
@@ -704,6 +716,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
       mbar_init(&sh.full[s], 1);
       mbar_init(&sh.empty[s], DEC_CWARPS);
     }
+    mbar_init(&sh.gbar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -757,7 +770,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
   const int rb = sh.r_begin[BPH_O], rb2 = rb >> 1, re2 = sh.r_end[BPH_O] >> 1;
   long long* dbg = (PROF && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
-  BCons cs{0, 0};
+  BCons cs{0, 0, 0};
   float best = -INFINITY;  // lm_head: this lane's best logit of ITS sequence (lane & 7)
   int best_i = 0x7fffffff;
 
@@ -772,9 +785,9 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
     const int gslot = (kind == BPH_Q) ? 0 : (kind == BPH_O) ? 1 : (kind == BPH_GATEUP) ? 2 : (kind == BPH_DOWN) ? 3 : -1;
     long long* gdbg = (PROF && p.dbg && tid == 0 && layer == 1 && gslot >= 0) ? reinterpret_cast<long long*>(p.dbg) + 2 * n_steps + 8 + 8 * blockIdx.x + 2 * gslot : nullptr;
     if (PROF && gdbg) gdbg[0] = global_ns();
-    if (kind == BPH_Q || kind == BPH_GATEUP || kind == BPH_LMHEAD) {
-      gather_rmsnorm_b(kind == BPH_GATEUP ? xo : xd, sH, step == 0 ? static_cast<const __nv_bfloat16*>(p.embed) : nullptr, H, tag, tm, sh, ln_s, p.rms_eps,
-                       kind == BPH_GATEUP ? 1u : 0u, rb2, re2, warp, lane);
+    if (kind == BPH_Q || kind == BPH_GATEUP || kind == BPH_LMHEAD) {  // residual stream in + RMSNorm
+      gather_b(kind == BPH_GATEUP ? xo : xd, sH, H, true, step == 0 ? static_cast<const __nv_bfloat16*>(p.embed) : nullptr, tag, tm, sh, ring, cs, ln_s,
+               p.rms_eps, kind == BPH_GATEUP ? 1u : 0u, rb2, re2, warp, lane);
       if (kind != BPH_LMHEAD) {
         const __nv_bfloat16* next_w = (kind == BPH_Q)    ? static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H
                                       : (layer + 1 < L) ? static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer + 1) * H
@@ -783,7 +796,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
       }
     } else if (kind == BPH_O || kind == BPH_DOWN) {  // a plain vector in: the attention output for o_proj, the SwiGLU output for down_proj
       const bool o = (kind == BPH_O);
-      gather_plain_b(o ? attn : hbuf, o ? sH : sI, o ? H : I, tag, tm, active_mask, warp, lane);
+      gather_b(o ? attn : hbuf, o ? sH : sI, o ? H : I, false, nullptr, tag, tm, sh, ring, cs, ln_s, 0.f, 0u, rb2, re2, warp, lane);
     }
     if (PROF && dbg) dbg[2 * step + 1] = global_ns();
     if (PROF && gdbg) gdbg[1] = global_ns();

@@ -289,6 +289,22 @@ class OpenVLAForActionPrediction:
         return out
 
     @torch.no_grad()
+    def predict_action_batch(self, inputs: Sequence[Mapping], unnorm_key: Optional[str] = None) -> np.ndarray:
+        """`predict_action` (modeling_prismatic.py:506-537) for N processor outputs at once: [N, action_dim] float64, row i identical to
+        `predict_action(**inputs[i], unnorm_key=unnorm_key)` — N simulator environments / robots share each pass over the weights."""
+        n = self.get_action_dim(unnorm_key)
+        ids = []
+        for i in inputs:
+            x = i["input_ids"]
+            if not torch.all(x[:, -1] == 29871):
+                x = torch.cat((x, torch.tensor([[29871]], dtype=x.dtype, device=x.device)), dim=1)
+            ids.append(x)
+        gen = self.generate_batch(ids, [i["pixel_values"] for i in inputs], max_new_tokens=n)
+        tail = torch.stack([g[0, -n:] for g in gen]).reshape(-1)
+        _, actions = self.detokenize_on_device(tail, unnorm_key)
+        return actions.cpu().numpy().reshape(len(gen), n)
+
+    @torch.no_grad()
     def generate_actions_batch(self, inputs: Sequence[Mapping], tokenizer: Any = None, type: str = "act",  # noqa: A002
                                max_new_tokens: Union[int, Sequence[int]] = 512, do_sample: bool = False) -> List[Tuple[Any, str]]:
         """`generate_actions(inputs, tokenizer, ...)` (README.md:44-47) for a list of processor outputs at once: one (action[7], reasoning)

@@ -123,3 +123,32 @@ class OpenVLAInference:
         import cv2 as cv  # the reference resizes with OpenCV's area interpolation (:147-149)
 
         return cv.resize(image, tuple(self.image_size), interpolation=cv.INTER_AREA)
+
+
+class BatchedOpenVLAInference:
+    """N SimplerEnv environments behind ONE model: `step(images, task_descriptions)` runs the N requests through `predict_action_batch`
+    (8 sequences per pass over the weights, emx_decode_batch_step) and then each environment's own post-processing state machine
+    (sticky gripper, task reset) exactly as N independent `OpenVLAInference` objects would. The reference evaluates its environments one
+    by one because its cached generation asserts batch size 1 (modeling_prismatic.py:326, :460-463)."""
+
+    def __init__(self, n_envs: int, **kwargs: Any) -> None:
+        first = OpenVLAInference(**kwargs)
+        shared = dict(kwargs, vla=first.vla, processor=first.processor)
+        self.envs: List[OpenVLAInference] = [first] + [OpenVLAInference(**shared) for _ in range(n_envs - 1)]
+        self.vla, self.processor = first.vla, first.processor
+
+    def reset(self, task_descriptions: List[Optional[str]]) -> None:
+        for env, t in zip(self.envs, task_descriptions):
+            env.reset(t)
+
+    def step(self, images: List[np.ndarray], task_descriptions: Optional[List[Optional[str]]] = None) -> List[Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]]:
+        assert len(images) == len(self.envs)
+        tasks = task_descriptions if task_descriptions is not None else [None] * len(self.envs)
+        inputs = []
+        for env, image, task in zip(self.envs, images, tasks):
+            if task is not None and task != env.task_description:
+                env.reset(task)
+            assert image.dtype == np.uint8
+            inputs.append(self.processor(task, Image.fromarray(env._resize_image(image))).to(env.device, dtype=torch.bfloat16))
+        raw = self.vla.predict_action_batch(inputs, unnorm_key=self.envs[0].unnorm_key)
+        return [env.postprocess(raw[i][None]) for i, env in enumerate(self.envs)]

@@ -163,3 +163,40 @@ def test_full_size_batch_scripted_512_tokens_mixed_limits():
     new, _ = model.engine.generate_batch(torch.cat(ids, 0), pv, limits, eos_token_id=None)
     for b, lim in enumerate(limits):
         assert new[b].cpu().tolist() == script[:lim], f"sequence {b} (limit {lim}): ids differ from the script"
+
+
+def test_simpler_policy_on_the_engine_single_and_batched():
+    """the SimplerEnv policy wrapper driving the REAL engine. `OpenVLAInference.step` (openvla_model.py:72-145) on one
+    environment, and `BatchedOpenVLAInference.step` over 5 environments (different frames and tasks) in one batched decode: every
+    environment's raw action and post-processed action equal its own single-environment step, bit for bit."""
+    from emmax_b200 import AutoProcessor, BatchedOpenVLAInference, OpenVLAForActionPrediction, OpenVLAInference, tiny_config
+    from emmax_b200.synthetic import make_state_dict, predict_action_chain
+
+    cfg = tiny_config()
+    stats = cfg.norm_stats["synthetic"]
+    cfg.norm_stats = {"bridge_orig": stats}
+    # plant the predict_action chain (29871 -> 7 action ids) so the greedy action tokens are well separated from bf16 noise
+    prev0, chain = predict_action_chain([])
+    sd = make_state_dict(cfg, seed=21, device="cpu", extra_chains=[(prev0, chain)])
+    model = OpenVLAForActionPrediction(cfg, sd, max_batch=8, max_context=1024).to("cuda")
+    proc = AutoProcessor.from_pretrained(None)
+    rng = np.random.default_rng(4)
+    n_env = 5
+    frames = [rng.integers(0, 256, (256, 320, 3), dtype=np.uint8) for _ in range(n_env)]
+    tasks = ["put carrot in pot", "open the drawer", "put carrot in pot", "stack the green block on the yellow block", "close drawer"]
+    kw = dict(policy_setup="widowx_bridge", vla=model, processor=proc, device="cuda")
+    batched = BatchedOpenVLAInference(n_env, **kw)
+    singles = [OpenVLAInference(**kw) for _ in range(n_env)]
+    for step in range(2):
+        got = batched.step(frames, tasks)
+        for e in range(n_env):
+            raw, act = singles[e].step(frames[e], tasks[e])
+            for k in raw:
+                assert np.array_equal(got[e][0][k], raw[k]), (step, e, k)
+            for k in act:
+                assert np.array_equal(np.asarray(got[e][1][k]), np.asarray(act[k])), (step, e, k)
+        frames = [np.roll(f, 7, axis=1) for f in frames]
+    # the planted chain really is what came out: the un-normalised action of the chain's tokens
+    want = model.detokenize_on_device(torch.tensor(chain, dtype=torch.int32, device="cuda"))[1].cpu().numpy()
+    raw, _ = singles[0].step(frames[0], tasks[0])
+    assert np.array_equal(np.concatenate([raw["world_vector"], raw["rotation_delta"], raw["open_gripper"]]), want)

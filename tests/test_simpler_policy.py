@@ -58,3 +58,40 @@ def test_step_matches_the_reference_class(golden_dir, setup):
             assert np.allclose(np.asarray(act[k], dtype=np.float64).reshape(-1), np.asarray(want["action"][k]).reshape(-1), rtol=0, atol=1e-12), (t, k)
     with pytest.raises(NotImplementedError):
         OpenVLAInference(policy_setup="aloha", vla=_VLA([]), processor=_Proc())
+
+
+def test_batched_policy_equals_independent_policies(golden_dir):
+    """BatchedOpenVLAInference over N environments == N independent OpenVLAInference objects fed the same model outputs (per-environment
+    sticky-gripper state, task resets), with the model called ONCE per step through predict_action_batch."""
+    from emmax_b200 import BatchedOpenVLAInference
+
+    g = json.load(open(os.path.join(golden_dir, "simpler_policy_golden.json")))["google_robot"]
+    outs = np.asarray(g["model_outputs"], dtype=np.float64)
+    n_env, T = 3, len(outs)
+    # environment e sees the golden action stream shifted by e steps
+    streams = [np.roll(outs, -e, axis=0) for e in range(n_env)]
+
+    class _BatchVLA:
+        calls, t = 0, 0
+
+        def predict_action_batch(self, inputs, unnorm_key=None):
+            assert len(inputs) == n_env and unnorm_key == g["unnorm_key"]
+            self.calls += 1
+            out = np.stack([streams[e][self.t] for e in range(n_env)])
+            self.t += 1
+            return out
+
+    vla = _BatchVLA()
+    pol = BatchedOpenVLAInference(n_env, policy_setup="google_robot", action_scale=g["action_scale"], vla=vla, processor=_Proc(), device="cpu")
+    singles = [OpenVLAInference(policy_setup="google_robot", action_scale=g["action_scale"], vla=_VLA(streams[e]), processor=_Proc(), device="cpu") for e in range(n_env)]
+    img = np.zeros((256, 320, 3), dtype=np.uint8)
+    for t in range(T):
+        tasks = [g["tasks"][t]] * n_env
+        got = pol.step([img] * n_env, tasks)
+        for e in range(n_env):
+            raw, act = singles[e].step(img, tasks[e])
+            for k in raw:
+                assert np.array_equal(got[e][0][k], raw[k]), (t, e, k)
+            for k in act:
+                assert np.array_equal(np.asarray(got[e][1][k]), np.asarray(act[k])), (t, e, k)
+    assert vla.calls == T
