@@ -14,7 +14,7 @@ from typing import Any, Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libemmax.so")
+LIB_PATH = os.environ.get("EMX_LIB", os.path.join(_HERE, "libemmax.so"))  # (EMX_LIB: A/B builds of the kernels in tools/ probes)
 
 EPI_GELU = 1
 EPI_SWIGLU = 2
@@ -69,7 +69,7 @@ class DecodeBatchParams(C.Structure):
         ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("block_table", C.c_void_p),
         ("page_size", C.c_int32), ("n_pages", C.c_int32), ("max_pages", C.c_int32), ("out_stride", C.c_int32),
         ("x", C.c_void_p), ("xo", C.c_void_p), ("attn", C.c_void_p), ("qkv", C.c_void_p), ("h", C.c_void_p),
-        ("part", C.c_void_p), ("argmax_part", C.c_void_p),
+        ("part", C.c_void_p), ("argmax_part", C.c_void_p), ("sync", C.c_void_p),
         ("out_tokens", C.c_void_p), ("logits_out", C.c_void_p), ("state", C.c_void_p), ("dbg", C.c_void_p),
         ("eos_token", C.c_int32), ("l2_lookahead_stages", C.c_int32),
     ]  # fmt: skip

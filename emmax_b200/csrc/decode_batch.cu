@@ -23,6 +23,7 @@
 //   * per-sequence position, block table, RoPE row, token limit and EOS state; sequences that are finished (or slots beyond `batch`)
 //     are inactive: nobody waits for their units, nothing of theirs is stored.
 // Rounding points mirror the torch-eager reference exactly as decode_mega.cu does.
+#include <cstdio>
 #include "decode_common.cuh"
 #include "emmax.h"
 
@@ -189,8 +190,16 @@ __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, co
         continue;
       }
       const int K = sh.K[kind], r_end = sh.r_end[kind];
-      // the gather in front of this phase occupies ring slots of its own (none for k / v rows, and none for the embedding rows of layer 0)
-      if (kind != BPH_K && kind != BPH_V && !(layer == 0 && kind == BPH_Q)) it += gather_stages(K);
+      // the gather in front of this phase occupies ring slots of its own
+      // (k / v rows and the embedding rows of layer 0 have none). The producers issue nothing for them but still wait for each of
+      // these slots in turn: an mbarrier wait carries ONE parity bit, so a warp must observe every phase of a slot's `empty` barrier
+      // in order — skipping the wait would let the test for the slot's NEXT use pass two phases early.
+      if (kind != BPH_K && kind != BPH_V && !(layer == 0 && kind == BPH_Q)) {
+        for (int v = 0; v < gather_stages(K); ++v, ++it) {
+          if (!PREFETCH && lane == 0) mbar_wait(&empty[it % DEC_STAGES], ((it / DEC_STAGES) & 1) ^ 1);
+        }
+        __syncwarp();
+      }
       const __nv_bfloat16* W = sh.W[kind] + layer * sh.layer_stride[kind];
       for (int r = sh.r_begin[kind]; r < r_end; r += DEC_GROUP) {
         const int nrows = min(DEC_GROUP, r_end - r);
@@ -264,6 +273,7 @@ struct BCons {
   uint32_t it;     // ring stage counter (weight stages, K/V items and the virtual stages of the gathers)
   uint32_t group;  // row groups / attention flushes so far: selects the partial buffer, its named barrier and the rotating warp
   uint32_t gph;    // completed phases of the gather mbarrier
+  uint32_t gathers;  // exchanges (gathers out of an LL buffer) done so far in this launch
 };
 
 // One gather: K-element vectors of all sequences (LL units at buf + n * seq_stride, ll_pos order) -> TMEM. norm: LlamaRMSNorm on the way,
@@ -271,7 +281,9 @@ struct BCons {
 // and the CTA's own rows of the residual stream are kept in shared memory for the residual add of the next o_proj / down_proj epilogue.
 // embed != nullptr (layer 0): the vectors are plain bf16 rows of the embedding table, no exchange, no ring slots.
 __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int K, bool norm, const __nv_bfloat16* embed, uint32_t tag, uint32_t tm, BatchShared& sh,
-                                      uint8_t* ring, BCons& cs, const uint32_t* ln_s, float eps, uint32_t parity, int rb2, int re2, int warp, int lane) {
+                                      uint8_t* ring, BCons& cs, const uint32_t* ln_s, float eps, uint32_t parity, int rb2, int re2, int warp, int lane,
+                                      void* sync_cnt, uint32_t gathers_per_launch, long long* gprof) {
+  // gprof (instrumented twin, thread 0 only): [0] cbar, [1] arrival counter, [2] free slots, [3] copy landed, [4] read + park + vote, [5] norm tail, [6] attempts
   const int n = lane >> 2, t = lane & 3;
   const bool act = (sh.active_mask >> n) & 1;
   const int nc = gather_stages(K);
@@ -295,11 +307,42 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
     }
   } else {
     const int units = static_cast<int>(seq_stride);  // per sequence, a multiple of 16
+    // Arrival counter of the exchange: the vector was produced by the phase every CTA has just finished, so "all CTAs have arrived here"
+    // means "every unit is published". It only decides WHEN the copy is worth issuing (one attempt instead of a burst of re-copies from
+    // the CTAs that get here early, which would flood the L2 the stragglers are still writing through); the tags stay the proof.
+    long long tg = gprof ? global_ns() : 0;
+    auto lap = [&](int k) {
+      if (gprof) {
+        const long long now = global_ns();
+        gprof[k] += now - tg, tg = now;
+      }
+    };
+    cbar();  // every warp of this CTA is done with the previous phase: its epilogues' / combines' stores are issued
+    lap(0);
+    if (threadIdx.x == 0) {
+      unsigned long long* cnt = static_cast<unsigned long long*>(sync_cnt);
+      asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(cnt) : "memory");  // (release: cumulative over the barrier above)
+      const unsigned long long want = (static_cast<unsigned long long>(sh.epoch) * gathers_per_launch + cs.gathers + 1ull) * gridDim.x;
+      uint32_t spins = 0;
+      for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(cnt) : "memory");
+        if (v >= want) break;
+        __nanosleep(64);
+        if (++spins > EMX_SPIN_LIMIT) __trap();
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what the generic proxy has just observed
+      lap(1);
+    }
+    ++cs.gathers;
 #pragma unroll 1
     for (int c0 = 0; c0 < nc; c0 += DEC_STAGES) {  // rounds of up to 3 chunks = 3 ring slots
       const int nr = min(DEC_STAGES, nc - c0);
       bool first = true;
       float ss_try;
+#ifdef EMX_GATHER_DEBUG
+      uint32_t dbg_attempts = 0;
+#endif
       for (;;) {
         if (threadIdx.x == 0) {
           uint32_t bytes = 0;
@@ -311,6 +354,7 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
             }
             bytes += static_cast<uint32_t>(__popc(sh.active_mask)) * static_cast<uint32_t>(min(1024, units - 1024 * (c0 + j)) * 8);
           }
+          lap(2);
           mbar_arrive_expect_tx(&sh.gbar, bytes);
           const uint64_t policy = l2_policy_evict_last();
           for (int j = 0; j < nr; ++j) {
@@ -323,6 +367,8 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
         }
         mbar_wait(&sh.gbar, cs.gph & 1);
         ++cs.gph;
+        if (threadIdx.x == 0) lap(3);
+        if (gprof && threadIdx.x == 0) gprof[6] += 1;
         ss_try = 0.f;
         bool bad = false;
 #pragma unroll 1
@@ -332,11 +378,12 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
           if (ks > 0) {  // warp-uniform
             const uint8_t* base = ring + ((cs.it + (hh >> 1)) % DEC_STAGES) * DEC_STAGE_BYTES + n * DB_GSEQ_STRIDE + 128 * (8 * warp + 4 * (hh & 1)) + 32 * t;
             uint32_t r[16];
+            bool hbad = false;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               uint4 v = make_uint4(0u, tag, 0u, tag);
               if (act && i < ks) v = *reinterpret_cast<const uint4*>(base + 128 * (i >> 1) + 16 * (i & 1));  // {payload, tag, payload, tag}
-              bad |= (v.y != tag) | (v.w != tag);
+              hbad |= (v.y != tag) | (v.w != tag);
               r[2 * i] = v.x, r[2 * i + 1] = v.z;
             }
             if (norm) {
@@ -347,11 +394,23 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
                 if (act && (q >> 1) < ks && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
               }
             }
-            tmem_st_32x16(tm + 16 * hc, r);
+            // (two tcgen05.st to the same columns are not ordered without a wait: never park words that a retry will replace)
+            if (!__any_sync(0xffffffffu, hbad)) tmem_st_32x16(tm + 16 * hc, r);
+            bad |= hbad;
           }
         }
-        if (!vote_any(bad)) break;  // (also: everybody is done reading the slots, they may be overwritten)
+        const bool again = vote_any(bad);  // (also: everybody is done reading the slots, they may be overwritten)
+        if (threadIdx.x == 0) lap(4);
+        if (!again) break;
         first = false;
+        __nanosleep(500);
+#ifdef EMX_GATHER_DEBUG
+        if (++dbg_attempts > 20000u) {
+          if (bad && (threadIdx.x & 31) < 8)
+            printf("gather stuck: cta %d tid %d K %d norm %d c0 %d tag %u it %u gph %u act %d\n", blockIdx.x, threadIdx.x, K, int(norm), c0, tag, cs.it, cs.gph, int(act));
+          break;
+        }
+#endif
       }
       ss += ss_try;
       __syncwarp();
@@ -364,6 +423,7 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
     tmem_st_wait();
     return;
   }
+  const long long tg_tail = gprof ? global_ns() : 0;
   // sum of squares of sequence n: the 4 lanes of a quad, then the 8 warps
   ss += __shfl_xor_sync(0xffffffffu, ss, 1);
   ss += __shfl_xor_sync(0xffffffffu, ss, 2);
@@ -394,6 +454,7 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
   }
   tmem_st_wait();
   cbar();  // everybody is done with ln_s: the next norm's weights may be fetched into it
+  if (gprof && threadIdx.x == 0 && !embed) gprof[5] += global_ns() - tg_tail;
 }
 
 // ---- consumer: tensor-core dot products of one weight phase, 8 sequences at once ---------------------------------------------
@@ -770,7 +831,8 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
   const int rb = sh.r_begin[BPH_O], rb2 = rb >> 1, re2 = sh.r_end[BPH_O] >> 1;
   long long* dbg = (PROF && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
-  BCons cs{0, 0, 0};
+  BCons cs{0, 0, 0, 0};
+  long long* gprof = (PROF && dbg) ? dbg + 2 * (BPH_STEPS * L + 1) + 8 + 8 * gridDim.x : nullptr;  // (host zeroes it)
   float best = -INFINITY;  // lm_head: this lane's best logit of ITS sequence (lane & 7)
   int best_i = 0x7fffffff;
 
@@ -787,7 +849,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
     if (PROF && gdbg) gdbg[0] = global_ns();
     if (kind == BPH_Q || kind == BPH_GATEUP || kind == BPH_LMHEAD) {  // residual stream in + RMSNorm
       gather_b(kind == BPH_GATEUP ? xo : xd, sH, H, true, step == 0 ? static_cast<const __nv_bfloat16*>(p.embed) : nullptr, tag, tm, sh, ring, cs, ln_s,
-               p.rms_eps, kind == BPH_GATEUP ? 1u : 0u, rb2, re2, warp, lane);
+               p.rms_eps, kind == BPH_GATEUP ? 1u : 0u, rb2, re2, warp, lane, p.sync, 4u * L, gprof);
       if (kind != BPH_LMHEAD) {
         const __nv_bfloat16* next_w = (kind == BPH_Q)    ? static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H
                                       : (layer + 1 < L) ? static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer + 1) * H
@@ -796,7 +858,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
       }
     } else if (kind == BPH_O || kind == BPH_DOWN) {  // a plain vector in: the attention output for o_proj, the SwiGLU output for down_proj
       const bool o = (kind == BPH_O);
-      gather_b(o ? attn : hbuf, o ? sH : sI, o ? H : I, false, nullptr, tag, tm, sh, ring, cs, ln_s, 0.f, 0u, rb2, re2, warp, lane);
+      gather_b(o ? attn : hbuf, o ? sH : sI, o ? H : I, false, nullptr, tag, tm, sh, ring, cs, ln_s, 0.f, 0u, rb2, re2, warp, lane, p.sync, 4u * L, gprof);
     }
     if (PROF && dbg) dbg[2 * step + 1] = global_ns();
     if (PROF && gdbg) gdbg[1] = global_ns();
@@ -906,7 +968,7 @@ extern "C" int emx_decode_batch_step(const emx_decode_batch_params* params, cuda
   EMX_REQUIRE(p.batch >= 1 && p.batch <= DB_MAXB, "emx_decode_batch_step: batch %d not in 1..%d", p.batch, DB_MAXB);
   EMX_REQUIRE(p.hidden % 16 == 0 && p.inter % 16 == 0 && p.vocab % 2 == 0, "emx_decode_batch_step: hidden/inter must be multiples of 16, vocab even");
   EMX_REQUIRE(p.heads * DEC_HD == p.hidden, "emx_decode_batch_step: heads x head_dim must equal hidden");
-  EMX_REQUIRE(p.x && p.xo && p.qkv && p.attn && p.h && p.part && p.argmax_part && p.state && p.out_tokens && p.block_table,
+  EMX_REQUIRE(p.x && p.xo && p.qkv && p.attn && p.h && p.part && p.argmax_part && p.state && p.out_tokens && p.block_table && p.sync,
               "emx_decode_batch_step: null pointer");
   EMX_REQUIRE(p.hidden * 2 <= DB_LN_BYTES, "emx_decode_batch_step: hidden > %d not supported by the fused gather + RMSNorm", DB_LN_BYTES / 2);
   EMX_REQUIRE(p.inter <= 8 * DEC_KC && p.hidden <= 8 * DEC_KC, "emx_decode_batch_step: activation vector exceeds the 256 TMEM columns of a thread");

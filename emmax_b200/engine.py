@@ -400,6 +400,7 @@ class Engine:
         self.b_qkv, self.b_h = ll(MB * 3 * H // 2), ll(MB * R(I // 2))
         self.b_part = ll(MB * t.num_attention_heads * ATT_MAX_SEGMENTS * (t.head_dim + 2))
         self.b_argmax = ll(grid * MB * 2)
+        self.b_sync = ll(2)
         self.b_state = torch.zeros(C.sizeof(DecodeBatchState) // 4, dtype=torch.int32, device=dev)
         self.b_out = torch.zeros((MB, self.max_new), dtype=torch.int32, device=dev)
         self.h_bflag = torch.zeros(C.sizeof(DecodeBatchState) // 4, dtype=torch.int32).pin_memory()
@@ -415,7 +416,7 @@ class Engine:
         p.k_cache, p.v_cache, p.block_table = ptr(self.k_cache), ptr(self.v_cache), ptr(self.block_table)
         p.page_size, p.n_pages, p.max_pages, p.out_stride = self.PAGE, self.n_pages, self.pages_per_seq, self.b_out.shape[1]
         p.x, p.xo, p.attn, p.qkv, p.h = ptr(self.b_x), ptr(self.b_xo), ptr(self.b_attn), ptr(self.b_qkv), ptr(self.b_h)
-        p.part, p.argmax_part = ptr(self.b_part), ptr(self.b_argmax)
+        p.part, p.argmax_part, p.sync = ptr(self.b_part), ptr(self.b_argmax), ptr(self.b_sync)
         p.out_tokens, p.logits_out, p.state, p.dbg = ptr(self.b_out), None, ptr(self.b_state), None
         p.eos_token = -1
         p.l2_lookahead_stages = int(os.environ.get("EMX_BATCH_L2_LOOKAHEAD_STAGES", "6"))

@@ -230,10 +230,11 @@ typedef struct emx_decode_batch_params {
   void* h;        /* [8][R(inter/2)]: SwiGLU output */
   void* part;     /* [8][heads][EMX_DECODE_ATT_MAX_SEGMENTS][head_dim + 2]: split-KV partials (fp32 payloads) */
   void* argmax_part; /* [grid][8][2] */
+  void* sync;        /* one uint64 (zeroed once at allocation, kernel-owned): arrival counter of the exchanges */
   int32_t* out_tokens;  /* out_tokens[i * out_stride + n_generated[i]] = new token of sequence i */
   float* logits_out;    /* optional [8][vocab] fp32 (bf16-rounded values), for parity tests */
   emx_decode_batch_state* state;
-  int64_t* dbg;         /* optional (>= 2 * (7 * layers + 1) + 8 + 8 * grid int64): CTA 0 stores %globaltimer before / after every phase's gather,
+  int64_t* dbg;         /* optional (>= 2 * (7 * layers + 1) + 8 + 8 * grid + 8 int64, zeroed by the caller): CTA 0 stores %globaltimer before / after every phase's gather,
                          * every CTA the entry / exit times of layer 1's four gathers; selects the instrumented twin */
   int32_t eos_token;    /* -1 disables EOS handling */
   /* look-ahead (ring stages of 64 KB) of the idle-triggered cp.async.bulk.prefetch.L2 warp beyond the shared-memory ring; 0 disables */

@@ -46,10 +46,16 @@ for B, LA in [(int(b), int(la)) for b in args.batches.split(",") for la in args.
     for _ in range(args.steps):
         _lib.check(lib.emx_decode_batch_step(C.byref(p), _lib.stream()))
     e1.record()
+    for _ in range(60):  # keep the GPU busy while the clocks are sampled
+        _lib.check(lib.emx_decode_batch_step(C.byref(p), _lib.stream()))
+    import subprocess
+    clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader"],
+                         capture_output=True, text=True).stdout.strip()
     torch.cuda.synchronize()
+    print(f"   [clocks under load: {clk}]")
     ctx = int(st[8].item())
     print(f"== batch {B}, L2 look-ahead {LA} stages, context {ctx}: PRODUCT kernel {e0.elapsed_time(e1) / args.steps:.3f} ms/launch", flush=True)
-    dbg = torch.zeros(2 * n_steps + 8 + 8 * GRID, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(2 * n_steps + 8 + 8 * GRID + 8, dtype=torch.int64, device="cuda")
     p.dbg = dbg.data_ptr()
     gath, body, tot, skew = np.zeros(8), np.zeros(8), [], []
     for _ in range(args.steps):
@@ -57,7 +63,7 @@ for B, LA in [(int(b), int(la)) for b in args.batches.split(",") for la in args.
         torch.cuda.synchronize()
         t = dbg.cpu().numpy().astype(np.float64)
         tot.append((t[2 * n_steps] - t[0]) / 1e3)
-        g = t[2 * n_steps + 8 :].reshape(GRID, 4, 2)
+        g = t[2 * n_steps + 8 : 2 * n_steps + 8 + 8 * GRID].reshape(GRID, 4, 2)
         skew.append([(g[:, k, 0].max() - g[:, k, 0].min(), g[:, k, 1].max() - g[:, k, 1].min(), np.median(g[:, k, 1] - g[:, k, 0]), (g[:, k, 1] - g[:, k, 0]).min()) for k in range(4)])
         for s in range(n_steps):
             k = 7 if s == n_steps - 1 else s % 7
@@ -67,6 +73,9 @@ for B, LA in [(int(b), int(la)) for b in args.batches.split(",") for la in args.
     print(f"   instrumented twin: {np.mean(tot):.1f} us per launch (CTA 0, first gather -> end of lm_head)")
     print("   per layer (us):  " + "  ".join(f"{KINDS[k]}: gather {gath[k] / n / L / 1e3:.2f} + body {body[k] / n / L / 1e3:.2f}" for k in range(7)))
     print(f"   per launch (us): gathers {gath[:7].sum() / n / 1e3:.0f}, bodies {body[:7].sum() / n / 1e3:.0f}, lm_head gather {gath[7] / n / 1e3:.1f} + body {body[7] / n / 1e3:.1f}")
+    gp = dbg.cpu().numpy()[2 * n_steps + 8 + 8 * GRID :].astype(np.float64) / n  # accumulated over the launches
+    print(f"   gathers of CTA 0, thread 0, per launch (us): cbar {gp[0] / 1e3:.0f}, arrival counter {gp[1] / 1e3:.0f}, free slots {gp[2] / 1e3:.0f}, copy landed {gp[3] / 1e3:.0f}, "
+          f"read+park+vote {gp[4] / 1e3:.0f} (first loop trip {gp[7] / 1e3:.0f}), norm tail {gp[5] / 1e3:.0f}; attempts {gp[6] * 1.0:.0f} for {4 * L} gathers")
     sk = np.mean(np.array(skew), axis=0) / 1e3
     print("   layer 1, all CTAs (us): " + "  ".join(f"{nm}: entry spread {sk[k, 0]:.1f}, exit spread {sk[k, 1]:.1f}, gather median {sk[k, 2]:.1f} / min {sk[k, 3]:.1f}"
                                                     for k, nm in enumerate(["q", "o", "gateup", "down"])), flush=True)
