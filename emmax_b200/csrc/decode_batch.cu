@@ -282,7 +282,8 @@ struct BCons {
 // embed != nullptr (layer 0): the vectors are plain bf16 rows of the embedding table, no exchange, no ring slots.
 __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int K, bool norm, const __nv_bfloat16* embed, uint32_t tag, uint32_t tm, BatchShared& sh,
                                       uint8_t* ring, BCons& cs, const uint32_t* ln_s, float eps, uint32_t parity, int rb2, int re2, int warp, int lane,
-                                      void* sync_cnt, uint32_t gathers_per_launch, long long* gprof) {
+                                      void* sync_cnt, uint32_t gathers_per_launch, long long* gprof, long long* gcta) {
+  // gcta (instrumented twin, thread 0 of every CTA, layer 1 only): [0] after the entry barrier, [1] arrival counter complete
   // gprof (instrumented twin, thread 0 only): [0] cbar, [1] arrival counter, [2] free slots, [3] copy landed, [4] read + park + vote, [5] norm tail, [6] attempts
   const int n = lane >> 2, t = lane & 3;
   const bool act = (sh.active_mask >> n) & 1;
@@ -307,6 +308,7 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
     }
   } else {
     const int units = static_cast<int>(seq_stride);  // per sequence, a multiple of 16
+    const uint32_t ring_s = smem_u32(ring);
     // Arrival counter of the exchange: the vector was produced by the phase every CTA has just finished, so "all CTAs have arrived here"
     // means "every unit is published". It only decides WHEN the copy is worth issuing (one attempt instead of a burst of re-copies from
     // the CTAs that get here early, which would flood the L2 the stragglers are still writing through); the tags stay the proof.
@@ -319,9 +321,13 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
     };
     cbar();  // every warp of this CTA is done with the previous phase: its epilogues' / combines' stores are issued
     lap(0);
+    if (gcta && threadIdx.x == 0) gcta[0] = global_ns();
     if (threadIdx.x == 0) {
       unsigned long long* cnt = static_cast<unsigned long long*>(sync_cnt);
-      asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(cnt) : "memory");  // (release: cumulative over the barrier above)
+      // relaxed on purpose: a release would put a MEMBAR.GPU (microseconds while the SM's bulk copies are in flight) on the critical path of
+      // every exchange. This CTA's LL stores were issued before the barrier above and drain to the L2 ahead of this reduction in practice;
+      // if one ever lags, its tag is stale in the copy and the round is simply copied again.
+      asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(cnt) : "memory");
       const unsigned long long want = (static_cast<unsigned long long>(sh.epoch) * gathers_per_launch + cs.gathers + 1ull) * gridDim.x;
       uint32_t spins = 0;
       for (;;) {
@@ -333,6 +339,7 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
       }
       asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what the generic proxy has just observed
       lap(1);
+      if (gcta) gcta[1] = global_ns();
     }
     ++cs.gathers;
 #pragma unroll 1
@@ -376,22 +383,26 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
           const int hc = 2 * c0 + hh;
           const int ks = half_ksteps(K, hc, warp);
           if (ks > 0) {  // warp-uniform
-            const uint8_t* base = ring + ((cs.it + (hh >> 1)) % DEC_STAGES) * DEC_STAGE_BYTES + n * DB_GSEQ_STRIDE + 128 * (8 * warp + 4 * (hh & 1)) + 32 * t;
+            const uint32_t base = ring_s + ((cs.it + (hh >> 1)) % DEC_STAGES) * DEC_STAGE_BYTES + n * DB_GSEQ_STRIDE + 128 * (8 * warp + 4 * (hh & 1)) + 32 * t;
             uint32_t r[16];
             bool hbad = false;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               uint4 v = make_uint4(0u, tag, 0u, tag);
-              if (act && i < ks) v = *reinterpret_cast<const uint4*>(base + 128 * (i >> 1) + 16 * (i & 1));  // {payload, tag, payload, tag}
+              if (act && i < ks) v = lds128(base + 128 * (i >> 1) + 16 * (i & 1));  // {payload, tag, payload, tag}
               hbad |= (v.y != tag) | (v.w != tag);
               r[2 * i] = v.x, r[2 * i + 1] = v.z;
             }
             if (norm) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                ss_try += sumsq2(r[q]);
-                const int u = g_unit(hc, warp, t, q);
-                if (act && (q >> 1) < ks && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
+              for (int q = 0; q < 16; ++q) ss_try += sumsq2(r[q]);
+              const int ub = g_unit(hc, warp, 0, 0);  // this trip covers units [ub, ub + 64): own rows of the residual stream among them? (warp-uniform)
+              if (ub < re2 && ub + 64 > rb2) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  const int u = g_unit(hc, warp, t, q);
+                  if (act && (q >> 1) < ks && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
+                }
               }
             }
             // (two tcgen05.st to the same columns are not ordered without a wait: never park words that a retry will replace)
@@ -445,8 +456,12 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         if ((q >> 1) < ks) {
+          // bf16(w * bf16(x * rs)) on both halves of the word: fp32 multiply, ONE packed round (cvt.rn.bf16x2.f32), then a packed bf16
+          // multiply — the product of two bf16 is exact in fp32, so HMUL2.BF16's single rounding is the reference's
           const uint32_t g = ln_s[g_unit(hc, warp, t, q)], v = r[q];
-          r[q] = pack_bf16(bf16_lo(g) * bf16_round(bf16_lo(v) * rs), bf16_hi(g) * bf16_round(bf16_hi(v) * rs));
+          const __nv_bfloat162 y = __floats2bfloat162_rn(bf16_lo(v) * rs, bf16_hi(v) * rs);
+          const __nv_bfloat162 o = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&g), y);
+          r[q] = *reinterpret_cast<const uint32_t*>(&o);
         }
       }
       tmem_st_32x16(tm + 16 * hc, r);
@@ -576,12 +591,12 @@ struct Head4 {
 // One online-softmax step of this warp over its 16 keys of the stage (keys 16 warp .. 16 warp + 15 of the item's 128; K rows at
 // [page][row][128] from byte 0, V rows from byte 32 K). Lane l owns head elements 4 l .. 4 l + 3 of q, K, V and the accumulator.
 __device__ __forceinline__ void att_block(const uint8_t* stage, int warp, int lane, int nvalid, float scale, AttState& s) {
-  const uint8_t* kb = stage + (warp >> 2) * DB_PAGE_BYTES + (warp & 3) * 16 * (DEC_HD * 2) + lane * 8;
-  const uint8_t* vb = kb + 2 * DB_PAGE_BYTES;
+  const uint32_t kb = smem_u32(stage) + (warp >> 2) * DB_PAGE_BYTES + (warp & 3) * 16 * (DEC_HD * 2) + lane * 8;
+  const uint32_t vb = kb + 2 * DB_PAGE_BYTES;
   float pr[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const uint2 kw = *reinterpret_cast<const uint2*>(kb + i * (DEC_HD * 2));
+    const uint2 kw = lds64(kb + i * (DEC_HD * 2));
     pr[i] = fmaf(s.q[3], bf16_hi(kw.y), fmaf(s.q[2], bf16_lo(kw.y), fmaf(s.q[1], bf16_hi(kw.x), s.q[0] * bf16_lo(kw.x))));
   }
   // transposing butterfly: 16 partial dot products per lane -> the complete score of key (lane >> 1) in every lane
@@ -620,7 +635,7 @@ __device__ __forceinline__ void att_block(const uint8_t* stage, int warp, int la
   for (int i = 0; i < 16; ++i) {
     const float pi = __shfl_sync(0xffffffffu, pb, 2 * i);
     if (i < nvalid) {  // rows beyond the valid keys may hold anything
-      const uint2 vw = *reinterpret_cast<const uint2*>(vb + i * (DEC_HD * 2));
+      const uint2 vw = lds64(vb + i * (DEC_HD * 2));
       s.acc[0] = fmaf(pi, bf16_lo(vw.x), s.acc[0]), s.acc[1] = fmaf(pi, bf16_hi(vw.x), s.acc[1]);
       s.acc[2] = fmaf(pi, bf16_lo(vw.y), s.acc[2]), s.acc[3] = fmaf(pi, bf16_hi(vw.y), s.acc[3]);
     }
@@ -832,7 +847,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
   long long* dbg = (PROF && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
   BCons cs{0, 0, 0, 0};
-  long long* gprof = (PROF && dbg) ? dbg + 2 * (BPH_STEPS * L + 1) + 8 + 8 * gridDim.x : nullptr;  // (host zeroes it)
+  long long* gprof = (PROF && dbg) ? dbg + 2 * (BPH_STEPS * L + 1) + 8 + 16 * gridDim.x : nullptr;  // (host zeroes it)
   float best = -INFINITY;  // lm_head: this lane's best logit of ITS sequence (lane & 7)
   int best_i = 0x7fffffff;
 
@@ -849,7 +864,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
     if (PROF && gdbg) gdbg[0] = global_ns();
     if (kind == BPH_Q || kind == BPH_GATEUP || kind == BPH_LMHEAD) {  // residual stream in + RMSNorm
       gather_b(kind == BPH_GATEUP ? xo : xd, sH, H, true, step == 0 ? static_cast<const __nv_bfloat16*>(p.embed) : nullptr, tag, tm, sh, ring, cs, ln_s,
-               p.rms_eps, kind == BPH_GATEUP ? 1u : 0u, rb2, re2, warp, lane, p.sync, 4u * L, gprof);
+               p.rms_eps, kind == BPH_GATEUP ? 1u : 0u, rb2, re2, warp, lane, p.sync, 4u * L, gprof, gdbg ? gdbg + 8 * gridDim.x : nullptr);
       if (kind != BPH_LMHEAD) {
         const __nv_bfloat16* next_w = (kind == BPH_Q)    ? static_cast<const __nv_bfloat16*>(p.ln2) + static_cast<long>(layer) * H
                                       : (layer + 1 < L) ? static_cast<const __nv_bfloat16*>(p.ln1) + static_cast<long>(layer + 1) * H
@@ -858,7 +873,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
       }
     } else if (kind == BPH_O || kind == BPH_DOWN) {  // a plain vector in: the attention output for o_proj, the SwiGLU output for down_proj
       const bool o = (kind == BPH_O);
-      gather_b(o ? attn : hbuf, o ? sH : sI, o ? H : I, false, nullptr, tag, tm, sh, ring, cs, ln_s, 0.f, 0u, rb2, re2, warp, lane, p.sync, 4u * L, gprof);
+      gather_b(o ? attn : hbuf, o ? sH : sI, o ? H : I, false, nullptr, tag, tm, sh, ring, cs, ln_s, 0.f, 0u, rb2, re2, warp, lane, p.sync, 4u * L, gprof, gdbg ? gdbg + 8 * gridDim.x : nullptr);
     }
     if (PROF && dbg) dbg[2 * step + 1] = global_ns();
     if (PROF && gdbg) gdbg[1] = global_ns();
