@@ -20,7 +20,7 @@ constexpr int kNumSMs = 148;  // B200; launchers size their grids from the devic
 // Per-device launch state (ops.cu): SM count of the CURRENT device, and whether the function attributes of kernel family `slot` (dynamic
 // shared-memory opt-in) have been set on it. cudaFuncSetAttribute is per device, so a process driving several GPUs needs it once per GPU.
 constexpr int kMaxDevices = 64;
-enum AttrSlot { ATTR_GEMM128 = 0, ATTR_GEMM256, ATTR_DECODE, ATTR_DECODE_BATCH, ATTR_ATTN_TC, ATTR_MISC, ATTR_SLOTS };
+enum AttrSlot { ATTR_GEMM128 = 0, ATTR_GEMM256, ATTR_GEMM_PAIR, ATTR_DECODE, ATTR_DECODE_BATCH, ATTR_ATTN_TC, ATTR_MISC, ATTR_SLOTS };
 int device_sms(int* device = nullptr);  // < 0 on error (emx_last_error set)
 bool* device_attr_flag(int slot);       // nullptr on error
 
@@ -241,6 +241,58 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA pair (cluster of 2, tcgen05 cta_group::2): the leader (cluster rank 0) issues one MMA for both SMs; each CTA stages its own
+// half of A (128 of the 256 tile rows) and its own half of B (N/2 of the N tile rows) and keeps its own 128 accumulator lanes.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder, uint32_t ncols) {  // one warp of EACH CTA of the pair, same warp id
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 2-D tiled TMA load into THIS CTA's shared memory whose completion bytes are credited to an mbarrier given by its shared::cluster
+// address (the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, rows of 64 bf16 (= one swizzle span):
 //   start>>4 | LBO(ignored for swizzled K-major)=1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout SWIZZLE_128B (2)

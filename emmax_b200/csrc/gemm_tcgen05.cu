@@ -16,6 +16,8 @@
 // overlaps the TMA / MMA main loop of tile i + 1 — the short-K ViT GEMMs (16-18 k-blocks per tile) were epilogue-bound without it.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "emmax.h"
 
@@ -43,9 +45,119 @@ struct EpiParams {
   int flags;
 };
 
+struct EpiCtx {
+  bool has_bias, has_ls, has_res, do_gelu, do_swiglu;
+  __device__ explicit EpiCtx(const EpiParams& ep)
+      : has_bias(ep.bias != nullptr), has_ls(ep.ls != nullptr), has_res(ep.resid != nullptr), do_gelu(ep.flags & EMX_EPI_GELU),
+        do_swiglu(ep.flags & EMX_EPI_SWIGLU) {}
+};
+
+// 32 consecutive bf16 (a slice of bias / LayerScale, or of one residual row) as 4 x 16-byte loads when the slice is whole and
+// 16-byte aligned, element by element at the N tail or for odd leading dimensions. Packed: w[i] = {elem 2i, elem 2i+1}.
+__device__ __forceinline__ void ld32_bf16(const __nv_bfloat16* p, int valid, uint32_t (&w)[16]) {
+  if (valid >= 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 u = reinterpret_cast<const uint4*>(p)[j];
+      w[4 * j + 0] = u.x, w[4 * j + 1] = u.y, w[4 * j + 2] = u.z, w[4 * j + 3] = u.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t lo = 2 * j < valid ? static_cast<uint32_t>(__bfloat16_as_ushort(p[2 * j])) : 0u;
+      const uint32_t hi = 2 * j + 1 < valid ? static_cast<uint32_t>(__bfloat16_as_ushort(p[2 * j + 1])) : 0u;
+      w[j] = lo | (hi << 16);
+    }
+  }
+}
+__device__ __forceinline__ float bf16_of(const uint32_t (&w)[16], int j) { return (j & 1) ? bf16_hi(w[j >> 1]) : bf16_lo(w[j >> 1]); }
+
+// tcgen05.wait::ld that also names the destination registers, so that no use of them can be scheduled in front of the wait
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
+}
+
+// One epilogue warp's share of an accumulator tile: lane i owns output row m (TMEM lane base + i), BN fp32 columns starting at TMEM
+// address `taddr`, output columns n0 .. n0 + BN. Fused chain with the eager rounding points: bf16(acc + bias) -> bf16(GELU) ->
+// bf16(* LayerScale) -> bf16(+ residual) | SwiGLU over interleaved (gate, up) column pairs. The per-column vectors and the residual
+// row are fetched with 16-byte loads issued BEFORE the TMEM wait, so their latency overlaps the tcgen05.ld.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(uint32_t taddr, int m, int n0, int M, int N, __nv_bfloat16* C, int ldc, const EpiParams& ep,
+                                              const EpiCtx& ec) {
+  const bool row_ok = m < M;
+  const long rrow = ec.has_res ? static_cast<long>(ep.resid_mod > 0 ? m % ep.resid_mod : m) * ep.ldr : 0;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int nb = n0 + c * 32;
+    if (nb >= N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c * 32, r);
+    const int valid = N - nb;  // >= 32: whole chunk
+    uint32_t wb[16], wl[16], wr[16];
+    if (ec.has_bias) ld32_bf16(ep.bias + nb, valid, wb);
+    if (ec.has_ls) ld32_bf16(ep.ls + nb, valid, wl);
+    if (ec.has_res && row_ok) ld32_bf16(ep.resid + rrow + nb, valid, wr);
+    tmem_ld_wait_on(r);
+    if (!row_ok) continue;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (ec.has_bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += bf16_of(wb, j);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);  // Linear output (bias fused before rounding, as cuBLASLt)
+    if (ec.do_gelu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = bf16_round(gelu_erf(v[j]));
+    }
+    if (ec.has_ls) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j] * bf16_of(wl, j));
+    }
+    if (ec.has_res) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j] + bf16_of(wr, j));
+    }
+    if (ec.do_swiglu) {
+      // interleaved (gate, up) columns -> one output column per pair: bf16(bf16(silu(g)) * u)
+      __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + nb / 2;
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = pack_bf16(bf16_round(silu(v[4 * j])) * v[4 * j + 1], bf16_round(silu(v[4 * j + 2])) * v[4 * j + 3]);
+      if (valid >= 32 && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
+        reinterpret_cast<uint4*>(crow)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<uint4*>(crow)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (2 * j + 1 < valid) crow[j] = __ushort_as_bfloat16(static_cast<unsigned short>((j & 1) ? (o[j >> 1] >> 16) : (o[j >> 1] & 0xffffu)));
+      }
+    } else {
+      __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + nb;
+      if (valid >= 32 && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          reinterpret_cast<uint4*>(crow)[j] = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < valid) crow[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* __restrict__ C,
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C,
                int ldc, int M, int N, int K, EpiParams ep) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -127,77 +239,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp - 4;  // TMEM lane quarter this warp may read
-    const bool has_bias = ep.bias != nullptr, has_ls = ep.ls != nullptr, has_res = ep.resid != nullptr;
-    const bool do_gelu = ep.flags & EMX_EPI_GELU, do_swiglu = ep.flags & EMX_EPI_SWIGLU;
+    const EpiCtx ec(ep);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-    const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
-    const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
-    mbar_wait(&tmem_full[buf], bph);
-    tc_fence_after();
-    const int m = m0 + q * 32 + lane;
-    const long rrow = has_res ? static_cast<long>(ep.resid_mod > 0 ? m % ep.resid_mod : m) * ep.ldr : 0;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 32, r);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (m >= M || nb >= N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const bool fullchunk = nb + 32 <= N;
-      if (has_bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (fullchunk || nb + j < N) v[j] += ld_bf16(ep.bias + nb + j);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);  // Linear output (bias fused before rounding, as cuBLASLt)
-      if (do_gelu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = bf16_round(gelu_erf(v[j]));
-      }
-      if (has_ls) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (fullchunk || nb + j < N) v[j] = bf16_round(v[j] * ld_bf16(ep.ls + nb + j));
-      }
-      if (has_res) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (fullchunk || nb + j < N) v[j] = bf16_round(v[j] + ld_bf16(ep.resid + rrow + nb + j));
-      }
-      if (do_swiglu) {
-        // interleaved (gate, up) columns -> one output column per pair: bf16(bf16(silu(g)) * u)
-        __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + nb / 2;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (fullchunk || nb + 2 * j + 1 < N) crow[j] = __float2bfloat16_rn(bf16_round(silu(v[2 * j])) * v[2 * j + 1]);
-      } else {
-        __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + nb;
-        if (fullchunk && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-            o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-            o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            reinterpret_cast<uint4*>(crow)[j] = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < N) crow[j] = __float2bfloat16_rn(v[j]);
-        }
-      }
-    }
-    // this warp's quarter of the accumulator buffer is read out: hand it back to the MMA warp
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+      const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+      mbar_wait(&tmem_full[buf], bph);
+      tc_fence_after();
+      epilogue_rows<BN>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN, m0 + q * 32 + lane, n0, M, N, C, ldc, ep, ec);
+      // this warp's quarter of the accumulator buffer is read out: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
   }
   tc_fence_before();
@@ -205,6 +258,131 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant for the large-M problems (bs = 32 prefill probe, batched ViT): cluster of 2 CTAs = one TPC, tcgen05 cta_group::2,
+// output tile 256 x 256 per pair. Why: with cta_group::1 every SM pulls a 128-row A slab AND a 256-row W slab per k-block (48 KB per
+// 128x256x64 MMA block = 96 B/clk/SM at full tensor rate), 2.3 x what the L2 -> SM fabric delivers chip-wide (~6300 B/clk / 148 SMs,
+// B300_MICROARCH.md "LTS throughput cap"): the single-CTA kernel is L2-bound at ~45 % of the tensor peak. In a pair each SM stages
+// only its own half of both operands (16 KB + 16 KB per k-block) and the tensor cores read the other half from the peer's shared
+// memory: 64 B/clk/SM, and 6 ring stages instead of 4 in the same shared memory.
+//   rank r of the pair: A rows m0 + 128 r .. +128, W rows n0 + 128 r .. +128, accumulator lanes = its 128 output rows x 256 columns,
+//   double-buffered (2 x 256 TMEM columns). Barriers: full[s] lives in the LEADER (both CTAs' TMA bytes are credited to it), empty[s]
+//   and tmem_full[b] are multicast commits to both CTAs, tmem_empty[b] is the leader's and counts the 8 epilogue warps of the pair.
+// ---------------------------------------------------------------------------------------------------------------
+struct PairCfg {
+  static constexpr int BN = 256;
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = BM * BK * 2;        // this CTA's 128 A rows
+  static constexpr int kBBytes = (BN / 2) * BK * 2;  // this CTA's 128 W rows
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C, int ldc, int M,
+                    int N, int K, EpiParams ep) {
+  using Cfg = PairCfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tmem_full = empty + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int nkb = (K + BK - 1) / BK;
+  const int mt = (M + 2 * BM - 1) / (2 * BM), n_tiles = mt * ((N + BN - 1) / BN);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);   // used in the leader only: its producer's arrive.expect_tx for the bytes of BOTH CTAs
+      mbar_init(&empty[s], 1);  // multicast commit of the leader's MMA warp
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);   // multicast commit
+      mbar_init(&tmem_empty[b], 8);  // leader only: 4 epilogue warps of each CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_holder, 2 * BN);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / remote TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        const int m0 = (tile % mt) * (2 * BM) + rank * BM, n0 = (tile / mt) * BN + rank * (BN / 2);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);  // own slot free (the commit is multicast)
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          const uint32_t leader_full = mapa_u32(smem_u32(&full[s]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
+          tma_load_2d_pair(sa, &tmA, kb * BK, m0, leader_full);
+          tma_load_2d_pair(sa + Cfg::kABytes, &tmB, kb * BK, n0, leader_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      uint32_t it = 0, tl = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tl) {
+        const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+        mbar_wait(&tmem_empty[buf], bph ^ 1);  // both CTAs have read this accumulator buffer out
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_pair(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty[s]);
+        }
+        umma_commit_pair(&tmem_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const EpiCtx ec(ep);
+    uint32_t tl = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tl) {
+      const int m0 = (tile % mt) * (2 * BM) + rank * BM, n0 = (tile / mt) * BN;
+      const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+      mbar_wait(&tmem_full[buf], bph);
+      tc_fence_after();
+      epilogue_rows<BN>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN, m0 + q * 32 + lane, n0, M, N, C, ldc, ep, ec);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may leave (shared memory, barriers, TMEM) while the other still depends on it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 2 * BN);
   }
 }
 
@@ -259,6 +437,22 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat
   return 0;
 }
 
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat16* C, int ldc, int M, int N, int K, const EpiParams& ep,
+                            cudaStream_t stream) {
+  bool* attr_set = device_attr_flag(ATTR_GEMM_PAIR);
+  const int sms = device_sms();
+  if (!attr_set || sms < 0) return -2;
+  if (!*attr_set) {
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+    *attr_set = true;
+  }
+  const int n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + PairCfg::BN - 1) / PairCfg::BN);
+  const int pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
+  gemm_tn_pair_kernel<<<2 * pairs, 256, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
+  EMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace emx
 
 extern "C" int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const void* bias,
@@ -275,6 +469,15 @@ extern "C" int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, voi
   const int sms = device_sms();
   if (sms < 0) return -2;
   const bool wide = (static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256) >= 2 * sms);
+  // CTA pairs (256 x 256 tiles) once M is large and there is at least one full round of pair tiles
+  const char* pe = getenv("EMX_GEMM_PAIR");  // A/B switch for tools/gemm_probe.py: 0 = never, 2 = whenever M > 128
+  const int pair_mode = pe ? pe[0] - '0' : 1;
+  const long pair_tiles = static_cast<long>((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+  if ((pair_mode == 1 && pair_tiles >= sms / 2 && M >= 4 * BM) || (pair_mode == 2 && M > BM)) {
+    if (int r = make_tmap(&ta, A, M, K, lda, BM)) return r;
+    if (int r = make_tmap(&tb, W, N, K, ldw, PairCfg::BN / 2)) return r;
+    return launch_gemm_pair(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, stream);
+  }
   if (int r = make_tmap(&ta, A, M, K, lda, BM)) return r;
   if (int r = make_tmap(&tb, W, N, K, ldw, wide ? 256 : 128)) return r;
   return wide ? launch_gemm<256>(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, stream)

@@ -54,6 +54,36 @@ def test_gemm_plain(lib, M, N, K):
     assert_close_bf16(out, want, name=f"gemm {M}x{N}x{K}")
 
 
+PAIR_SHAPES = [(777, 1000, 136), (1024, 768, 64), (300, 520, 4096), (2368, 4096, 1024), (8352, 1024, 1024), (129, 256, 72)]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_gemm_cta_pair(lib, M, N, K, monkeypatch):
+    """The cta_group::2 kernel (256 x 256 tiles per CTA pair), forced for every M > 128: M / N / K tails, odd tile counts, and
+    every fused epilogue, against the same torch restatement as the single-CTA kernel."""
+    from emmax_b200._lib import EPI_GELU, EPI_SWIGLU
+    from emmax_b200.engine import Engine
+
+    monkeypatch.setenv("EMX_GEMM_PAIR", "2")
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    acc = a.float() @ w.float().T
+    out = torch.zeros(M, N, dtype=BF, device="cuda")
+    Engine.gemm(a, w, out)
+    assert_close_bf16(out, acc.to(BF), name=f"pair gemm {M}x{N}x{K}")
+    bias, ls, res = rnd(N, seed=5), rnd(N, seed=6).abs(), rnd(M, N, seed=7)
+    Engine.gemm(a, w, out, bias=bias, flags=EPI_GELU)
+    assert_close_bf16(out, torch.nn.functional.gelu((acc + bias.float()).to(BF)), name="pair bias+gelu")
+    buf = res.clone()
+    Engine.gemm(a, w, buf, bias=bias, ls=ls, resid=buf)
+    want = ((acc + bias.float()).to(BF) * ls).to(BF) + res
+    assert_close_bf16(buf, want, name="pair bias+ls+resid", scale=want.abs() + acc.abs() + res.abs().float() + 1)
+    out2 = torch.zeros(M, N // 2, dtype=BF, device="cuda")
+    Engine.gemm(a, w, out2, flags=EPI_SWIGLU)
+    gu = acc.to(BF)
+    assert_close_bf16(out2, torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2], name="pair swiglu")
+    torch.cuda.synchronize()
+
+
 def test_gemm_epilogues(lib):
     from emmax_b200._lib import EPI_GELU, EPI_SWIGLU
     from emmax_b200.engine import Engine
