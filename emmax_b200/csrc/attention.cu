@@ -288,6 +288,237 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_mma_kernel(const __nv_bf
   }
 }
 
+// ---- v3: tcgen05 tensor cores, scores resident in tensor memory -----------------------------------------------------------------
+// One CTA per (128-query tile, head, batch item). The sequences of this path are short (ViT 256 / 261 tokens, prefill 256 + prompt),
+// so a query tile's WHOLE score row fits in tensor memory next to the output accumulator (<= 384 fp32 score columns + <= 128 output
+// columns of the 512): no online softmax, no accumulator rescaling.
+//   control warp (warp 4): TMA loads (4-D tensor map over the packed qkv buffer {head_dim, 3*heads, T, B}: rows beyond T and columns
+//     beyond head_dim are OUT OF BOUNDS and arrive as zeros, which is what pads head_dim 72 to 80 and the key count to a multiple of
+//     64), then S = Q K^T as tcgen05.mma M=128 x N<=256 x K=16 steps (Q and K both K-major, 128-byte swizzle), later O = P V with P as
+//     the K-major A operand and V — stored [key][head_dim], i.e. N-contiguous — as an MN-major B operand.
+//   warps 0..3: thread i owns query row i (TMEM lane i): pass 1 reads the score row (tcgen05.ld) for the row maximum, pass 2 forms
+//     p = exp2((s - max) * scale * log2 e) in fp32, sums it in fp32, rounds p to bf16 (as flash-attn) and writes it into shared memory
+//     in the swizzled K-major layout the tensor core reads (the K tile is dead by then: P overwrites it); after the PV commit the
+//     same thread scales its output row by 1 / sum and stores it.
+// V arrives while the scores are computed and soft-maxed. Keys > query (causal) or >= T get p = 0 exactly.
+constexpr int ATC_QT = 128;        // queries per CTA = TMEM lanes
+constexpr int ATC_MAX_KEYS = 384;  // score columns that fit next to the output accumulator
+constexpr int ATC_O_COL = 384;     // TMEM column of the output accumulator
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// MN-major operand (the N index is contiguous in shared memory), 128-byte swizzle: 64-element N blocks `lbo` bytes apart,
+// groups of 8 K rows (128 B each) 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(160, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int T, int heads, int causal, float scale) {
+  constexpr int HDP = (HD + 15) / 16 * 16;  // contraction length of Q K^T and N of P V (72 -> 80)
+  constexpr int SLABS = (HD + 63) / 64;     // 64-column (128-byte) slabs of a q / k / v row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int keys_pad = (T + 63) / 64 * 64;                        // rows of the K / V tiles in shared memory
+  const int kp_bytes = max(SLABS, 2) * keys_pad * 128;            // K tile, later P (keys_pad / 64 slabs of 128 rows x 128 B)
+  uint8_t* sQ = smem;                                             // [SLABS][128 rows][128 B]
+  uint8_t* sK = sQ + SLABS * ATC_QT * 128;                        // [SLABS][keys_pad rows][128 B]
+  uint8_t* sV = sK + kp_bytes;                                    // [SLABS][keys_pad rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + SLABS * keys_pad * 128);
+  uint64_t *bar_qk = bars, *bar_v = bars + 1, *bar_s = bars + 2, *bar_p = bars + 3, *bar_o = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATC_QT, head = blockIdx.y, b = blockIdx.z;
+  const int Hd = heads * HD;
+  const int keys_need = causal ? min(q0 + ATC_QT, T) : T;   // keys any query of this tile attends to
+  const int keys_used = (keys_need + 15) / 16 * 16;         // score columns computed (multiple of the MMA N / K granule)
+  const int key_boxes = (keys_need + 63) / 64;              // 64-row TMA boxes of K and of V
+
+  if (warp == 4) {
+    if (lane == 0) {
+      prefetch_tmap(&tm);
+      mbar_init(bar_qk, 1), mbar_init(bar_v, 1), mbar_init(bar_s, 1), mbar_init(bar_p, ATC_QT), mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- loads: Q and K first (one barrier), V behind them
+      mbar_arrive_expect_tx(bar_qk, static_cast<uint32_t>(SLABS * (2 + key_boxes) * 64 * 128));
+      for (int s = 0; s < SLABS; ++s) {
+        for (int r = 0; r < 2; ++r) tma_load_4d(sQ + (s * ATC_QT + r * 64) * 128, &tm, s * 64, head, q0 + r * 64, b, bar_qk);
+        for (int r = 0; r < key_boxes; ++r) tma_load_4d(sK + (s * keys_pad + r * 64) * 128, &tm, s * 64, heads + head, r * 64, b, bar_qk);
+      }
+      mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(SLABS * key_boxes * 64 * 128));
+      for (int s = 0; s < SLABS; ++s)
+        for (int r = 0; r < key_boxes; ++r) tma_load_4d(sV + (s * keys_pad + r * 64) * 128, &tm, s * 64, 2 * heads + head, r * 64, b, bar_v);
+
+      // ---- S = Q K^T
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      for (int n0 = 0; n0 < keys_used; n0 += 256) {
+        const int nn = min(256, keys_used - n0);
+        const uint32_t idesc = umma_idesc_bf16(ATC_QT, nn);
+#pragma unroll
+        for (int k = 0; k < HDP / 16; ++k) {
+          const uint32_t qa = smem_u32(sQ) + (k >> 2) * (ATC_QT * 128) + (k & 3) * 32;
+          const uint32_t ka = smem_u32(sK) + (k >> 2) * (keys_pad * 128) + n0 * 128 + (k & 3) * 32;
+          umma_bf16(tmem_base + n0, umma_desc_k128(qa), umma_desc_k128(ka), idesc, k != 0);
+        }
+      }
+      umma_commit(bar_s);
+
+      // ---- O = P V once the softmax warps have written P (over the K tile) and V has landed
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t idesc_pv = umma_idesc_bf16(ATC_QT, HDP) | (1u << 16);  // B operand MN-major
+      for (int k = 0; k < keys_used / 16; ++k) {
+        const uint32_t pa = smem_u32(sK) + (k >> 2) * (ATC_QT * 128) + (k & 3) * 32;
+        const uint32_t va = smem_u32(sV) + k * 2048;
+        umma_bf16(tmem_base + ATC_O_COL, umma_desc_k128(pa), umma_desc_mn128(va, keys_pad * 128), idesc_pv, k != 0);
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    const int row = warp * 32 + lane, q = q0 + row;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int n_valid = causal ? min(q + 1, T) : T;  // keys [0, n_valid) count for this query
+    const float sl2 = scale * 1.4426950408889634f;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    // pass 1: row maximum of the raw scores
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < keys_used; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < n_valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    const float m2 = mx * sl2;
+    // pass 2: p = exp2(s * sl2 - m2), fp32 row sum, bf16 P into the swizzled K-major A tile (slab = 64 keys, row pitch 128 B)
+    float l = 0.f;
+    for (int c0 = 0; c0 < keys_used; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + c0, r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float p0 = (c0 + 2 * j < n_valid) ? fast_exp2(fmaf(__uint_as_float(r[2 * j]), sl2, -m2)) : 0.f;
+        const float p1 = (c0 + 2 * j + 1 < n_valid) ? fast_exp2(fmaf(__uint_as_float(r[2 * j + 1]), sl2, -m2)) : 0.f;
+        l += p0 + p1;
+        pk[j] = pack_bf16(p0, p1);
+      }
+      uint8_t* prow = sK + (c0 >> 6) * (ATC_QT * 128) + row * 128;
+      const int ch0 = (c0 & 63) >> 3;  // first 16-byte chunk of this 32-key group inside the 64-key slab row: 0 or 4
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(prow + (((ch0 + ch) ^ (row & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+    }
+    fence_proxy_async();  // generic-proxy stores of P -> visible to the tensor core's async-proxy reads
+    tc_fence_before();
+    mbar_arrive(bar_p);
+    // epilogue: O row / l
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = out + (static_cast<long>(b) * T + q) * Hd + head * HD;
+#pragma unroll
+    for (int c0 = 0; c0 < HDP; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + ATC_O_COL + c0, r);
+      tmem_ld_wait();
+      if (q < T) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + 8 * j < HD)
+            *reinterpret_cast<uint4*>(orow + c0 + 8 * j) =
+                make_uint4(pack_bf16(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv),
+                           pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv),
+                           pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv),
+                           pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int HD>
+static int launch_attn_tc(const __nv_bfloat16* in, __nv_bfloat16* o, int B, int T, int heads, int causal, float scale, cudaStream_t s) {
+  static PFN_encodeTiledA enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<PFN_encodeTiledA>(p);
+  }
+  EMX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t Hd = static_cast<cuuint64_t>(heads) * HD;
+  CUtensorMap tm;
+  cuuint64_t dims[4] = {HD, static_cast<cuuint64_t>(3 * heads), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {HD * 2ull, 3 * Hd * 2, static_cast<cuuint64_t>(T) * 3 * Hd * 2};
+  cuuint32_t box[4] = {64, 1, 64, 1}, estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EMX_REQUIRE(r == CUDA_SUCCESS, "emx_attn_fwd: cuTensorMapEncodeTiled failed (%d): B=%d T=%d heads=%d hd=%d", (int)r, B, T, heads, HD);
+  constexpr int SLABS = (HD + 63) / 64;
+  const int keys_pad = (T + 63) / 64 * 64;
+  const int smem = SLABS * ATC_QT * 128 + (SLABS > 2 ? SLABS : 2) * keys_pad * 128 + SLABS * keys_pad * 128 + 64 + 1024;
+  bool* attr_set = device_attr_flag(ATTR_ATTN_TC);
+  if (!attr_set) return -2;
+  // the opt-in is per kernel instantiation as well as per device: 3 head dims share the slot through a bit mask
+  static_assert(sizeof(bool) == 1, "");
+  static unsigned char done[kMaxDevices] = {};
+  int dev = 0;
+  EMX_CHECK_CUDA(cudaGetDevice(&dev));
+  const unsigned char bit = HD == 64 ? 1 : HD == 72 ? 2 : 4;
+  if (dev < kMaxDevices && !(done[dev] & bit)) {
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done[dev] |= bit;
+  }
+  attn_fwd_tc_kernel<HD><<<dim3((T + ATC_QT - 1) / ATC_QT, heads, B), 160, smem, s>>>(tm, o, T, heads, causal, scale);
+  return 0;
+}
+
 template <int HD>
 static int launch_attn_mma(const __nv_bfloat16* in, __nv_bfloat16* o, int B, int T, int heads, int causal, float scale, cudaStream_t s) {
   // 64-query CTAs when that still gives every SM two CTAs, else 32-query CTAs (bs = 1: 16-32 heads x 5 query blocks)
@@ -311,6 +542,21 @@ extern "C" int emx_attn_fwd(const void* qkv, void* out, int B, int T, int heads,
   const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   static const bool simt = getenv("EMX_ATTN_SIMT") != nullptr;  // v1 (fp32 SIMT) kept as an A/B reference for the probes
+  const char* tce = getenv("EMX_ATTN_TC");                      // A/B switch: 0 = mma.sync v2 for every shape
+  const bool tc = !(tce && tce[0] == '0') && T <= ATC_MAX_KEYS && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (!simt && tc) {
+    int r = 0;
+    switch (head_dim) {
+      case 64: r = launch_attn_tc<64>(in, o, B, T, heads, causal, scale, s); break;
+      case 72: r = launch_attn_tc<72>(in, o, B, T, heads, causal, scale, s); break;
+      case 128: r = launch_attn_tc<128>(in, o, B, T, heads, causal, scale, s); break;
+      default: EMX_REQUIRE(false, "emx_attn_fwd: head_dim %d not supported (64, 72, 128)", head_dim);
+    }
+    if (r) return r;
+    EMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (!simt) {
     switch (head_dim) {
       case 64: launch_attn_mma<64>(in, o, B, T, heads, causal, scale, s); break;

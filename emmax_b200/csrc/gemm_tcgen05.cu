@@ -15,7 +15,9 @@
 // accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so the epilogue of tile i (TMEM read-out, fused math, global stores)
 // overlaps the TMA / MMA main loop of tile i + 1 — the short-K ViT GEMMs (16-18 k-blocks per tile) were epilogue-bound without it.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = epilogue (warp w reads
+// TMEM lane quarter w mod 4; warps 4..7 take the left half of the tile's columns, 8..11 the right half: the GELU (erff) epilogue of the
+// short-K ViT / projector tiles is longer than their main loop with four warps).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -26,6 +28,8 @@ namespace emx {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;                     // two per TMEM lane quarter, each covering half of the tile's columns
+constexpr int kGemmThreads = (4 + kEpiWarps) * 32;  // warps 0..3: TMA producer, MMA issuer, TMEM allocator, idle
 
 template <int BN>
 struct GemmCfg {
@@ -156,7 +160,7 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int m, int n0, int
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C,
                int ldc, int M, int N, int K, EpiParams ep) {
   using Cfg = GemmCfg<BN>;
@@ -183,7 +187,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[b], kEpiWarps);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -238,15 +242,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int q = warp - 4;  // TMEM lane quarter this warp may read
+    const int q = warp & 3, ch = (warp - 4) >> 2;  // TMEM lane quarter this warp may read (warp id mod 4); column half it covers
     const EpiCtx ec(ep);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-      const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+      const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN + ch * (BN / 2);
       const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
       mbar_wait(&tmem_full[buf], bph);
       tc_fence_after();
-      epilogue_rows<BN>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN, m0 + q * 32 + lane, n0, M, N, C, ldc, ep, ec);
+      epilogue_rows<BN / 2>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
+                            ep, ec);
       // this warp's quarter of the accumulator buffer is read out: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -281,7 +286,7 @@ struct PairCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C, int ldc, int M,
                     int N, int K, EpiParams ep) {
   using Cfg = PairCfg;
@@ -311,7 +316,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);   // multicast commit
-      mbar_init(&tmem_empty[b], 8);  // leader only: 4 epilogue warps of each CTA
+      mbar_init(&tmem_empty[b], 2 * kEpiWarps);  // leader only: the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
@@ -364,15 +369,16 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int q = warp - 4;
+    const int q = warp & 3, ch = (warp - 4) >> 2;
     const EpiCtx ec(ep);
     uint32_t tl = 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tl) {
-      const int m0 = (tile % mt) * (2 * BM) + rank * BM, n0 = (tile / mt) * BN;
+      const int m0 = (tile % mt) * (2 * BM) + rank * BM, n0 = (tile / mt) * BN + ch * (BN / 2);
       const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
       mbar_wait(&tmem_full[buf], bph);
       tc_fence_after();
-      epilogue_rows<BN>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN, m0 + q * 32 + lane, n0, M, N, C, ldc, ep, ec);
+      epilogue_rows<BN / 2>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
+                            ep, ec);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
@@ -432,7 +438,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat
     *attr_set = true;
   }
   const int n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  gemm_tn_kernel<BN><<<n_tiles < sms ? n_tiles : sms, 256, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
+  gemm_tn_kernel<BN><<<n_tiles < sms ? n_tiles : sms, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -448,7 +454,7 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, __nv_b
   }
   const int n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + PairCfg::BN - 1) / PairCfg::BN);
   const int pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
-  gemm_tn_pair_kernel<<<2 * pairs, 256, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
+  gemm_tn_pair_kernel<<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -183,6 +183,39 @@ __global__ void rope_kvstore_kernel(__nv_bfloat16* __restrict__ qkv, int T, int 
   __nv_bfloat16* k = q + Hd;
   const __nv_bfloat16* v = q + 2 * Hd;
   const int page = block_table[b * max_pages + pos / page_size], slot = pos % page_size;
+  if ((half & 7) == 0) {
+    // 8 rotation pairs per thread: 16-byte loads / stores of both halves of q and k, of the bf16 cos / sin rows and of v
+    const int hv = half >> 3;
+    for (int i = threadIdx.x; i < heads * hv; i += blockDim.x) {
+      const int h = i / hv, j = (i % hv) << 3;
+      const uint4 cv = *reinterpret_cast<const uint4*>(cos_tab + static_cast<long>(pos) * half + j);
+      const uint4 sv = *reinterpret_cast<const uint4*>(sin_tab + static_cast<long>(pos) * half + j);
+      const int a = h * hd + j, bidx = a + half;
+      const long dst = ((static_cast<long>(page) * heads + h) * page_size + slot) * hd + j;
+      const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw[4] = {sv.x, sv.y, sv.z, sv.w};
+      auto rotate = [&](const uint4 lo, const uint4 hi, uint4& olo, uint4& ohi) {
+        const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w}, u[4] = {hi.x, hi.y, hi.z, hi.w};
+        uint32_t ol[4], ou[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float c0 = bf16_lo(cw[e]), c1 = bf16_hi(cw[e]), s0 = bf16_lo(sw[e]), s1 = bf16_hi(sw[e]);
+          const float x10 = bf16_lo(l[e]), x11 = bf16_hi(l[e]), x20 = bf16_lo(u[e]), x21 = bf16_hi(u[e]);
+          ol[e] = pack_bf16(bf16_round(x10 * c0) + bf16_round(-x20 * s0), bf16_round(x11 * c1) + bf16_round(-x21 * s1));
+          ou[e] = pack_bf16(bf16_round(x20 * c0) + bf16_round(x10 * s0), bf16_round(x21 * c1) + bf16_round(x11 * s1));
+        }
+        olo = make_uint4(ol[0], ol[1], ol[2], ol[3]), ohi = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+      };
+      uint4 r1, r2;
+      rotate(*reinterpret_cast<const uint4*>(q + a), *reinterpret_cast<const uint4*>(q + bidx), r1, r2);
+      *reinterpret_cast<uint4*>(q + a) = r1, *reinterpret_cast<uint4*>(q + bidx) = r2;
+      rotate(*reinterpret_cast<const uint4*>(k + a), *reinterpret_cast<const uint4*>(k + bidx), r1, r2);
+      *reinterpret_cast<uint4*>(k + a) = r1, *reinterpret_cast<uint4*>(k + bidx) = r2;
+      *reinterpret_cast<uint4*>(k_cache + dst) = r1, *reinterpret_cast<uint4*>(k_cache + dst + half) = r2;
+      *reinterpret_cast<uint4*>(v_cache + dst) = *reinterpret_cast<const uint4*>(v + a);
+      *reinterpret_cast<uint4*>(v_cache + dst + half) = *reinterpret_cast<const uint4*>(v + bidx);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < heads * half; i += blockDim.x) {
     const int h = i / half, j = i % half;
     const float c = ld_bf16(cos_tab + static_cast<long>(pos) * half + j), s = ld_bf16(sin_tab + static_cast<long>(pos) * half + j);

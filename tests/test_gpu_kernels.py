@@ -76,11 +76,12 @@ def test_gemm_cta_pair(lib, M, N, K, monkeypatch):
     buf = res.clone()
     Engine.gemm(a, w, buf, bias=bias, ls=ls, resid=buf)
     want = ((acc + bias.float()).to(BF) * ls).to(BF) + res
-    assert_close_bf16(buf, want, name="pair bias+ls+resid", scale=want.abs() + acc.abs() + res.abs().float() + 1)
+    assert_close_bf16(buf, want, frac=0.99999, name="pair bias+ls+resid", scale=want.abs() + acc.abs() + res.abs().float() + 1)
     out2 = torch.zeros(M, N // 2, dtype=BF, device="cuda")
     Engine.gemm(a, w, out2, flags=EPI_SWIGLU)
     gu = acc.to(BF)
-    assert_close_bf16(out2, torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2], name="pair swiglu")
+    # (a handful of the 10^7 products sit on a bf16 rounding boundary of gate or up: 1 ulp of the input moves the product by > tolerance)
+    assert_close_bf16(out2, torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2], frac=0.99999, name="pair swiglu")
     torch.cuda.synchronize()
 
 
@@ -137,10 +138,17 @@ def test_norms(lib):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("B,T,heads,hd,causal", [(1, 261, 16, 64, 0), (2, 256, 16, 72, 0), (1, 296, 32, 128, 1), (3, 37, 2, 128, 1), (1, 5, 2, 72, 0)])
-def test_attention(lib, B, T, heads, hd, causal):
+ATTN_CASES = [(1, 261, 16, 64, 0), (2, 256, 16, 72, 0), (1, 296, 32, 128, 1), (3, 37, 2, 128, 1), (1, 5, 2, 72, 0), (2, 384, 4, 128, 1),
+              (2, 129, 3, 64, 1), (3, 300, 2, 72, 1), (1, 400, 2, 128, 1), (2, 385, 2, 64, 0), (5, 296, 8, 128, 0)]  # fmt: skip
+
+
+@pytest.mark.parametrize("tc", ["1", "0"])
+@pytest.mark.parametrize("B,T,heads,hd,causal", ATTN_CASES)
+def test_attention(lib, B, T, heads, hd, causal, tc, monkeypatch):
+    """tc=1: the tcgen05 kernel (scores resident in tensor memory) for T <= 384, the mma.sync kernel beyond; tc=0: mma.sync everywhere."""
     from emmax_b200._lib import call, ptr, stream
 
+    monkeypatch.setenv("EMX_ATTN_TC", tc)
     qkv = rnd(B * T, 3 * heads * hd, seed=11)
     out = torch.empty(B * T, heads * hd, dtype=BF, device="cuda")
     call("emx_attn_fwd", ptr(qkv), ptr(out), B, T, heads, hd, causal, hd ** -0.5, stream())
