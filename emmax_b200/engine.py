@@ -170,10 +170,19 @@ class Engine:
         call("emx_gemm_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias), ptr(ls),
              ptr(resid), resid.stride(0) if resid is not None else 0, resid_mod, flags, stream())  # fmt: skip
 
+    MAX_CACHED_SHAPES = 8  # distinct (batch, prompt length) workspaces + prefill graphs kept; a new shape costs one eager prefill + a capture
+
     def _workspace(self, B: int, n_ids: int) -> dict:
         key = (B, n_ids)
         if key in self._ws:
+            self._ws[key] = self._ws.pop(key)  # most recently used last
             return self._ws[key]
+        while len(self._ws) >= self.MAX_CACHED_SHAPES:
+            # least recently used prompt shape: drop its workspace (~45 MB at S = 300 per batch item) and the graphs captured over it
+            old = next(iter(self._ws))
+            del self._ws[old]
+            for gk in [gk for gk in self._graphs if gk[:2] == old]:
+                del self._graphs[gk]
         dev, t, cfg = self.device, self.t, self.config
         P = cfg.num_patches
         S = n_ids + P

@@ -427,3 +427,18 @@ def test_robot_loop_entry_points_on_the_engine(tiny):
         acts, text = R.get_seq_action(model, proc, "emma-x", obs, "put carrot in pot", None, type="act", center_crop=crop)
         acts2, text2 = model.generate_actions(img, "In: put carrot in pot\nOut:", "act", max_new_tokens=512, do_sample=False)
         assert text == text2 and len(acts) == len(acts2) and all(np.array_equal(x, y) for x, y in zip(acts, acts2))
+
+
+def test_prompt_shape_cache_is_bounded(tiny):
+    """A robot loop with varied instructions must not grow device memory without bound: workspaces + prefill graphs are kept for the
+    MAX_CACHED_SHAPES most recently used (batch, prompt length) pairs, and a shape that was evicted is simply rebuilt (same first token)."""
+    model, _, g, input_ids, _ = tiny
+    eng = model.engine
+    pv = torch.from_numpy(g["pixel_values"]).to("cuda", BF)
+    first = int(eng.prefill(input_ids.cuda(), pv)["first"][0])
+    for extra in range(1, eng.MAX_CACHED_SHAPES + 4):
+        ids = torch.cat([input_ids, input_ids[:, -1:].repeat(1, extra)], dim=1).cuda()
+        eng.prefill(ids, pv)
+        assert len(eng._ws) <= eng.MAX_CACHED_SHAPES and len(eng._graphs) <= eng.MAX_CACHED_SHAPES
+    assert (1, input_ids.shape[1]) not in eng._ws, "the first shape should have been evicted by now"
+    assert int(eng.prefill(input_ids.cuda(), pv)["first"][0]) == first
