@@ -11,7 +11,7 @@
 // bias / GELU / LayerScale / residual / SwiGLU chain with the SAME bf16 rounding points as the unfused torch-eager
 // reference (each reference op output is bf16).
 //
-// Persistent: one CTA per SM walks the output tiles (M index fastest, so neighbouring CTAs share the W tile in L2); the fp32
+// Persistent: one CTA per SM walks the output tiles (grouped order, see tile_coords: neighbouring CTAs share W and A blocks in L2); the fp32
 // accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so the epilogue of tile i (TMEM read-out, fused math, global stores)
 // overlaps the TMA / MMA main loop of tile i + 1 — the short-K ViT GEMMs (16-18 k-blocks per tile) were epilogue-bound without it.
 //
@@ -39,6 +39,19 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// Tile order: groups of kGroupM consecutive M tiles; inside a group the M index runs fastest, then N. The CTAs that run concurrently
+// (one wave = 148 tiles or 74 pair tiles) then share ~8 A row blocks and ~9-18 W row blocks (a few tens of MB: L2-resident) instead of
+// ALL of A (77 MB at M = 9472, K = 4096) against two W blocks, which re-streamed A from HBM once per pair of N tiles.
+constexpr int kGroupM = 8;
+__device__ __forceinline__ void tile_coords(int tile, int mt, int nt, int& mi, int& ni) {
+  const int per_group = kGroupM * nt;
+  const int g = tile / per_group, r = tile - g * per_group;
+  const int m_first = g * kGroupM;
+  const int gm = min(kGroupM, mt - m_first);
+  ni = r / gm;
+  mi = m_first + (r - ni * gm);
+}
 
 struct EpiParams {
   const __nv_bfloat16* bias;   // [N] or null
@@ -85,81 +98,123 @@ __device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&r)[32]) {
                  "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
 }
 
-// One epilogue warp's share of an accumulator tile: lane i owns output row m (TMEM lane base + i), BN fp32 columns starting at TMEM
-// address `taddr`, output columns n0 .. n0 + BN. Fused chain with the eager rounding points: bf16(acc + bias) -> bf16(GELU) ->
-// bf16(* LayerScale) -> bf16(+ residual) | SwiGLU over interleaved (gate, up) column pairs. The per-column vectors and the residual
-// row are fetched with 16-byte loads issued BEFORE the TMEM wait, so their latency overlaps the tcgen05.ld.
-template <int BN>
-__device__ __forceinline__ void epilogue_rows(uint32_t taddr, int m, int n0, int M, int N, __nv_bfloat16* C, int ldc, const EpiParams& ep,
-                                              const EpiCtx& ec) {
-  const bool row_ok = m < M;
-  const long rrow = ec.has_res ? static_cast<long>(ep.resid_mod > 0 ? m % ep.resid_mod : m) * ep.ldr : 0;
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    const int nb = n0 + c * 32;
-    if (nb >= N) break;  // warp-uniform
-    uint32_t r[32];
-    tmem_ld_32x32(taddr + c * 32, r);
-    const int valid = N - nb;  // >= 32: whole chunk
-    uint32_t wb[16], wl[16], wr[16];
-    if (ec.has_bias) ld32_bf16(ep.bias + nb, valid, wb);
-    if (ec.has_ls) ld32_bf16(ep.ls + nb, valid, wl);
-    if (ec.has_res && row_ok) ld32_bf16(ep.resid + rrow + nb, valid, wr);
-    tmem_ld_wait_on(r);
-    if (!row_ok) continue;
-    float v[32];
+// One epilogue warp's share of an accumulator tile: lane i owns output row m (TMEM lane base + i), NC fp32 columns starting at TMEM
+// address `taddr`, output columns n0 .. n0 + NC. Fused chain with the eager rounding points: bf16(acc + bias) -> bf16(GELU) ->
+// bf16(* LayerScale) -> bf16(+ residual) | SwiGLU over interleaved (gate, up) column pairs.
+// The residual slice of the row does not depend on the accumulator: EpiResid::load fetches ALL of it (16-byte loads) before the warp
+// waits for the tile's MMAs, so the L2 round trips of the residual hide behind the main loop instead of being paid once per 32-column
+// chunk (the ViT proj / fc2 and Llama o / down tiles were bound by exactly that chain). bias / LayerScale slices (same for every row,
+// L1 hits) are fetched per chunk, in front of the TMEM wait.
+// Epilogue specialisations (picked on the host from the flags; each kernel instantiation carries only its own chain):
+//   EPI_ANY   : every combination, 32-column chunks in a rolled loop (bias / GELU / LayerScale / residual / SwiGLU tested at run time)
+//   EPI_RESID : bias -> LayerScale -> residual (no GELU, no SwiGLU), chunk loop unrolled over the prefetched residual
+//   EPI_SWIGLU: SwiGLU only
+enum EpiKind { EPI_ANY = 0, EPI_RESID = 1, EPI_SWIGLU = 2 };
+
+template <int NC, int EPI>
+struct EpiResid {
+  uint32_t w[EPI == EPI_RESID ? NC / 32 : 1][16];
+  __device__ __forceinline__ void load(const EpiParams& ep, const EpiCtx& ec, int m, int n0, int M, int N) {
+    if constexpr (EPI == EPI_RESID) {
+      if (m >= M) return;
+      const __nv_bfloat16* row = ep.resid + static_cast<long>(ep.resid_mod > 0 ? m % ep.resid_mod : m) * ep.ldr;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (ec.has_bias) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += bf16_of(wb, j);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);  // Linear output (bias fused before rounding, as cuBLASLt)
-    if (ec.do_gelu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = bf16_round(gelu_erf(v[j]));
-    }
-    if (ec.has_ls) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j] * bf16_of(wl, j));
-    }
-    if (ec.has_res) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j] + bf16_of(wr, j));
-    }
-    if (ec.do_swiglu) {
-      // interleaved (gate, up) columns -> one output column per pair: bf16(bf16(silu(g)) * u)
-      __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + nb / 2;
-      uint32_t o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = pack_bf16(bf16_round(silu(v[4 * j])) * v[4 * j + 1], bf16_round(silu(v[4 * j + 2])) * v[4 * j + 3]);
-      if (valid >= 32 && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
-        reinterpret_cast<uint4*>(crow)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        reinterpret_cast<uint4*>(crow)[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (2 * j + 1 < valid) crow[j] = __ushort_as_bfloat16(static_cast<unsigned short>((j & 1) ? (o[j >> 1] >> 16) : (o[j >> 1] & 0xffffu)));
+      for (int c = 0; c < NC / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb < N) ld32_bf16(row + nb, N - nb, w[c]);
       }
+    }
+  }
+};
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int m, int nb, bool row_ok, int N, __nv_bfloat16* C, int ldc, const EpiParams& ep,
+                                               const EpiCtx& ec, const uint32_t (&wres)[16], long rrow) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  const int valid = N - nb;  // >= 32: whole chunk
+  uint32_t wb[16], wl[16], wr[16];
+  if (EPI != EPI_SWIGLU && ec.has_bias) ld32_bf16(ep.bias + nb, valid, wb);
+  if (EPI != EPI_SWIGLU && ec.has_ls) ld32_bf16(ep.ls + nb, valid, wl);
+  if (EPI == EPI_ANY && ec.has_res && row_ok) ld32_bf16(ep.resid + rrow + nb, valid, wr);
+  tmem_ld_wait_on(r);
+  if (!row_ok) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (EPI != EPI_SWIGLU && ec.has_bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += bf16_of(wb, j);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);  // Linear output (bias fused before rounding, as cuBLASLt)
+  if (EPI == EPI_ANY && ec.do_gelu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(gelu_erf(v[j]));
+  }
+  if (EPI != EPI_SWIGLU && ec.has_ls) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j] * bf16_of(wl, j));
+  }
+  if (EPI == EPI_RESID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j] + bf16_of(wres, j));
+  } else if (EPI == EPI_ANY && ec.has_res) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j] + bf16_of(wr, j));
+  }
+  if (EPI == EPI_SWIGLU || (EPI == EPI_ANY && ec.do_swiglu)) {
+    // interleaved (gate, up) columns -> one output column per pair: bf16(bf16(silu(g)) * u)
+    __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + nb / 2;
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = pack_bf16(bf16_round(silu(v[4 * j])) * v[4 * j + 1], bf16_round(silu(v[4 * j + 2])) * v[4 * j + 3]);
+    if (valid >= 32 && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
+      reinterpret_cast<uint4*>(crow)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<uint4*>(crow)[1] = make_uint4(o[4], o[5], o[6], o[7]);
     } else {
-      __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + nb;
-      if (valid >= 32 && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          reinterpret_cast<uint4*>(crow)[j] = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-      } else {
+      for (int j = 0; j < 16; ++j)
+        if (2 * j + 1 < valid) crow[j] = __ushort_as_bfloat16(static_cast<unsigned short>((j & 1) ? (o[j >> 1] >> 16) : (o[j >> 1] & 0xffffu)));
+    }
+  } else {
+    __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + nb;
+    if (valid >= 32 && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < valid) crow[j] = __float2bfloat16_rn(v[j]);
-      }
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<uint4*>(crow)[j] = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) crow[j] = __float2bfloat16_rn(v[j]);
     }
   }
 }
 
-template <int BN>
+template <int NC, int EPI>
+__device__ __forceinline__ void epilogue_rows(uint32_t taddr, int m, int n0, int M, int N, __nv_bfloat16* C, int ldc, const EpiParams& ep,
+                                              const EpiCtx& ec, const EpiResid<NC, EPI>& res) {
+  const bool row_ok = m < M;
+  if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+    for (int c = 0; c < NC / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= N) break;  // warp-uniform
+      epilogue_chunk<EPI>(taddr + c * 32, m, nb, row_ok, N, C, ldc, ep, ec, res.w[c], 0);
+    }
+  } else {
+    const long rrow = (EPI == EPI_ANY && ec.has_res) ? static_cast<long>(ep.resid_mod > 0 ? m % ep.resid_mod : m) * ep.ldr : 0;
+#pragma unroll 1
+    for (int c = 0; c < NC / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= N) break;  // warp-uniform
+      epilogue_chunk<EPI>(taddr + c * 32, m, nb, row_ok, N, C, ldc, ep, ec, res.w[0], rrow);
+    }
+  }
+}
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C,
                int ldc, int M, int N, int K, EpiParams ep) {
@@ -174,7 +229,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + BK - 1) / BK;
-  const int mt = (M + BM - 1) / BM, n_tiles = mt * ((N + BN - 1) / BN);
+  const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN, n_tiles = mt * nt;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -201,7 +256,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t it = 0;  // ring iteration, continues across tiles: the producer runs ahead into the next tile
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+        int mi, ni;
+        tile_coords(tile, mt, nt, mi, ni);
+        const int m0 = mi * BM, n0 = ni * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -246,12 +303,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const EpiCtx ec(ep);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-      const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN + ch * (BN / 2);
+      int mi, ni;
+      tile_coords(tile, mt, nt, mi, ni);
+      const int m0 = mi * BM, n0 = ni * BN + ch * (BN / 2);
       const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+      EpiResid<BN / 2, EPI> res;
+      res.load(ep, ec, m0 + q * 32 + lane, n0, M, N);
       mbar_wait(&tmem_full[buf], bph);
       tc_fence_after();
-      epilogue_rows<BN / 2>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
-                            ep, ec);
+      epilogue_rows<BN / 2, EPI>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
+                            ep, ec, res);
       // this warp's quarter of the accumulator buffer is read out: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -286,6 +347,7 @@ struct PairCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C, int ldc, int M,
                     int N, int K, EpiParams ep) {
@@ -303,7 +365,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int nkb = (K + BK - 1) / BK;
-  const int mt = (M + 2 * BM - 1) / (2 * BM), n_tiles = mt * ((N + BN - 1) / BN);
+  const int mt = (M + 2 * BM - 1) / (2 * BM), nt = (N + BN - 1) / BN, n_tiles = mt * nt;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -330,7 +392,9 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-        const int m0 = (tile % mt) * (2 * BM) + rank * BM, n0 = (tile / mt) * BN + rank * (BN / 2);
+        int mi, ni;
+        tile_coords(tile, mt, nt, mi, ni);
+        const int m0 = mi * (2 * BM) + rank * BM, n0 = ni * BN + rank * (BN / 2);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -373,12 +437,16 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const EpiCtx ec(ep);
     uint32_t tl = 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tl) {
-      const int m0 = (tile % mt) * (2 * BM) + rank * BM, n0 = (tile / mt) * BN + ch * (BN / 2);
+      int mi, ni;
+      tile_coords(tile, mt, nt, mi, ni);
+      const int m0 = mi * (2 * BM) + rank * BM, n0 = ni * BN + ch * (BN / 2);
       const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+      EpiResid<BN / 2, EPI> res;
+      res.load(ep, ec, m0 + q * 32 + lane, n0, M, N);
       mbar_wait(&tmem_full[buf], bph);
       tc_fence_after();
-      epilogue_rows<BN / 2>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
-                            ep, ec);
+      epilogue_rows<BN / 2, EPI>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
+                            ep, ec, res);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
@@ -426,6 +494,13 @@ static int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int
   return 0;
 }
 
+static int epi_kind(const EpiParams& ep) {
+  const bool gelu = ep.flags & EMX_EPI_GELU, swiglu = ep.flags & EMX_EPI_SWIGLU;
+  if (swiglu && !gelu && !ep.bias && !ep.ls && !ep.resid) return EPI_SWIGLU;
+  if (ep.resid && !gelu && !swiglu) return EPI_RESID;
+  return EPI_ANY;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat16* C, int ldc, int M, int N, int K, const EpiParams& ep,
                        cudaStream_t stream) {
@@ -434,11 +509,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat
   const int sms = device_sms();
   if (!attr_set || sms < 0) return -2;
   if (!*attr_set) {
-    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     *attr_set = true;
   }
   const int n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  gemm_tn_kernel<BN><<<n_tiles < sms ? n_tiles : sms, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  switch (epi_kind(ep)) {
+    case EPI_RESID: gemm_tn_kernel<BN, EPI_RESID><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
+    case EPI_SWIGLU: gemm_tn_kernel<BN, EPI_SWIGLU><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
+    default: gemm_tn_kernel<BN, EPI_ANY><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
+  }
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -449,12 +531,18 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, __nv_b
   const int sms = device_sms();
   if (!attr_set || sms < 0) return -2;
   if (!*attr_set) {
-    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel<EPI_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
     *attr_set = true;
   }
   const int n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + PairCfg::BN - 1) / PairCfg::BN);
   const int pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
-  gemm_tn_pair_kernel<<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep);
+  switch (epi_kind(ep)) {
+    case EPI_RESID: gemm_tn_pair_kernel<EPI_RESID><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
+    case EPI_SWIGLU: gemm_tn_pair_kernel<EPI_SWIGLU><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
+    default: gemm_tn_pair_kernel<EPI_ANY><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
+  }
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

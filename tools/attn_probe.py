@@ -16,6 +16,7 @@ from emmax_b200._lib import call, ptr, stream
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--warm", type=int, default=3)
 args = ap.parse_args()
 try:
     from flash_attn import flash_attn_qkvpacked_func
@@ -25,7 +26,7 @@ except Exception as e:  # noqa: BLE001
 
 
 def time_ms(fn, reps):
-    for _ in range(3):
+    for _ in range(args.warm):
         fn()
     torch.cuda.synchronize()
     out = []

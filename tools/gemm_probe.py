@@ -20,6 +20,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--modes", default="0,1,2")
 ap.add_argument("--batches", default="32,1")
+ap.add_argument("--warm", type=int, default=3)
+ap.add_argument("--no-cublas", action="store_true")
 args = ap.parse_args()
 BF = torch.bfloat16
 
@@ -38,7 +40,7 @@ def shapes(B):
 
 
 def time_ms(fn, reps):
-    for _ in range(3):
+    for _ in range(args.warm):
         fn()
     torch.cuda.synchronize()
     out = []
@@ -64,7 +66,7 @@ for B in [int(b) for b in args.batches.split(",")]:
         res = out if "res" in epi else None
         flags = EPI_SWIGLU if swiglu else (1 if "gelu" in epi else 0)
         ref = torch.empty(M, N, dtype=BF, device="cuda")
-        t_cublas = time_ms(lambda: torch.matmul(a, w.T, out=ref), args.reps)
+        t_cublas = time_ms(lambda: torch.matmul(a, w.T, out=ref), args.reps) if not args.no_cublas else float("nan")
         row = {"batch": B, "gemm": name, "M": M, "N": N, "K": K, "epilogue": epi, "cublas_plain_ms": round(t_cublas, 4),
                "cublas_tflops": round(2 * M * N * K / t_cublas / 1e9, 1)}  # fmt: skip
         for mode in args.modes.split(","):
