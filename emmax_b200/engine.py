@@ -159,6 +159,7 @@ class Engine:
         self.d_out_tokens = torch.zeros(self.max_new, dtype=torch.int32, device=dev)
         self.h_flag = torch.zeros(4, dtype=torch.int32).pin_memory()
         self._ws: Dict[Tuple[int, int], dict] = {}
+        self._slot_tables: Dict[Tuple[int, ...], torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------------------------
     # kernel wrappers
@@ -255,18 +256,31 @@ class Engine:
     def _layer_cache(self, cache: torch.Tensor, layer: int) -> int:
         return cache.data_ptr() + layer * self.layer_cache_bytes
 
-    def _llm_prefill(self, ws: dict, B: int, n_ids: int, slot: int = 0) -> None:
+    def _slot_table(self, slot) -> int:
+        """Device pointer of the block-table rows a prefill writes through: `slot` = first of B consecutive sequence slots, or an explicit
+        tuple of slots (continuous batching refills whichever slots are free): their rows gathered into a small table of their own."""
+        if isinstance(slot, int):
+            return self.block_table[slot].data_ptr()
+        key = tuple(int(b) for b in slot)
+        if key not in self._slot_tables:
+            if len(self._slot_tables) >= 64:
+                self._slot_tables.pop(next(iter(self._slot_tables)))
+            self._slot_tables[key] = self.block_table[list(key)].contiguous()
+        return self._slot_tables[key].data_ptr()
+
+    def _llm_prefill(self, ws: dict, B: int, n_ids: int, slot=0) -> None:
         """multimodal assembly + full-sequence Llama forward, KV written to the paged cache of sequences slot .. slot + B - 1
         (modeling_prismatic.py:380-415)"""
         t, cfg = self.t, self.config
         H, I, L, S = t.hidden_size, t.intermediate_size, t.num_hidden_layers, ws["S"]
         heads, hd = t.num_attention_heads, t.head_dim
         call("emx_embed_assemble", ptr(ws["ids"]), n_ids, ptr(self.embed), ptr(ws["patches"]), cfg.num_patches, ptr(ws["x"]), B, H, stream())
+        tbl = self._slot_table(slot)
         for l in range(L):
             call("emx_rmsnorm", ptr(ws["x"]), ptr(self.ln1[l]), ptr(ws["n"]), B * S, H, t.rms_norm_eps, stream())
             self.gemm(ws["n"], self.w_qkv[l], ws["qkv"])
             call("emx_rope_kvstore", ptr(ws["qkv"]), B, S, heads, hd, ptr(self.cos_tab), ptr(self.sin_tab), 0,
-                 self._layer_cache(self.k_cache, l), self._layer_cache(self.v_cache, l), self.block_table[slot].data_ptr(),
+                 self._layer_cache(self.k_cache, l), self._layer_cache(self.v_cache, l), tbl,
                  self.pages_per_seq, self.PAGE, stream())  # fmt: skip
             call("emx_attn_fwd", ptr(ws["qkv"]), ptr(ws["att"]), B, S, heads, hd, 1, hd**-0.5, stream())
             self.gemm(ws["att"], self.w_o[l], ws["x"], resid=ws["x"])
@@ -280,7 +294,7 @@ class Engine:
             call("emx_lmhead_argmax", ptr(self.lm_head), H, ptr(ws["last_n"][b]), t.vocab_size, H, ptr(ws["logits"][b]),
                  ptr(ws["first"][b : b + 1]), None, stream())  # fmt: skip
 
-    def _prefill_body(self, ws: dict, B: int, n_ids: int, slot: int = 0) -> None:
+    def _prefill_body(self, ws: dict, B: int, n_ids: int, slot=0) -> None:
         self._vision(ws, B)
         self._projector(ws)
         self._llm_prefill(ws, B, n_ids, slot)
@@ -288,12 +302,17 @@ class Engine:
     # ------------------------------------------------------------------------------------------------------------
     @_on_engine_device
     @torch.no_grad()
-    def prefill(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, use_graph: bool = True, slot: int = 0) -> dict:
-        """Vision + projector + LLM prefill for B same-length prompts, into the KV pages of sequences slot .. slot + B - 1.
-        Returns the workspace (first tokens, logits, features)."""
+    def prefill(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, use_graph: bool = True, slot=0) -> dict:
+        """Vision + projector + LLM prefill for B same-length prompts, into the KV pages of sequences slot .. slot + B - 1 (`slot` an int)
+        or of the B sequence slots listed in `slot` (a tuple). Returns the workspace (first tokens, logits, features)."""
         B, n_ids = input_ids.shape
-        if slot < 0 or slot + B > self.max_batch:
-            raise ValueError(f"batch {B} at slot {slot} exceeds engine capacity {self.max_batch}")
+        if isinstance(slot, int):
+            if slot < 0 or slot + B > self.max_batch:
+                raise ValueError(f"batch {B} at slot {slot} exceeds engine capacity {self.max_batch}")
+        else:
+            slot = tuple(int(b) for b in slot)
+            if len(slot) != B or len(set(slot)) != B or min(slot) < 0 or max(slot) >= self.max_batch:
+                raise ValueError(f"slots {slot}: need {B} distinct slots below the engine capacity {self.max_batch}")
         S = n_ids + self.config.num_patches
         if S + 1 > self.max_context:
             raise ValueError(f"prompt of {S} positions does not fit max_context={self.max_context}")
@@ -312,6 +331,8 @@ class Engine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._prefill_body(ws, B, n_ids, slot)
+            while len(self._graphs) >= 4 * self.MAX_CACHED_SHAPES:  # (several slot placements per prompt shape under continuous batching)
+                del self._graphs[next(iter(self._graphs))]
             self._graphs[key] = (g, _lib.launch_count - before)
             _lib.count_launches(before - _lib.launch_count)  # capture enqueued nothing
         g, n_kernels = self._graphs[key]
@@ -413,6 +434,114 @@ class Engine:
         self.b_state = torch.zeros(C.sizeof(DecodeBatchState) // 4, dtype=torch.int32, device=dev)
         self.b_out = torch.zeros((MB, self.max_new), dtype=torch.int32, device=dev)
         self.h_bflag = torch.zeros(C.sizeof(DecodeBatchState) // 4, dtype=torch.int32).pin_memory()
+
+    @_on_engine_device
+    @torch.no_grad()
+    def serve(self, requests, eos_token_id: Optional[int] = 2, use_graph: bool = True, poll_every: int = 32) -> List[torch.Tensor]:
+        """Continuous batching over the sequence slots of the batched decode kernel: a stream of independent requests
+        `(input_ids [1, n], pixel_values [1, 6, h, w], max_new_tokens)` is decoded min(8, max_batch) at a time, and a slot whose sequence
+        has reached its token limit (or EOS) is refilled with the next request at once — prefilled straight into that slot's KV pages
+        (same-length prompts admitted together share one batched prefill) — instead of idling until the longest sequence of its batch is
+        done. With BASELINE.json configs[4]'s mix of 128- and 512-token requests a static batch of 8 runs half empty for 3/4 of its
+        launches; here every launch carries 8 live sequences. Per-sequence results are those of `generate` (same kernels, same state
+        machine: position, limit and EOS are per slot). Returns the generated ids per request, in request order."""
+        MB = MAX_DECODE_BATCH
+        S = min(MB, self.max_batch)
+        P = self.config.num_patches
+        reqs = []
+        for i, (ids, pv, lim) in enumerate(requests):
+            lim = int(lim)
+            if ids.dim() != 2 or ids.shape[0] != 1 or pv.shape[0] != 1:
+                raise ValueError(f"request {i}: input_ids [1, n] and pixel_values [1, ...] expected")
+            if lim < 1 or lim > self.max_new or ids.shape[1] + P + lim > self.max_context:
+                raise ValueError(f"request {i}: {ids.shape[1] + P} prompt positions + {lim} new tokens exceed max_context={self.max_context}")
+            reqs.append((ids, pv, lim))
+        if self.pages_per_seq > 2 * ATT_MAX_SEGMENTS:
+            raise ValueError(f"batched decode supports contexts up to {2 * ATT_MAX_SEGMENTS * self.PAGE} (max_context={self.max_context})")
+        self._alloc_batch()
+        dev = self.device
+        st = self.b_state.view(-1)
+        st[: 5 * MB].zero_()
+        st[3 * MB : 4 * MB].fill_(1)  # every slot starts free = finished
+        use_eos = eos_token_id is not None
+        p = self._decode_batch_params(S)
+        p.eos_token = int(eos_token_id) if use_eos else -1
+        lib, s = _lib.load(), stream()
+        slot_req, slot_left, slot_pos = [-1] * S, [0] * S, [0] * S
+        results: List[Optional[torch.Tensor]] = [None] * len(reqs)
+        nxt = done = n_launched = 0
+        kv_reads = kv_writes = 0  # cached positions read / appended over all launches (host mirror; exact when no sequence stops at EOS)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        dec_ms_events = []
+
+        def retire(b: int, n_tokens: int) -> None:
+            nonlocal done
+            results[slot_req[b]] = self.b_out[b, :n_tokens].clone()
+            slot_req[b], slot_left[b] = -1, 0
+            done += 1
+
+        while done < len(reqs):
+            # ---- admit: next requests into the free slots, same-length prompts in one batched prefill
+            free = [b for b in range(S) if slot_req[b] < 0]
+            while free and nxt < len(reqs):
+                n_ids = reqs[nxt][0].shape[1]
+                group = [nxt]
+                while len(group) < len(free) and group[-1] + 1 < len(reqs) and reqs[group[-1] + 1][0].shape[1] == n_ids:
+                    group.append(group[-1] + 1)
+                slots = tuple(free[: len(group)])
+                free = free[len(group) :]
+                ids = torch.cat([reqs[r][0] for r in group]).to(dev)
+                pv = torch.cat([reqs[r][1] for r in group]).to(dev, BF16)
+                ws = self.prefill(ids, pv, use_graph=use_graph, slot=slots if len(slots) > 1 else slots[0])
+                first = ws["first"][: len(group)]
+                idx = torch.tensor(slots, dtype=torch.int64, device=dev)
+                lims = torch.tensor([reqs[r][2] for r in group], dtype=torch.int32, device=dev)
+                st.index_copy_(0, idx, first)
+                st.index_copy_(0, idx + MB, torch.full((len(group),), n_ids + P, dtype=torch.int32, device=dev))
+                st.index_copy_(0, idx + 2 * MB, torch.ones(len(group), dtype=torch.int32, device=dev))
+                st.index_copy_(0, idx + 3 * MB, (first == eos_token_id).to(torch.int32) if use_eos else torch.zeros(len(group), dtype=torch.int32, device=dev))
+                st.index_copy_(0, idx + 4 * MB, lims)
+                self.b_out[:, 0].index_copy_(0, idx, first)
+                for b, r in zip(slots, group):
+                    slot_req[b], slot_left[b], slot_pos[b] = r, reqs[r][2] - 1, n_ids + P
+                nxt += len(group)
+            for b in range(S):  # a limit of 1 is complete after its prefill
+                if slot_req[b] >= 0 and slot_left[b] == 0 and not use_eos:
+                    retire(b, reqs[slot_req[b]][2])
+            live = [b for b in range(S) if slot_req[b] >= 0]
+            if not live:
+                continue
+            # ---- decode until the next slot frees up (or the next EOS poll)
+            steps = min(slot_left[b] for b in live if slot_left[b] > 0) if any(slot_left[b] > 0 for b in live) else 0
+            if use_eos:
+                steps = min(steps, poll_every) if steps else 0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                _lib.check(lib.emx_decode_batch_step(C.byref(p), s))
+                for b in live:
+                    if slot_left[b] > 0:
+                        kv_reads += slot_pos[b]
+                        kv_writes += 1
+                        slot_pos[b] += 1
+                        slot_left[b] -= 1
+            e1.record()
+            dec_ms_events.append((e0, e1))
+            n_launched += steps
+            if use_eos:
+                hf = st[: 5 * MB].tolist()  # blocking read of the slot state once per poll interval
+                for b in live:
+                    if hf[3 * MB + b] != 0 or hf[2 * MB + b] >= reqs[slot_req[b]][2]:
+                        retire(b, hf[2 * MB + b])
+            else:
+                for b in live:
+                    if slot_left[b] == 0:
+                        retire(b, reqs[slot_req[b]][2])
+        ev1.record()
+        _lib.count_launches(n_launched)
+        self.last_serve = dict(events=(ev0, ev1), decode_events=dec_ms_events, launches=n_launched, kv_reads=kv_reads, kv_writes=kv_writes)
+        return results  # type: ignore[return-value]
 
     def _decode_batch_params(self, B: int) -> DecodeBatchParams:
         t = self.t

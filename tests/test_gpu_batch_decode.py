@@ -200,3 +200,57 @@ def test_simpler_policy_on_the_engine_single_and_batched():
     want = model.detokenize_on_device(torch.tensor(chain, dtype=torch.int32, device="cuda"))[1].cpu().numpy()
     raw, _ = singles[0].step(frames[0], tasks[0])
     assert np.array_equal(np.concatenate([raw["world_vector"], raw["rotation_delta"], raw["open_gripper"]]), want)
+
+
+def test_tiny_continuous_batching_stream_equals_single_runs():
+    """Engine.serve: 19 requests (different prompt lengths, different token limits) streamed through the 8 sequence slots — a slot is
+    refilled the moment its sequence reaches its limit, same-length neighbours share one batched prefill into whatever slots are free.
+    Scripted head (argmax margins far above bf16 noise, so greedy ids are a bit-exact check: the flash-decoding split of a row depends on
+    its neighbours' contexts and moves low-order bits): every request's ids equal the script AND its own bs=1 `generate`; neighbours,
+    slot placement and refills must not matter."""
+    from emmax_b200 import OpenVLAForActionPrediction, SyntheticLlamaTokenizer, tiny_config
+    from emmax_b200.synthetic import default_script, make_state_dict
+
+    cfg = tiny_config()
+    script = default_script(SyntheticLlamaTokenizer(), 30, seed=6)[:-1]  # (without the closing EOS: limits alone end the sequences)
+    prev = 83
+    sd = make_state_dict(cfg, seed=11, device="cpu", script=script, script_prev=prev)
+    model = OpenVLAForActionPrediction(cfg, sd, max_batch=8, max_context=1024).to("cuda")
+    eng = model.engine
+    lens = [23, 23, 23, 31, 17, 17, 40, 23, 23, 12, 12, 12, 12, 29, 23, 23, 18, 18, 33]
+    limits = [9, 29, 5, 17, 29, 1, 12, 25, 7, 29, 3, 14, 22, 6, 29, 11, 2, 19, 8]
+    ids, pv = _prompts(cfg, lens, 13), _pixels(len(lens), 14)
+    for x in ids:
+        x[0, -1] = prev
+    got = eng.serve([(ids[i], pv[i : i + 1], limits[i]) for i in range(len(lens))], eos_token_id=None)
+    torch.cuda.synchronize()
+    assert eng.last_serve["launches"] < sum(limits) // 4, "slots were not shared"
+    for i in range(len(lens)):
+        assert got[i].cpu().tolist() == script[: limits[i]], f"request {i} (prompt {lens[i]}, limit {limits[i]}): ids differ from the script"
+    for i in (1, 4, 6, 13):
+        one, _ = eng.generate(ids[i], pv[i : i + 1], limits[i], eos_token_id=None)
+        assert torch.equal(got[i], one), f"request {i}: stream result differs from its bs=1 run"
+
+
+def test_tiny_continuous_batching_scripted_eos():
+    """Scripted head ending in EOS: with EOS active the stream retires sequences at the lagged poll; ids bit-equal to the script (cut at
+    each limit), through the model-level `generate_batch(..., continuous=True)`."""
+    from emmax_b200 import OpenVLAForActionPrediction, SyntheticLlamaTokenizer, tiny_config
+    from emmax_b200.synthetic import default_script, make_state_dict
+
+    cfg = tiny_config()
+    tok = SyntheticLlamaTokenizer()
+    script = default_script(tok, 40, seed=5)
+    prev = 91
+    sd = make_state_dict(cfg, seed=12, device="cpu", script=script, script_prev=prev)
+    model = OpenVLAForActionPrediction(cfg, sd, max_batch=8, max_context=1024).to("cuda")
+    lens = [12, 20, 12, 33, 12, 12, 20, 20, 15, 15, 15, 12]
+    limits = [64, 64, 10, 64, 40, 39, 64, 7, 64, 64, 21, 64]
+    ids = _prompts(cfg, lens, 3)
+    for x in ids:
+        x[0, -1] = prev
+    pv = _pixels(len(lens), 4)
+    out = model.generate_batch(ids, [pv[i : i + 1] for i in range(len(lens))], limits, eos_token_id=tok.eos_token_id, continuous=True)
+    for i, lim in enumerate(limits):
+        want = script[: min(lim, len(script))]
+        assert out[i][0, lens[i] :].cpu().tolist() == want, f"request {i} (limit {lim}): ids differ from the script"
