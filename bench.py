@@ -406,6 +406,8 @@ def measure_c5(cfg, model, proc, script, dev, world: int, rank: int, K: int, W: 
 
     e2e_ms, _ = timed(step_e2e, W, K)
     hbm_peak, _, peak_src = read_peaks()
+    btpath = os.path.join(ROOT, "profiles", "decode_batch_traffic.json")
+    btraffic = json.load(open(btpath)) if os.path.exists(btpath) else {}
     avg_ms = acc["ms"] / max(acc["launches"], 1)
     per_launch = acc["bytes"] / max(acc["launches"], 1)
     achieved = per_launch / (avg_ms * 1e-3) / 1e9
@@ -451,7 +453,10 @@ def measure_c5(cfg, model, proc, script, dev, world: int, rank: int, K: int, W: 
                 "h2d_bytes_per_step": int(h_reqs[0][0].numel() + h_reqs[0][1].numel() * 8), "d2h_bytes_per_step": 4 * sum(C5_LIMITS) + 4 * B},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "decode_batch_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src + " hbm_gbs", "bytes_per_launch": per_launch,
+                     "frac": achieved / hbm_peak, "traffic": btraffic.get("dram_bytes_per_launch"),
+                     "traffic_source": "profiles/decode_batch_traffic.json: ncu --set full capture of this kernel at batch 8, context 365 "
+                                       f"(algorithmic there: {btraffic.get('algorithmic_bytes_at_that_point')} B, ratio {btraffic.get('ratio_to_algorithmic')})",
+                     "peak_source": peak_src + " hbm_gbs", "bytes_per_launch": per_launch,
                      "avg_launch_ms": avg_ms, "launches_timed": acc["launches"], "share_of_step": acc["ms"] / total_ms},
         "action_of_sequence_0": [round(float(a), 6) for a in last[0][0][0]],
     }  # fmt: skip
