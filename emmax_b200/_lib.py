@@ -75,12 +75,13 @@ class DecodeBatchParams(C.Structure):
     ]  # fmt: skip
 
 
-_P, _I, _F = C.c_void_p, C.c_int, C.c_float
+_P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_long
 _SIGNATURES = {
     "emx_last_error": (C.c_char_p, []),
     "emx_abi_version": (_I, []),
     "emx_arch": (C.c_char_p, []),
     "emx_gemm_bf16": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P]),
+    "emx_gemm_bf16_ws": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _L, _P]),
     "emx_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "emx_rmsnorm": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "emx_preprocess_u8": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),

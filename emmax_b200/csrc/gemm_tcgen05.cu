@@ -127,21 +127,38 @@ struct EpiResid {
   }
 };
 
-template <int EPI>
+// FROM_WS (split-K, last CTA of a tile): the accumulator chunk is the sum of the `splits` fp32 partials in the workspace, added in split
+// order (deterministic), instead of a TMEM read.
+template <int EPI, bool FROM_WS = false>
 __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int m, int nb, bool row_ok, int N, __nv_bfloat16* C, int ldc, const EpiParams& ep,
-                                               const EpiCtx& ec, const uint32_t (&wres)[16], long rrow) {
+                                               const EpiCtx& ec, const uint32_t (&wres)[16], long rrow, const float* wsp = nullptr, int splits = 0,
+                                               long split_stride = 0) {
   uint32_t r[32];
-  tmem_ld_32x32(taddr, r);
+  if constexpr (!FROM_WS) tmem_ld_32x32(taddr, r);
   const int valid = N - nb;  // >= 32: whole chunk
   uint32_t wb[16], wl[16], wr[16];
   if (EPI != EPI_SWIGLU && ec.has_bias) ld32_bf16(ep.bias + nb, valid, wb);
   if (EPI != EPI_SWIGLU && ec.has_ls) ld32_bf16(ep.ls + nb, valid, wl);
   if (EPI == EPI_ANY && ec.has_res && row_ok) ld32_bf16(ep.resid + rrow + nb, valid, wr);
-  tmem_ld_wait_on(r);
-  if (!row_ok) return;
   float v[32];
+  if constexpr (FROM_WS) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4* src = reinterpret_cast<const float4*>(wsp + sp * split_stride);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 f = __ldcg(src + j);
+        v[4 * j] += f.x, v[4 * j + 1] += f.y, v[4 * j + 2] += f.z, v[4 * j + 3] += f.w;
+      }
+    }
+    if (!row_ok) return;
+  } else {
+    tmem_ld_wait_on(r);
+    if (!row_ok) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  }
   if (EPI != EPI_SWIGLU && ec.has_bias) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += bf16_of(wb, j);
@@ -317,6 +334,168 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Split-K variant for the small-M problems of a bs = 1 request whose 128 x 128 tiles do not fill the machine (Llama o_proj / down_proj at
+// M = 296: 96 tiles; ViT proj / fc2 at M ~ 260: 18-24 tiles): work item = (tile, k-range). Every CTA dumps its fp32 partial tile into the
+// caller's workspace; the CTA that arrives LAST at the tile's counter adds the partials in split order (deterministic, whoever is last) and
+// runs the fused epilogue chain on the sum. Same pipeline as gemm_tn_kernel (BN = 128).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSplitCounterBytes = 4096;  // head of the workspace: one self-resetting arrival counter per tile (<= 1024 tiles)
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C, int ldc, int M, int N,
+                      int K, EpiParams ep, int splits, uint8_t* workspace) {
+  constexpr int BN = 128;
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tmem_full = empty + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  volatile uint32_t* last_flag = tmem_holder + 1;
+  unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
+  float* wsf = reinterpret_cast<float*>(workspace + kSplitCounterBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + BK - 1) / BK;
+  const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN, n_tiles = mt * nt, n_items = n_tiles * splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item % n_tiles, split = item / n_tiles;
+        int mi, ni;
+        tile_coords(tile, mt, nt, mi, ni);
+        const int m0 = mi * BM, n0 = ni * BN;
+        const int kb0 = split * nkb / splits, kb1 = (split + 1) * nkb / splits;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmA, kb * BK, m0, &full[s]);
+          tma_load_2d(sa + Cfg::kABytes, &tmB, kb * BK, n0, &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t it = 0, tl = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl) {
+        const int split = item / n_tiles;
+        const int kb0 = split * nkb / splits, kb1 = (split + 1) * nkb / splits;
+        const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+        mbar_wait(&tmem_empty[buf], bph ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_k128(sa), bdesc = umma_desc_k128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3, ch = (warp - 4) >> 2;
+    const EpiCtx ec(ep);
+    const int row = q * 32 + lane;
+    const long split_stride = static_cast<long>(BM) * BN;  // floats between the partials of one tile
+    uint32_t tl = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl) {
+      const int tile = item % n_tiles, split = item / n_tiles;
+      int mi, ni;
+      tile_coords(tile, mt, nt, mi, ni);
+      const int m0 = mi * BM, n0 = ni * BN + ch * (BN / 2);
+      const uint32_t buf = tl & 1, bph = (tl >> 1) & 1;
+      float* wtile = wsf + static_cast<long>(tile) * splits * split_stride + static_cast<long>(row) * BN + ch * (BN / 2);
+      mbar_wait(&tmem_full[buf], bph);
+      tc_fence_after();
+      // ---- dump this k-range's partial (fp32, this thread's row, its half of the columns)
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2 / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait_on(r);
+        float4* dst = reinterpret_cast<float4*>(wtile + split * split_stride + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          __stcg(dst + j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);  // accumulator buffer handed back: the MMA warp runs on
+      // ---- arrive at the tile's counter; the last of the `splits` CTAs reduces and finishes the tile
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (threadIdx.x == 128) {
+        const unsigned int old = atomicAdd(&counters[tile], 1u);
+        const bool last = old == static_cast<unsigned int>(splits - 1);
+        if (last) counters[tile] = 0;  // everybody has arrived: ready for the next launch
+        *last_flag = last ? 1u : 0u;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (*last_flag) {
+        __threadfence();
+        const int m = m0 + row;
+        EpiResid<BN / 2, EPI> res;
+        res.load(ep, ec, m, n0, M, N);
+        const bool row_ok = m < M;
+        const long rrow = (EPI == EPI_ANY && ec.has_res) ? static_cast<long>(ep.resid_mod > 0 ? m % ep.resid_mod : m) * ep.ldr : 0;
+#pragma unroll
+        for (int c = 0; c < BN / 2 / 32; ++c) {
+          const int nb = n0 + c * 32;
+          if (nb < N)
+            epilogue_chunk<EPI, true>(0, m, nb, row_ok, N, C, ldc, ep, ec, res.w[EPI == EPI_RESID ? c : 0], rrow, wtile + c * 32, splits, split_stride);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // last_flag is rewritten for the next item
     }
   }
   tc_fence_before();
@@ -525,6 +704,45 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat
   return 0;
 }
 
+static int launch_gemm_splitk(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat16* C, int ldc, int M, int N, int K, const EpiParams& ep,
+                              int splits, void* workspace, cudaStream_t stream) {
+  using Cfg = GemmCfg<128>;
+  bool* attr_set = device_attr_flag(ATTR_GEMM_SPLITK);
+  const int sms = device_sms();
+  if (!attr_set || sms < 0) return -2;
+  if (!*attr_set) {
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_splitk_kernel<EPI_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_splitk_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_splitk_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    *attr_set = true;
+  }
+  const int n_items = ((M + BM - 1) / BM) * ((N + 127) / 128) * splits;
+  const int grid = n_items < sms ? n_items : sms;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  switch (epi_kind(ep)) {
+    case EPI_RESID: gemm_tn_splitk_kernel<EPI_RESID><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, splits, ws); break;
+    case EPI_SWIGLU: gemm_tn_splitk_kernel<EPI_SWIGLU><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, splits, ws); break;
+    default: gemm_tn_splitk_kernel<EPI_ANY><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, splits, ws); break;
+  }
+  EMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// k-ranges per 128 x 128 tile for an under-filled problem: minimise  rounds(tiles * s) * (k-blocks / s * t_kb + t_fixed) + t_reduce  with the
+// measured per-CTA rates of this kernel (~0.43 us per 32 KB k-block: the L2 -> SM ingest of one SM; ~3 us of pipeline fill + epilogue per
+// work item; ~1.5 us for the dump + reduction). 1 = do not split.
+static int pick_splits(long tiles, int nkb, int sms, long workspace_bytes) {
+  int best = 1;
+  double best_t = 1e30;
+  for (int s = 1; s <= 8 && s * 4 <= nkb; ++s) {
+    if (s > 1 && (tiles > 1024 || static_cast<long>(kSplitCounterBytes) + tiles * s * BM * 128 * 4 > workspace_bytes)) break;
+    const double rounds = static_cast<double>((tiles * s + sms - 1) / sms);
+    const double t = rounds * (static_cast<double>(nkb) / s * 0.43 + 3.0) + (s > 1 ? 1.5 : 0.0);
+    if (t < best_t * 0.93) best_t = t, best = s;  // a split has to buy at least 7 %
+  }
+  return best;
+}
+
 static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat16* C, int ldc, int M, int N, int K, const EpiParams& ep,
                             cudaStream_t stream) {
   bool* attr_set = device_attr_flag(ATTR_GEMM_PAIR);
@@ -551,6 +769,12 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, __nv_b
 
 extern "C" int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const void* bias,
                              const void* layerscale, const void* resid, int ldr, int resid_mod, int flags, cudaStream_t stream) {
+  return emx_gemm_bf16_ws(A, lda, W, ldw, C, ldc, M, N, K, bias, layerscale, resid, ldr, resid_mod, flags, nullptr, 0, stream);
+}
+
+extern "C" int emx_gemm_bf16_ws(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const void* bias,
+                                const void* layerscale, const void* resid, int ldr, int resid_mod, int flags, void* workspace,
+                                long workspace_bytes, cudaStream_t stream) {
   using namespace emx;
   EMX_REQUIRE(M > 0 && N > 0 && K > 0, "emx_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   EMX_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "emx_gemm_bf16: lda/ldw must be multiples of 8 elements (TMA 16-B strides): %d %d", lda, ldw);
@@ -562,7 +786,11 @@ extern "C" int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, voi
   // BN = 128 keeps the grid at >= ~1 wave for the M <= 300 problems of a bs=1 request; BN = 256 for large M.
   const int sms = device_sms();
   if (sms < 0) return -2;
-  const bool wide = (static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256) >= 2 * sms);
+  // 128 x 256 tiles once they fill ~0.9 of a wave (each CTA then pulls 48 KB per 128x256x64 MMA block instead of 2 x 32 KB: the GEMMs of
+  // this path are bound by the bytes an SM can pull from L2); EMX_GEMM_WIDE_MIN_PCT overrides the threshold (A/B runs)
+  const char* we = getenv("EMX_GEMM_WIDE_MIN_PCT");
+  const long wide_min = static_cast<long>(sms) * (we ? atoi(we) : 90) / 100;
+  const bool wide = (static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256) >= wide_min);
   // CTA pairs (256 x 256 tiles) once M is large and there is at least one full round of pair tiles
   const char* pe = getenv("EMX_GEMM_PAIR");  // A/B switch for tools/gemm_probe.py: 0 = never, 2 = whenever M > 128
   const int pair_mode = pe ? pe[0] - '0' : 1;
@@ -571,6 +799,18 @@ extern "C" int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, voi
     if (int r = make_tmap(&ta, A, M, K, lda, BM)) return r;
     if (int r = make_tmap(&tb, W, N, K, ldw, PairCfg::BN / 2)) return r;
     return launch_gemm_pair(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, stream);
+  }
+  if (!wide && workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+    // OFF unless EMX_GEMM_SPLITK=1: measured on B200 (profiles/r02_splitk_negative.txt) every bs = 1 problem got 7-11 us SLOWER with it - the
+    // dump -> fence -> counter -> serial reduction tail costs ~10 us, and k-ranges on more SMs do not stream faster in proportion (the
+    // weights come from HBM). Kept as a tested building block (tests/test_gpu_kernels.py::test_gemm_split_k) with that result recorded.
+    const char* se = getenv("EMX_GEMM_SPLITK");
+    const int splits = !(se && se[0] == '1') ? 1 : pick_splits(static_cast<long>((M + BM - 1) / BM) * ((N + 127) / 128), (K + BK - 1) / BK, sms, workspace_bytes);
+    if (splits > 1) {
+      if (int r = make_tmap(&ta, A, M, K, lda, BM)) return r;
+      if (int r = make_tmap(&tb, W, N, K, ldw, 128)) return r;
+      return launch_gemm_splitk(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, splits, workspace, stream);
+    }
   }
   if (int r = make_tmap(&ta, A, M, K, lda, BM)) return r;
   if (int r = make_tmap(&tb, W, N, K, ldw, wide ? 256 : 128)) return r;

@@ -159,17 +159,23 @@ class Engine:
         self.d_out_tokens = torch.zeros(self.max_new, dtype=torch.int32, device=dev)
         self.h_flag = torch.zeros(4, dtype=torch.int32).pin_memory()
         self._ws: Dict[Tuple[int, int], dict] = {}
+        # split-K scratch (emx_gemm_bf16_ws): one per branch that may run concurrently inside the prefill graph (LLM + projector, each tower)
+        self._scratch = [torch.zeros(32 << 20, dtype=torch.uint8, device=self.device) for _ in range(1 + len(self.vits))]
         self._slot_tables: Dict[Tuple[int, ...], torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------------------------
     # kernel wrappers
     # ------------------------------------------------------------------------------------------------------------
     @staticmethod
-    def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias=None, ls=None, resid=None, resid_mod: int = 0, flags: int = 0) -> None:
+    def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias=None, ls=None, resid=None, resid_mod: int = 0, flags: int = 0,
+             scratch: Optional[torch.Tensor] = None) -> None:
+        """scratch: zero-initialised device buffer of this stream / graph branch: lets the library split K for small-M problems that
+        do not fill the machine (emx_gemm_bf16_ws)."""
         M, K = a.shape
         N = w.shape[0]
-        call("emx_gemm_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias), ptr(ls),
-             ptr(resid), resid.stride(0) if resid is not None else 0, resid_mod, flags, stream())  # fmt: skip
+        call("emx_gemm_bf16_ws", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias), ptr(ls),
+             ptr(resid), resid.stride(0) if resid is not None else 0, resid_mod, flags, ptr(scratch), scratch.numel() if scratch is not None else 0,
+             stream())  # fmt: skip
 
     MAX_CACHED_SHAPES = 8  # distinct (batch, prompt length) workspaces + prefill graphs kept; a new shape costs one eager prefill + a capture
 
@@ -233,25 +239,26 @@ class Engine:
         vw = self.vits[i]
         v, w = vw.dims, ws[f"v{i}"]
         D, T, hd = v.embed_dim, v.num_tokens, v.head_dim
+        sc = self._scratch[1 + i]  # this tower's split-K scratch (the towers run concurrently)
         call("emx_patch_im2col", ptr(ws["pixels"]), B, 6, 3 * i, side, side, v.patch_size, ptr(w["im2col"]), vw.kpad, stream())
-        self.gemm(w["im2col"], vw.w_pe, w["pe"], bias=vw.b_pe)
+        self.gemm(w["im2col"], vw.w_pe, w["pe"], bias=vw.b_pe, scratch=sc)
         call("emx_vit_assemble", ptr(w["pe"]), ptr(vw.pos), ptr(vw.prefix), ptr(w["tok"]), B, P, v.num_prefix_tokens, D, stream())
         for blk in vw.blocks:
             call("emx_layernorm", ptr(w["tok"]), ptr(blk["norm1.weight"]), ptr(blk["norm1.bias"]), ptr(w["n"]), B * T, D, v.ln_eps, stream())
-            self.gemm(w["n"], blk["attn.qkv.weight"], w["qkv"], bias=blk["attn.qkv.bias"])
+            self.gemm(w["n"], blk["attn.qkv.weight"], w["qkv"], bias=blk["attn.qkv.bias"], scratch=sc)
             call("emx_attn_fwd", ptr(w["qkv"]), ptr(w["att"]), B, T, v.num_heads, hd, 0, hd**-0.5, stream())
-            self.gemm(w["att"], blk["attn.proj.weight"], w["tok"], bias=blk["attn.proj.bias"], ls=blk.get("ls1.scale_factor"), resid=w["tok"])
+            self.gemm(w["att"], blk["attn.proj.weight"], w["tok"], bias=blk["attn.proj.bias"], ls=blk.get("ls1.scale_factor"), resid=w["tok"], scratch=sc)
             call("emx_layernorm", ptr(w["tok"]), ptr(blk["norm2.weight"]), ptr(blk["norm2.bias"]), ptr(w["n"]), B * T, D, v.ln_eps, stream())
-            self.gemm(w["n"], blk["mlp.fc1.weight"], w["hid"], bias=blk["mlp.fc1.bias"], flags=EPI_GELU)
-            self.gemm(w["hid"], blk["mlp.fc2.weight"], w["tok"], bias=blk["mlp.fc2.bias"], ls=blk.get("ls2.scale_factor"), resid=w["tok"])
+            self.gemm(w["n"], blk["mlp.fc1.weight"], w["hid"], bias=blk["mlp.fc1.bias"], flags=EPI_GELU, scratch=sc)
+            self.gemm(w["hid"], blk["mlp.fc2.weight"], w["tok"], bias=blk["mlp.fc2.bias"], ls=blk.get("ls2.scale_factor"), resid=w["tok"], scratch=sc)
         call("emx_vit_gather_features", ptr(w["tok"]), ptr(ws["feats"]), B, P, v.num_prefix_tokens, D, cfg.vision_embed_dim, col0, stream())
 
     def _projector(self, ws: dict) -> None:
         """fc1 -> GELU -> fc2 -> GELU -> fc3  (modeling_prismatic.py:152-156)"""
         pj = self.proj
-        self.gemm(ws["feats"], pj["fc1.weight"], ws["p1"], bias=pj["fc1.bias"], flags=EPI_GELU)
-        self.gemm(ws["p1"], pj["fc2.weight"], ws["p2"], bias=pj["fc2.bias"], flags=EPI_GELU)
-        self.gemm(ws["p2"], pj["fc3.weight"], ws["patches"], bias=pj["fc3.bias"])
+        self.gemm(ws["feats"], pj["fc1.weight"], ws["p1"], bias=pj["fc1.bias"], flags=EPI_GELU, scratch=self._scratch[0])
+        self.gemm(ws["p1"], pj["fc2.weight"], ws["p2"], bias=pj["fc2.bias"], flags=EPI_GELU, scratch=self._scratch[0])
+        self.gemm(ws["p2"], pj["fc3.weight"], ws["patches"], bias=pj["fc3.bias"], scratch=self._scratch[0])
 
     def _layer_cache(self, cache: torch.Tensor, layer: int) -> int:
         return cache.data_ptr() + layer * self.layer_cache_bytes
@@ -278,15 +285,15 @@ class Engine:
         tbl = self._slot_table(slot)
         for l in range(L):
             call("emx_rmsnorm", ptr(ws["x"]), ptr(self.ln1[l]), ptr(ws["n"]), B * S, H, t.rms_norm_eps, stream())
-            self.gemm(ws["n"], self.w_qkv[l], ws["qkv"])
+            self.gemm(ws["n"], self.w_qkv[l], ws["qkv"], scratch=self._scratch[0])
             call("emx_rope_kvstore", ptr(ws["qkv"]), B, S, heads, hd, ptr(self.cos_tab), ptr(self.sin_tab), 0,
                  self._layer_cache(self.k_cache, l), self._layer_cache(self.v_cache, l), tbl,
                  self.pages_per_seq, self.PAGE, stream())  # fmt: skip
             call("emx_attn_fwd", ptr(ws["qkv"]), ptr(ws["att"]), B, S, heads, hd, 1, hd**-0.5, stream())
-            self.gemm(ws["att"], self.w_o[l], ws["x"], resid=ws["x"])
+            self.gemm(ws["att"], self.w_o[l], ws["x"], resid=ws["x"], scratch=self._scratch[0])
             call("emx_rmsnorm", ptr(ws["x"]), ptr(self.ln2[l]), ptr(ws["n"]), B * S, H, t.rms_norm_eps, stream())
-            self.gemm(ws["n"], self.w_gateup[l], ws["h"], flags=EPI_SWIGLU)
-            self.gemm(ws["h"], self.w_down[l], ws["x"], resid=ws["x"])
+            self.gemm(ws["n"], self.w_gateup[l], ws["h"], flags=EPI_SWIGLU, scratch=self._scratch[0])
+            self.gemm(ws["h"], self.w_down[l], ws["x"], resid=ws["x"], scratch=self._scratch[0])
         # lm_head on the LAST position only (the reference computes all S rows and discards S-1 of them)
         x3 = ws["x"].view(B, S, H)
         for b in range(B):

@@ -38,6 +38,14 @@ const char* emx_arch(void);
 #define EMX_EPI_SWIGLU 2
 int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const void* bias,
                   const void* layerscale, const void* resid, int ldr, int resid_mod, int flags, emx_stream_t stream);
+/* Same, with a caller-owned scratch buffer that allows split-K for the small-M problems of a bs = 1 request whose output tiles do not
+ * fill the machine (Llama o_proj / down_proj at M = 296, ViT proj / fc2 at M ~ 260): 16-byte aligned device memory, ZERO-INITIALISED once
+ * (its first 4096 bytes are self-resetting per-tile arrival counters; the rest holds fp32 partial tiles), at least
+ * 4096 + tiles * splits * 128 * 128 * 4 bytes or the call does not split; not to be shared by GEMMs that may run concurrently (one per
+ * stream / graph branch). The partials are added in a fixed order: results do not depend on which CTA finishes last. */
+int emx_gemm_bf16_ws(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const void* bias,
+                     const void* layerscale, const void* resid, int ldr, int resid_mod, int flags, void* workspace, long workspace_bytes,
+                     emx_stream_t stream);
 
 /* ---- normalisation ------------------------------------------------------------------------------------------
  * LayerNorm (ViT blocks, eps 1e-6; ATen vectorized_layer_norm in the reference, via timm Block.norm1/norm2) and

@@ -85,6 +85,42 @@ def test_gemm_cta_pair(lib, M, N, K, monkeypatch):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("M,N,K", [(296, 4096, 4096), (261, 1024, 4096), (256, 1152, 1152), (296, 4096, 11008), (130, 136, 1032), (5, 520, 2048)])
+def test_gemm_split_k(lib, M, N, K, monkeypatch):
+    """emx_gemm_bf16_ws: small-M problems whose 128 x 128 tiles do not fill the machine are split along K (work item = tile x k-range, fp32
+    partials in the caller's scratch, the last CTA of a tile adds them in split order and runs the fused epilogue). Same tolerances as the
+    un-split kernel, every epilogue kind, and bit-identical results from run to run (the reduction order is fixed)."""
+    from emmax_b200._lib import EPI_GELU, EPI_SWIGLU
+    from emmax_b200.engine import Engine
+
+    monkeypatch.setenv("EMX_GEMM_SPLITK", "1")  # off by default: measured slower than the un-split kernel (profiles/r02_splitk_negative.txt)
+    scratch = torch.zeros(32 << 20, dtype=torch.uint8, device="cuda")
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    acc = a.float() @ w.float().T
+    out = torch.zeros(M, N, dtype=BF, device="cuda")
+    Engine.gemm(a, w, out, scratch=scratch)
+    assert_close_bf16(out, acc.to(BF), name=f"split-K gemm {M}x{N}x{K}")
+    again = torch.zeros_like(out)
+    Engine.gemm(a, w, again, scratch=scratch)
+    assert torch.equal(out, again), "split-K result differs from run to run"
+    plain = torch.zeros_like(out)
+    Engine.gemm(a, w, plain)  # un-split kernel: same product, different summation order
+    assert_close_bf16(out, plain, name="split-K vs un-split")
+    bias, ls, res = rnd(N, seed=5), rnd(N, seed=6).abs(), rnd(M, N, seed=7)
+    Engine.gemm(a, w, out, bias=bias, flags=EPI_GELU, scratch=scratch)
+    assert_close_bf16(out, torch.nn.functional.gelu((acc + bias.float()).to(BF)), name="split-K bias+gelu")
+    buf = res.clone()
+    Engine.gemm(a, w, buf, bias=bias, ls=ls, resid=buf, scratch=scratch)
+    want = ((acc + bias.float()).to(BF) * ls).to(BF) + res
+    assert_close_bf16(buf, want, frac=0.99999, name="split-K bias+ls+resid", scale=want.abs() + acc.abs() + res.abs().float() + 1)
+    out2 = torch.zeros(M, N // 2, dtype=BF, device="cuda")
+    Engine.gemm(a, w, out2, flags=EPI_SWIGLU, scratch=scratch)
+    gu = acc.to(BF)
+    assert_close_bf16(out2, torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2], frac=0.99999, name="split-K swiglu")
+    assert int(scratch[:4096].view(torch.int32).abs().sum()) == 0, "tile counters must be back at zero after every launch"
+    torch.cuda.synchronize()
+
+
 def test_gemm_epilogues(lib):
     from emmax_b200._lib import EPI_GELU, EPI_SWIGLU
     from emmax_b200.engine import Engine
