@@ -424,7 +424,7 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ in, __nv_bflo
 using namespace emx;
 
 extern "C" const char* emx_last_error(void) { return g_err; }
-extern "C" int emx_abi_version(void) { return 3; }
+extern "C" int emx_abi_version(void) { return 4; }
 extern "C" const char* emx_arch(void) { return "sm_100a"; }
 
 #define BF(p) static_cast<const __nv_bfloat16*>(p)
