@@ -704,7 +704,7 @@ def run_ours(args) -> None:
         if extras_on:
             # short legs of the other BASELINE configs + the GPU comparator, so that the driver's one default run carries them too
             extras = {}
-            for name, fn in (("c5", lambda: measure_c5(cfg, model, proc, script, dev, 1, 0, 2, 3, timed, lambda new: None)),
+            for name, fn in (("c5", lambda: measure_c5(cfg, model, proc, script, dev, 1, 0, 4, 3, timed, lambda new: None)),
                              ("c3", lambda: measure_c3(cfg, model, proc, dev, 3, 3, timed)),
                              ("gpu_comparator", lambda: gpu_comparator_sample(cfg, sd, script, dev, steps=2, warmup=1))):  # fmt: skip
                 try:
