@@ -503,17 +503,11 @@ static int launch_attn_tc(const __nv_bfloat16* in, __nv_bfloat16* o, int B, int 
   constexpr int SLABS = (HD + 63) / 64;
   const int keys_pad = (T + 63) / 64 * 64;
   const int smem = SLABS * ATC_QT * 128 + (SLABS > 2 ? SLABS : 2) * keys_pad * 128 + SLABS * keys_pad * 128 + 64 + 1024;
-  bool* attr_set = device_attr_flag(ATTR_ATTN_TC);
+  bool* attr_set = device_attr_flag(HD == 64 ? ATTR_ATTN_TC64 : HD == 72 ? ATTR_ATTN_TC72 : ATTR_ATTN_TC128);  // per device and instantiation
   if (!attr_set) return -2;
-  // the opt-in is per kernel instantiation as well as per device: 3 head dims share the slot through a bit mask
-  static_assert(sizeof(bool) == 1, "");
-  static unsigned char done[kMaxDevices] = {};
-  int dev = 0;
-  EMX_CHECK_CUDA(cudaGetDevice(&dev));
-  const unsigned char bit = HD == 64 ? 1 : HD == 72 ? 2 : 4;
-  if (dev < kMaxDevices && !(done[dev] & bit)) {
+  if (!*attr_set) {
     EMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    done[dev] |= bit;
+    *attr_set = true;
   }
   attn_fwd_tc_kernel<HD><<<dim3((T + ATC_QT - 1) / ATC_QT, heads, B), 160, smem, s>>>(tm, o, T, heads, causal, scale);
   return 0;
