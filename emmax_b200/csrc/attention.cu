@@ -292,11 +292,12 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_mma_kernel(const __nv_bf
 // One CTA per (128-query tile, head, batch item). The sequences of this path are short (ViT 256 / 261 tokens, prefill 256 + prompt),
 // so a query tile's WHOLE score row fits in tensor memory next to the output accumulator (<= 384 fp32 score columns + <= 128 output
 // columns of the 512): no online softmax, no accumulator rescaling.
-//   control warp (warp 4): TMA loads (4-D tensor map over the packed qkv buffer {head_dim, 3*heads, T, B}: rows beyond T and columns
+//   control warp (warp 8): TMA loads (4-D tensor map over the packed qkv buffer {head_dim, 3*heads, T, B}: rows beyond T and columns
 //     beyond head_dim are OUT OF BOUNDS and arrive as zeros, which is what pads head_dim 72 to 80 and the key count to a multiple of
 //     64), then S = Q K^T as tcgen05.mma M=128 x N<=256 x K=16 steps (Q and K both K-major, 128-byte swizzle), later O = P V with P as
 //     the K-major A operand and V — stored [key][head_dim], i.e. N-contiguous — as an MN-major B operand.
-//   warps 0..3: thread i owns query row i (TMEM lane i): pass 1 reads the score row (tcgen05.ld) for the row maximum, pass 2 forms
+//   warps 0..7: thread (w mod 4, lane) owns query row 32 (w mod 4) + lane (= its TMEM lane) and the column half w / 4 of it (the two
+//     halves exchange their row maximum and row sum through shared memory): pass 1 reads the score row (tcgen05.ld) for the row maximum, pass 2 forms
 //     p = exp2((s - max) * scale * log2 e) in fp32, sums it in fp32, rounds p to bf16 (as flash-attn) and writes it into shared memory
 //     in the swizzled K-major layout the tensor core reads (the K tile is dead by then: P overwrites it); after the PV commit the
 //     same thread scales its output row by 1 / sum and stores it.
@@ -304,6 +305,9 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_mma_kernel(const __nv_bf
 constexpr int ATC_QT = 128;        // queries per CTA = TMEM lanes
 constexpr int ATC_MAX_KEYS = 384;  // score columns that fit next to the output accumulator
 constexpr int ATC_O_COL = 384;     // TMEM column of the output accumulator
+constexpr int ATC_SWARPS = 8;      // softmax / epilogue warps: two per TMEM lane quarter, each taking half of the row's columns
+constexpr int ATC_CTRL = ATC_SWARPS;              // warp id of the control warp (TMA + MMA issue + TMEM allocation)
+constexpr int ATC_THREADS = (ATC_SWARPS + 1) * 32;
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
@@ -330,7 +334,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 template <int HD>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(ATC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int T, int heads, int causal, float scale) {
   constexpr int HDP = (HD + 15) / 16 * 16;  // contraction length of Q K^T and N of P V (72 -> 80)
   constexpr int SLABS = (HD + 63) / 64;     // 64-column (128-byte) slabs of a q / k / v row
@@ -344,6 +348,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + SLABS * keys_pad * 128);
   uint64_t *bar_qk = bars, *bar_v = bars + 1, *bar_s = bars + 2, *bar_p = bars + 3, *bar_o = bars + 4;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+  float* s_mx = reinterpret_cast<float*>(sQ);  // [2][128] partial row maxima of the two column halves: over the Q tile, dead once S is complete
+  float* s_l = s_mx + 2 * ATC_QT;              // [2][128] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATC_QT, head = blockIdx.y, b = blockIdx.z;
@@ -352,10 +358,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
   const int keys_used = (keys_need + 15) / 16 * 16;         // score columns computed (multiple of the MMA N / K granule)
   const int key_boxes = (keys_need + 63) / 64;              // 64-row TMA boxes of K and of V
 
-  if (warp == 4) {
+  if (warp == ATC_CTRL) {
     if (lane == 0) {
       prefetch_tmap(&tm);
-      mbar_init(bar_qk, 1), mbar_init(bar_v, 1), mbar_init(bar_s, 1), mbar_init(bar_p, ATC_QT), mbar_init(bar_o, 1);
+      mbar_init(bar_qk, 1), mbar_init(bar_v, 1), mbar_init(bar_s, 1), mbar_init(bar_p, ATC_SWARPS * 32), mbar_init(bar_o, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -366,7 +372,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 4) {
+  if (warp == ATC_CTRL) {
     if (lane == 0) {
       // ---- loads: Q and K first (one barrier), V behind them
       mbar_arrive_expect_tx(bar_qk, static_cast<uint32_t>(SLABS * (2 + key_boxes) * 64 * 128));
@@ -407,15 +413,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
     }
     __syncwarp();
   } else {
-    const int row = warp * 32 + lane, q = q0 + row;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int qt = warp & 3, half = warp >> 2;  // TMEM lane quarter (warp id mod 4) and which half of the columns this warp covers
+    const int row = qt * 32 + lane, q = q0 + row;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(qt * 32) << 16);
     const int n_valid = causal ? min(q + 1, T) : T;  // keys [0, n_valid) count for this query
     const float sl2 = scale * 1.4426950408889634f;
+    const int nch = (keys_used + 31) / 32, ch_split = (nch + 1) / 2;  // 32-column chunks of the score row: [0, ch_split) | [ch_split, nch)
+    const int cb = half ? ch_split * 32 : 0, ce = half ? keys_used : min(keys_used, ch_split * 32);
     mbar_wait(bar_s, 0);
     tc_fence_after();
-    // pass 1: row maximum of the raw scores
+    // pass 1: row maximum of the raw scores (own half, then both halves through shared memory)
     float mx = -INFINITY;
-    for (int c0 = 0; c0 < keys_used; c0 += 32) {
+    for (int c0 = cb; c0 < ce; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(trow + c0, r);
       tmem_ld_wait();
@@ -423,10 +432,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
       for (int j = 0; j < 32; ++j)
         if (c0 + j < n_valid) mx = fmaxf(mx, __uint_as_float(r[j]));
     }
+    s_mx[half * ATC_QT + row] = mx;
+    asm volatile("bar.sync 1, %0;" ::"n"(ATC_SWARPS * 32) : "memory");
+    mx = fmaxf(s_mx[row], s_mx[ATC_QT + row]);
     const float m2 = mx * sl2;
     // pass 2: p = exp2(s * sl2 - m2), fp32 row sum, bf16 P into the swizzled K-major A tile (slab = 64 keys, row pitch 128 B)
     float l = 0.f;
-    for (int c0 = 0; c0 < keys_used; c0 += 32) {
+    for (int c0 = cb; c0 < ce; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(trow + c0, r);
       tmem_ld_wait();
@@ -444,16 +456,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
       for (int ch = 0; ch < 4; ++ch)
         *reinterpret_cast<uint4*>(prow + (((ch0 + ch) ^ (row & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
     }
+    s_l[half * ATC_QT + row] = l;
     fence_proxy_async();  // generic-proxy stores of P -> visible to the tensor core's async-proxy reads
     tc_fence_before();
     mbar_arrive(bar_p);
-    // epilogue: O row / l
+    asm volatile("bar.sync 1, %0;" ::"n"(ATC_SWARPS * 32) : "memory");  // both partial row sums are visible
+    // epilogue: O row / l, own half of the output columns (32-column chunks)
+    const float inv = 1.0f / (s_l[row] + s_l[ATC_QT + row]);
+    constexpr int NCO = (HDP + 31) / 32, CO_SPLIT = (NCO + 1) / 2;
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    const float inv = 1.0f / l;
     __nv_bfloat16* orow = out + (static_cast<long>(b) * T + q) * Hd + head * HD;
 #pragma unroll
-    for (int c0 = 0; c0 < HDP; c0 += 32) {
+    for (int cc = 0; cc < CO_SPLIT; ++cc) {
+      const int c0 = (half ? CO_SPLIT + cc : cc) * 32;
+      if (c0 >= HDP || (half && CO_SPLIT + cc >= NCO)) break;  // warp-uniform
       uint32_t r[32];
       tmem_ld_32x32(trow + ATC_O_COL + c0, r);
       tmem_ld_wait();
@@ -471,7 +488,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == ATC_CTRL) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -509,7 +526,7 @@ static int launch_attn_tc(const __nv_bfloat16* in, __nv_bfloat16* o, int B, int 
     EMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     *attr_set = true;
   }
-  attn_fwd_tc_kernel<HD><<<dim3((T + ATC_QT - 1) / ATC_QT, heads, B), 160, smem, s>>>(tm, o, T, heads, causal, scale);
+  attn_fwd_tc_kernel<HD><<<dim3((T + ATC_QT - 1) / ATC_QT, heads, B), ATC_THREADS, smem, s>>>(tm, o, T, heads, causal, scale);
   return 0;
 }
 
