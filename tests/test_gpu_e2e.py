@@ -442,3 +442,41 @@ def test_prompt_shape_cache_is_bounded(tiny):
         assert len(eng._ws) <= eng.MAX_CACHED_SHAPES and len(eng._graphs) <= eng.MAX_CACHED_SHAPES
     assert (1, input_ids.shape[1]) not in eng._ws, "the first shape should have been evicted by now"
     assert int(eng.prefill(input_ids.cuda(), pv)["first"][0]) == first
+
+
+def test_native_run_dir_checkpoint_generates_the_same_ids(tmp_path):
+    """SURVEY.md §8 f1 on the GPU: the same seeded weights saved the way the reference's native trainer saves them
+    (`<run>/checkpoints/*.pt` with {"model": {"vision_backbone", "projector", "llm_backbone"}} in native parameter names, `config.json`,
+    `dataset_statistics.json`; prismatic/models/load.py:122-228) and loaded with `load_vla` decode to the same greedy ids and the same
+    action as the model built directly from the HF-named state dict."""
+    import json
+    import warnings
+
+    from emmax_b200 import OpenVLAForActionPrediction, SyntheticLlamaTokenizer, load_vla, tiny_config
+    from emmax_b200.load import to_native_state_dict
+    from emmax_b200.synthetic import default_script, make_state_dict
+
+    cfg = tiny_config()
+    tok = SyntheticLlamaTokenizer()
+    script = default_script(tok, 40, seed=3)
+    prev = 29871
+    sd = make_state_dict(cfg, seed=17, device="cpu", script=script, script_prev=prev)
+    run = tmp_path / "emma-x-run"
+    (run / "checkpoints").mkdir(parents=True)
+    torch.save({"model": to_native_state_dict(sd)}, run / "checkpoints" / "latest-checkpoint.pt")
+    with open(run / "config.json", "w") as f:
+        json.dump({"vla": {"base_vlm": "prism-dinosiglip-224px+7b", "vla_id": "emma-x"}}, f)
+    with open(run / "dataset_statistics.json", "w") as f:
+        json.dump(cfg.norm_stats, f)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # (no tokenizer files in the run dir: the synthetic tokenizer warning is tested on the CPU)
+        native = load_vla(run / "checkpoints" / "latest-checkpoint.pt", config=cfg).to("cuda")
+    direct = OpenVLAForActionPrediction(cfg, dict(sd)).to("cuda")
+    ids = torch.tensor([[1] + np.random.default_rng(5).integers(3, 300, 30).tolist() + [prev]], device="cuda")
+    pv = torch.randn((1, 6, 224, 224), generator=torch.Generator(device="cuda").manual_seed(9), device="cuda").to(BF)
+    a, _ = native.engine.generate(ids, pv, 40, eos_token_id=tok.eos_token_id)
+    b, _ = direct.engine.generate(ids, pv, 40, eos_token_id=tok.eos_token_id)
+    assert a.cpu().tolist() == script and torch.equal(a, b)
+    act_a = native.predict_action(input_ids=ids, pixel_values=pv, unnorm_key=None, do_sample=False)
+    act_b = direct.predict_action(input_ids=ids, pixel_values=pv, unnorm_key=None, do_sample=False)
+    assert np.array_equal(act_a, act_b)
