@@ -78,6 +78,14 @@ def decode_bytes(cfg, ctx: int) -> int:
     return weights + kv_row * ctx + kv_row
 
 
+def c2_config(world: int) -> dict:
+    """The headline configuration block, identical in our arm and in the reference arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "prompt_ids": PROMPT_LEN, "prefill_positions": PROMPT_LEN + 256, "new_tokens": N_NEW,
+            "weights": "seeded random-init, full Emma-X architecture (DINOv2-L/14-reg4 + SigLIP-so400m/14 + Llama-2-7B)",
+            "parallelism": f"replicas x{world}" + (" + 1 NCCL all-gather of action tokens per step" if world > 1 else ""),
+            "l2": "per-step inputs (13.2 GB of weights streamed per token) exceed the 126 MB L2; no flush needed"}  # fmt: skip
+
+
 def batch_decode_bytes(cfg, ctxs) -> int:
     """One batched decode launch over the sequences with cached contexts `ctxs`: the weights once + every sequence's KV (SURVEY.md §8d:
     13,214,679,040 + sum_i 524,288 ctx_i + b 524,288)."""
@@ -216,8 +224,7 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": "actions/sec (7-DoF)", "value": value, "unit": "actions/s", "n_gpus": args.gpus,
         "steps": len(samples), "warmup": warm, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "prompt_ids": PROMPT_LEN, "prefill_positions": PROMPT_LEN + 256, "new_tokens": N_NEW,
-                   "weights": "seeded random-init, full Emma-X architecture", "device": "host CPU"},
+        "config": c2_config(args.gpus), "device": "host CPU",
         "cpu_baseline": {"value": value, "unit": "actions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -345,8 +352,7 @@ def run_reference_gpu(args) -> None:
     line = {"impl": "reference-gpu", "metric": "actions/sec (7-DoF)", "value": r["value"], "unit": "actions/s", "n_gpus": 1,
             "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "prompt_ids": PROMPT_LEN, "prefill_positions": PROMPT_LEN + 256, "new_tokens": N_NEW,
-                       "weights": "seeded random-init, full Emma-X architecture", "device": torch.cuda.get_device_name(dev)},
+            "config": c2_config(args.gpus), "device": torch.cuda.get_device_name(dev),
             "clocks": sampler.stop(), "gpu_comparator": r, "gpu_launches": 0,
             "e2e": {"value": r["value"], "unit": "actions/s", "h2d_bytes_per_step": 6 * 224 * 224 * 2 + PROMPT_LEN * 8, "d2h_bytes_per_step": (PROMPT_LEN + N_NEW) * 8}}  # fmt: skip
     print(json.dumps(line), flush=True)
@@ -685,10 +691,7 @@ def run_ours(args) -> None:
             "metric": "actions/sec (7-DoF)", "value": value, "unit": "actions/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "prompt_ids": PROMPT_LEN, "prefill_positions": PROMPT_LEN + 256, "new_tokens": N_NEW,
-                       "weights": "seeded random-init, full Emma-X architecture (DINOv2-L/14-reg4 + SigLIP-so400m/14 + Llama-2-7B)",
-                       "parallelism": f"replicas x{world}" + (" + 1 NCCL all-gather of action tokens per step" if world > 1 else ""),
-                       "l2": "per-step inputs (13.2 GB of weights streamed per token) exceed the 126 MB L2; no flush needed"},
+            "config": c2_config(world),
             "clocks": clocks, "parity": parity,
             "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
