@@ -43,7 +43,10 @@ struct GemmCfg {
 // Tile order: groups of kGroupM consecutive M tiles; inside a group the M index runs fastest, then N. The CTAs that run concurrently
 // (one wave = 148 tiles or 74 pair tiles) then share ~8 A row blocks and ~9-18 W row blocks (a few tens of MB: L2-resident) instead of
 // ALL of A (77 MB at M = 9472, K = 4096) against two W blocks, which re-streamed A from HBM once per pair of N tiles.
-constexpr int kGroupM = 8;
+#ifndef EMX_GROUP_M
+#define EMX_GROUP_M 8
+#endif
+constexpr int kGroupM = EMX_GROUP_M;
 __device__ __forceinline__ void tile_coords(int tile, int mt, int nt, int& mi, int& ni) {
   const int per_group = kGroupM * nt;
   const int g = tile / per_group, r = tile - g * per_group;
@@ -519,7 +522,10 @@ gemm_tn_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // ---------------------------------------------------------------------------------------------------------------
 struct PairCfg {
   static constexpr int BN = 256;
-  static constexpr int kStages = 6;
+#ifndef EMX_PAIR_STAGES
+#define EMX_PAIR_STAGES 6
+#endif
+  static constexpr int kStages = EMX_PAIR_STAGES;
   static constexpr int kABytes = BM * BK * 2;        // this CTA's 128 A rows
   static constexpr int kBBytes = (BN / 2) * BK * 2;  // this CTA's 128 W rows
   static constexpr int kStageBytes = kABytes + kBBytes;
