@@ -98,6 +98,60 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
 }
 
+// One WARP per row for the ViT widths (dim <= 2048): the row lives in registers (one read of x), the two statistics are warp-shuffle
+// reductions, no block barrier; 8 rows per 256-thread block. Same formula as layernorm_kernel (two-pass variance around the mean).
+constexpr int LN_MAXV = 8;  // 16-byte vectors per lane: dim <= 32 * 8 * 8 = 2048
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                             const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, int rows,
+                                                             int dim, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * dim);
+  const int nv = dim >> 3;
+  uint4 v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < nv ? xr[i] : make_uint4(0, 0, 0, 0);
+    s += bf16_lo(v[k].x) + bf16_hi(v[k].x) + bf16_lo(v[k].y) + bf16_hi(v[k].y) + bf16_lo(v[k].z) + bf16_hi(v[k].z) + bf16_lo(v[k].w) + bf16_hi(v[k].w);
+  }
+  const float mean = warp_sum(s) / dim;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    if (lane + 32 * k < nv) {
+      const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(u[j]) - mean, c = bf16_hi(u[j]) - mean;
+        ss += a * a + c * c;
+      }
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) / dim + eps);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const uint4* br = reinterpret_cast<const uint4*>(b);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * dim);
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) {
+      const uint4 ww = wr[i], bb = br[i];
+      const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, uw[4] = {ww.x, ww.y, ww.z, ww.w}, ub[4] = {bb.x, bb.y, bb.z, bb.w};
+      uint32_t r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = (bf16_lo(u[j]) - mean) * rstd * bf16_lo(uw[j]) + bf16_lo(ub[j]);
+        const float hi = (bf16_hi(u[j]) - mean) * rstd * bf16_hi(uw[j]) + bf16_hi(ub[j]);
+        r[j] = pack_bf16(lo, hi);
+      }
+      yr[i] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
 // ---- RMSNorm (LlamaRMSNorm): n = bf16(x * rsqrt(mean(x^2) + eps)); y = bf16(w * n) ----------------------------------
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                       __nv_bfloat16* __restrict__ y, int dim, float eps) {
@@ -432,7 +486,10 @@ extern "C" const char* emx_arch(void) { return "sm_100a"; }
 
 extern "C" int emx_layernorm(const void* x, const void* w, const void* b, void* y, int rows, int dim, float eps, cudaStream_t s) {
   EMX_REQUIRE(rows > 0 && dim % 8 == 0, "emx_layernorm: rows=%d dim=%d (dim must be a multiple of 8)", rows, dim);
-  layernorm_kernel<<<rows, 256, 0, s>>>(BF(x), BF(w), BF(b), BFM(y), dim, eps);
+  if (dim <= 32 * 8 * LN_MAXV)
+    layernorm_warp_kernel<<<(rows + 7) / 8, 256, 0, s>>>(BF(x), BF(w), BF(b), BFM(y), rows, dim, eps);
+  else
+    layernorm_kernel<<<rows, 256, 0, s>>>(BF(x), BF(w), BF(b), BFM(y), dim, eps);
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
