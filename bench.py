@@ -511,6 +511,41 @@ def measure_c3(cfg, model, proc, dev, K: int, W: int, timed) -> dict:
     }  # fmt: skip
 
 
+def predict_action_latency(cfg, model, proc, sd, script, dev, n: int = 20, warm: int = 3) -> dict:
+    """Latency of the OpenVLA-style entry point `predict_action` (modeling_prismatic.py:506-537: 7 action tokens after the prompt, the call
+    experiments/robot/openvla_utils.py:169 and the SimplerEnv policy make every control step): wall clock per call through the public API
+    from a pinned host frame (H2D, GPU image transform, prefill graph, 7 decode launches, device de-tokeniser, D2H of the action), next to
+    the same 7-token request through the HF-generate + flash-attn restatement on the same GPU."""
+    import time
+
+    image, ids = synthetic_request(0)
+    frame, h_ids = torch.from_numpy(np.asarray(image).copy()).pin_memory(), ids.pin_memory()
+
+    def call():
+        pv = proc.image_processor.preprocess_device(frame.to(dev, non_blocking=True))
+        return model.predict_action(input_ids=h_ids.to(dev, non_blocking=True), pixel_values=pv, unnorm_key=None, do_sample=False)
+
+    for _ in range(warm):
+        call()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        a = call()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    out = {"what": "predict_action (7 action tokens) per call, wall clock, public API from a pinned host frame", "calls": n,
+           "ms_p50": ts[n // 2], "ms_p10": ts[n // 10], "ms_p90": ts[(9 * n) // 10], "hz_p50": 1e3 / ts[n // 2],
+           "action": [round(float(x), 6) for x in a]}  # fmt: skip
+    try:
+        comp = gpu_comparator_sample(cfg, sd, script, dev, steps=5, warmup=2, n_new=7)
+        out["gpu_comparator_ms"] = comp["ms_per_step"]
+        out["ours_over_comparator"] = comp["ms_per_step"] / ts[n // 2]
+    except Exception as e:  # noqa: BLE001
+        out["gpu_comparator_ms"] = f"failed: {type(e).__name__}: {e}"
+    return out
+
+
 # =====================================================================================================================
 # our arm
 # =====================================================================================================================
@@ -709,7 +744,8 @@ def run_ours(args) -> None:
             extras = {}
             for name, fn in (("c5", lambda: measure_c5(cfg, model, proc, script, dev, 1, 0, 4, 3, timed, lambda new: None)),
                              ("c3", lambda: measure_c3(cfg, model, proc, dev, 3, 3, timed)),
-                             ("gpu_comparator", lambda: gpu_comparator_sample(cfg, sd, script, dev, steps=2, warmup=1))):  # fmt: skip
+                             ("gpu_comparator", lambda: gpu_comparator_sample(cfg, sd, script, dev, steps=2, warmup=1)),
+                             ("predict_action", lambda: predict_action_latency(cfg, model, proc, sd, script, dev))):  # fmt: skip
                 try:
                     extras[name] = fn()
                 except Exception as e:  # the headline line must survive a problem in an extra leg
