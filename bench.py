@@ -439,6 +439,20 @@ def measure_c5(cfg, model, proc, script, dev, world: int, rank: int, K: int, W: 
     s_bytes = ls["launches"] * (decode_bytes(cfg, 0) - kv_tok) + kv_tok * (ls["kv_reads"] + ls["kv_writes"])
     s_dec_ms = sum(e0.elapsed_time(e1) for e0, e1 in ls["decode_events"])
     s_achieved = s_bytes / max(s_dec_ms, 1e-9) / 1e6
+    # ---- the same stream admitted longest-first (token limits are known up front in an offline batch): the tail of the stream is then
+    # made of 128-token requests and the slots drain together (emmax_b200.engine.admission_order)
+    def step_stream_lpt(i: int) -> None:
+        outs[0] = eng.serve(stream if i >= 1 else warm, eos_token_id=2, use_graph=False, order="longest_first")
+        if i >= 1:
+            for g0 in range(0, len(stream), B):
+                tick_gather(outs[0][g0 : g0 + B])
+
+    lpt_ms, _ = timed(step_stream_lpt, 1, 1)
+    for r, new_r in enumerate(outs[0]):
+        if new_r.cpu().tolist() != list(script[: stream[r][2]]):
+            raise SystemExit(f"PARITY GATE FAILED (c5, continuous batching, longest first): request {r} differs from the planted script")
+    lpt = {"value": world * len(stream) / (lpt_ms / 1e3), "unit": "actions/s", "total_ms": lpt_ms, "decode_launches": eng.last_serve["launches"],
+           "over_static_batches": (world * len(stream) / (lpt_ms / 1e3)) / value}  # fmt: skip
     continuous = {
         "what": "the same K x 8 requests served as ONE stream through the 8 sequence slots (Engine.serve, continuous batching: a finished slot is "
                 "refilled with the next request at once); inputs resident in HBM; every request's ids checked against the planted script",
@@ -447,6 +461,7 @@ def measure_c5(cfg, model, proc, script, dev, world: int, rank: int, K: int, W: 
         "roofline": {"bound": "hbm", "kernel": "decode_batch_kernel", "achieved": s_achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": s_achieved / hbm_peak, "bytes_per_launch": s_bytes / max(ls["launches"], 1), "share_of_stream": s_dec_ms / stream_ms},
         "over_static_batches": (world * len(stream) / (stream_ms / 1e3)) / value,
+        "longest_first": lpt,
     }  # fmt: skip
     return {
         "metric": "actions/sec (7-DoF)", "value": value, "unit": "actions/s", "ms_per_step": total_ms / K, "steps": K, "warmup": W,

@@ -36,6 +36,18 @@ def _on_engine_device(fn):
     return wrapper
 
 
+def admission_order(limits, order: str = "fifo") -> List[int]:
+    """Order in which `Engine.serve` admits a stream of requests into the sequence slots. "fifo": arrival order. "longest_first": largest
+    token limit first, ties in arrival order (longest-processing-time-first list scheduling: with S slots the stream then ends at most one
+    SHORTEST request after the ideal sum(limits) / S launches, instead of one longest request after it)."""
+    idx = list(range(len(limits)))
+    if order == "fifo":
+        return idx
+    if order == "longest_first":
+        return sorted(idx, key=lambda r: -int(limits[r]))  # sorted() is stable: ties keep arrival order
+    raise ValueError(f"order must be 'fifo' or 'longest_first', got {order!r}")
+
+
 def _ceil_to(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -444,14 +456,18 @@ class Engine:
 
     @_on_engine_device
     @torch.no_grad()
-    def serve(self, requests, eos_token_id: Optional[int] = 2, use_graph: bool = True, poll_every: int = 32) -> List[torch.Tensor]:
+    def serve(self, requests, eos_token_id: Optional[int] = 2, use_graph: bool = True, poll_every: int = 32,
+              order: str = "fifo") -> List[torch.Tensor]:
         """Continuous batching over the sequence slots of the batched decode kernel: a stream of independent requests
         `(input_ids [1, n], pixel_values [1, 6, h, w], max_new_tokens)` is decoded min(8, max_batch) at a time, and a slot whose sequence
         has reached its token limit (or EOS) is refilled with the next request at once — prefilled straight into that slot's KV pages
         (same-length prompts admitted together share one batched prefill) — instead of idling until the longest sequence of its batch is
         done. With BASELINE.json configs[4]'s mix of 128- and 512-token requests a static batch of 8 runs half empty for 3/4 of its
         launches; here every launch carries 8 live sequences. Per-sequence results are those of `generate` (same kernels, same state
-        machine: position, limit and EOS are per slot). Returns the generated ids per request, in request order."""
+        machine: position, limit and EOS are per slot). Returns the generated ids per request, in request order.
+        `order`: "fifo" admits requests in arrival order; "longest_first" (an offline batch whose token limits are known up front) admits
+        the requests with the largest limits first, so that the tail of the stream is made of short requests and the slots drain
+        together instead of the last long request decoding alone (see `admission_order`)."""
         MB = MAX_DECODE_BATCH
         S = min(MB, self.max_batch)
         P = self.config.num_patches
@@ -463,6 +479,7 @@ class Engine:
             if lim < 1 or lim > self.max_new or ids.shape[1] + P + lim > self.max_context:
                 raise ValueError(f"request {i}: {ids.shape[1] + P} prompt positions + {lim} new tokens exceed max_context={self.max_context}")
             reqs.append((ids, pv, lim))
+        queue = admission_order([r[2] for r in reqs], order)
         if self.pages_per_seq > 2 * ATT_MAX_SEGMENTS:
             raise ValueError(f"batched decode supports contexts up to {2 * ATT_MAX_SEGMENTS * self.PAGE} (max_context={self.max_context})")
         self._alloc_batch()
@@ -492,10 +509,10 @@ class Engine:
             # ---- admit: next requests into the free slots, same-length prompts in one batched prefill
             free = [b for b in range(S) if slot_req[b] < 0]
             while free and nxt < len(reqs):
-                n_ids = reqs[nxt][0].shape[1]
-                group = [nxt]
-                while len(group) < len(free) and group[-1] + 1 < len(reqs) and reqs[group[-1] + 1][0].shape[1] == n_ids:
-                    group.append(group[-1] + 1)
+                n_ids = reqs[queue[nxt]][0].shape[1]
+                group = [queue[nxt]]
+                while len(group) < len(free) and nxt + len(group) < len(reqs) and reqs[queue[nxt + len(group)]][0].shape[1] == n_ids:
+                    group.append(queue[nxt + len(group)])
                 slots = tuple(free[: len(group)])
                 free = free[len(group) :]
                 ids = torch.cat([reqs[r][0] for r in group]).to(dev)

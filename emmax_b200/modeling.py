@@ -269,19 +269,20 @@ class OpenVLAForActionPrediction:
     # ---- batched requests: an extension over the reference, whose cached generation asserts batch size 1 --------------
     @torch.no_grad()
     def generate_batch(self, input_ids: Sequence[torch.Tensor], pixel_values: Sequence[torch.Tensor], max_new_tokens: Union[int, Sequence[int]] = 512,
-                       eos_token_id: Union[int, None, str] = "default", continuous: bool = False) -> List[torch.Tensor]:  # fmt: skip
+                       eos_token_id: Union[int, None, str] = "default", continuous: bool = False, order: str = "fifo") -> List[torch.Tensor]:  # fmt: skip
         """N independent requests (prompt ids [1, n_i], pixel_values [1, 6, h, w] each; N robots or N simulator environments) decoded
         8 at a time with ONE pass over the weights per token for the whole group (Engine.generate_batch / emx_decode_batch_step) - where
         the reference raises "Generation with batch size > 1 is not currently supported!" (modeling_prismatic.py:460-463) and a caller
         has to loop. Every request's result is what its own bs=1 `generate` returns: [1, n_i + T_i] ids.
         continuous=True: the N requests are a stream through the 8 sequence slots (Engine.serve): a slot is refilled with the next request as
-        soon as its sequence ends instead of waiting for the longest sequence of its group of 8."""
+        soon as its sequence ends instead of waiting for the longest sequence of its group of 8; `order` ("fifo" | "longest_first") is the
+        admission order of that stream (results always come back in request order)."""
         N = len(input_ids)
         limits = [int(max_new_tokens)] * N if isinstance(max_new_tokens, int) else [int(x) for x in max_new_tokens]
         eos = self.config.text_config.eos_token_id if eos_token_id == "default" else eos_token_id
         eng, dev = self.engine, self.device
         if continuous:
-            new = eng.serve([(input_ids[i], pixel_values[i], limits[i]) for i in range(N)], eos_token_id=eos)
+            new = eng.serve([(input_ids[i], pixel_values[i], limits[i]) for i in range(N)], eos_token_id=eos, order=order)
             return [torch.cat([input_ids[i].to(dev), new[i].to(torch.long)[None]], dim=1) for i in range(N)]
         group = min(_lib.MAX_DECODE_BATCH, eng.max_batch)
         out: List[torch.Tensor] = []
@@ -312,13 +313,13 @@ class OpenVLAForActionPrediction:
     @torch.no_grad()
     def generate_actions_batch(self, inputs: Sequence[Mapping], tokenizer: Any = None, type: str = "act",  # noqa: A002
                                max_new_tokens: Union[int, Sequence[int]] = 512, do_sample: bool = False,
-                               continuous: bool = False) -> List[Tuple[Any, str]]:
+                               continuous: bool = False, order: str = "fifo") -> List[Tuple[Any, str]]:
         """`generate_actions(inputs, tokenizer, ...)` (README.md:44-47) for a list of processor outputs at once: one (action[7], reasoning)
-        per request, each identical to its own bs=1 call. continuous=True: see generate_batch."""
+        per request, each identical to its own bs=1 call. continuous=True / order: see generate_batch."""
         if do_sample:
             raise NotImplementedError("only greedy decoding (do_sample=False) is implemented, as used by the reference callers")
         tokenizer = tokenizer if tokenizer is not None else self._tokenizer
-        gen = self.generate_batch([i["input_ids"] for i in inputs], [i["pixel_values"] for i in inputs], max_new_tokens, continuous=continuous)
+        gen = self.generate_batch([i["input_ids"] for i in inputs], [i["pixel_values"] for i in inputs], max_new_tokens, continuous=continuous, order=order)
         res = []
         for i, g in zip(inputs, gen):
             acts, text = self._parse_generated(g, i["input_ids"].shape[1], tokenizer, type)

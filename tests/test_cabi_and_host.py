@@ -242,3 +242,35 @@ def test_native_run_dir_loader_name_map(tmp_path):
     # experiments/robot/robot_utils.py:42 asks for float16; the engine stays bf16 and says so
     with pytest.warns(UserWarning, match="bf16"):
         vla._check_dtype(torch.float16)
+
+
+def test_admission_order_of_the_continuous_batching_stream():
+    """Engine.serve admits requests in `admission_order`: FIFO, or largest token limit first with ties in arrival order. A host-side model
+    of the 8-slot stream (one launch = one token for every live slot) shows what the second buys on BASELINE.json configs[4]'s mix of
+    128- and 512-token requests: the stream ends within one SHORT request of the ideal sum(limits) / 8 launches."""
+    import pytest
+
+    from emmax_b200.engine import admission_order
+
+    limits = [512, 128] * 12
+    assert admission_order(limits) == list(range(24))
+    lpt = admission_order(limits, "longest_first")
+    assert lpt == list(range(0, 24, 2)) + list(range(1, 24, 2))
+    assert admission_order([], "longest_first") == []
+    with pytest.raises(ValueError):
+        admission_order(limits, "random")
+
+    def launches(order):  # tokens after the first come from decode launches: limit - 1 per request
+        queue, slots, n = list(order), [0] * 8, 0
+        while queue or any(slots):
+            for b in range(8):
+                if slots[b] == 0 and queue:
+                    slots[b] = limits[queue.pop(0)] - 1
+            step = min(x for x in slots if x > 0)
+            slots = [max(x - step, 0) for x in slots]
+            n += step
+        return n
+
+    ideal = sum(x - 1 for x in limits) / 8
+    assert launches(lpt) < launches(admission_order(limits)), (launches(lpt), launches(admission_order(limits)))
+    assert launches(lpt) <= ideal + 127

@@ -230,6 +230,13 @@ def test_tiny_continuous_batching_stream_equals_single_runs():
     for i in (1, 4, 6, 13):
         one, _ = eng.generate(ids[i], pv[i : i + 1], limits[i], eos_token_id=None)
         assert torch.equal(got[i], one), f"request {i}: stream result differs from its bs=1 run"
+    # longest-first admission (an offline batch with known limits): same ids per request, in request order, in no more launches
+    fifo_launches = eng.last_serve["launches"]
+    lpt = eng.serve([(ids[i], pv[i : i + 1], limits[i]) for i in range(len(lens))], eos_token_id=None, order="longest_first")
+    torch.cuda.synchronize()
+    for i in range(len(lens)):
+        assert torch.equal(lpt[i], got[i]), f"request {i}: longest-first result differs from the FIFO stream's"
+    assert eng.last_serve["launches"] <= fifo_launches, (eng.last_serve["launches"], fifo_launches)
 
 
 def test_tiny_continuous_batching_scripted_eos():
