@@ -49,7 +49,6 @@ enum BatchPhase { BPH_Q = 0, BPH_K, BPH_V, BPH_ATT, BPH_O, BPH_GATEUP, BPH_DOWN,
 
 struct __align__(16) BatchShared {
   uint64_t full[DEC_STAGES], empty[DEC_STAGES];
-  uint64_t gbar, pad2;  // completion barrier of the gathers' bulk copies
   float red[2][DEC_CWARPS][DB_MAXB];  // RMSNorm: per-warp sums of squares
   int tok[DB_MAXB], pos[DB_MAXB], ngen[DB_MAXB];
   uint32_t active_mask, epoch, tmem_base, pad0;
@@ -238,10 +237,11 @@ __device__ __noinline__ void batch_producer(const emx_decode_batch_params& p, co
 // 8 sequences make a gather 128 KB (hidden) to 344 KB (intermediate) of LL units per CTA: polled from registers that is many dependent
 // L2 round trips (~2 us each under the weight stream) and a large unrolled instruction footprint (an instruction-cache miss costs as
 // much as a data miss here). Instead the vector travels like the weights: consumer thread 0 points the TMA engine at the LL buffers
-// (one cp.async.bulk per sequence and chunk, 8 KB) and lands them in the NEXT RING SLOTS — every byte in flight at once, no registers, a
-// few instructions. The producers skip these "virtual" stages of the schedule. Threads then read their own units from shared memory
-// (conflict-free: sequences are skewed by 16 bytes), check the tags, and a block-wide vote (bar.red.or) decides: if any unit of the round
-// was not published yet, the round is copied again — one L2 round trip after the last unit lands, everybody has everything.
+// (one cp.async.bulk per sequence and chunk, 8 KB) and lands them in the NEXT RING STAGES — every byte in flight at once, no registers, a
+// few instructions. The producer warps skip these stages of the schedule; for the consumers they are ordinary stages (wait `full`, read,
+// release `empty` per warp), so the ring refills with the phase's first weight stages behind them. Threads read their own units from
+// shared memory (conflict-free: sequences are skewed by 16 bytes) and check the tags; a unit that was not published yet when the copy
+// read it (the arrival counter that times the copy is relaxed) is fetched by its reader straight from the L2 (ll_repair).
 constexpr int DB_GSEQ_STRIDE = 1024 * 8 + 16;  // bytes between sequences inside a ring slot: one chunk = 1024 units, + 16 B bank skew
 static_assert(DB_MAXB * DB_GSEQ_STRIDE <= DEC_STAGE_BYTES, "a gather chunk of 8 sequences must fit one ring stage");
 
@@ -250,17 +250,18 @@ __device__ __forceinline__ int half_ksteps(int K, int hc, int warp) { return max
 // natural unit index of payload word q (0..15) of half chunk hc for (warp, t)
 __device__ __forceinline__ int g_unit(int hc, int warp, int t, int q) { return 16 * (64 * (hc >> 1) + 8 * warp + 4 * (hc & 1) + (q >> 2)) + 4 * (q & 3) + t; }
 
-__device__ __forceinline__ bool vote_any(bool pred) {  // OR over the 256 consumer threads (named barrier 1, as cbar)
-  uint32_t out;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.u32 q, %1, 0;\n\t"
-      "bar.red.or.pred p, 1, %2, q;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(out)
-      : "r"(static_cast<uint32_t>(pred)), "n"(DEC_CTHREADS)
-      : "memory");
-  return out != 0;
+// Slow path of a gather: the pair of units at `gp` carried a stale tag in the bulk copy (the arrival counter is relaxed, so a publisher's
+// stores may trail its arrival). Poll the pair itself; the tags are the proof.
+__device__ __noinline__ uint2 ll_repair(const uint64_t* gp, uint32_t tag) {
+  uint64_t a, b;
+  uint32_t spins = 0;
+  for (;;) {
+    ll_load2(gp, a, b);
+    if (tag_ok(a, tag) && tag_ok(b, tag)) break;
+    __nanosleep(100);
+    if (++spins > EMX_SPIN_LIMIT) __trap();
+  }
+  return make_uint2(static_cast<uint32_t>(a), static_cast<uint32_t>(b));
 }
 
 __device__ __forceinline__ void ln_fetch_async_b(const __nv_bfloat16* w, uint32_t* ln_s, int H) {
@@ -272,7 +273,6 @@ __device__ __forceinline__ void ln_fetch_async_b(const __nv_bfloat16* w, uint32_
 struct BCons {
   uint32_t it;     // ring stage counter (weight stages, K/V items and the virtual stages of the gathers)
   uint32_t group;  // row groups / attention flushes so far: selects the partial buffer, its named barrier and the rotating warp
-  uint32_t gph;    // completed phases of the gather mbarrier
   uint32_t gathers;  // exchanges (gathers out of an LL buffer) done so far in this launch
 };
 
@@ -310,14 +310,24 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
     const int units = static_cast<int>(seq_stride);  // per sequence, a multiple of 16
     const uint32_t ring_s = smem_u32(ring);
     // Arrival counter of the exchange: the vector was produced by the phase every CTA has just finished, so "all CTAs have arrived here"
-    // means "every unit is published". It only decides WHEN the copy is worth issuing (one attempt instead of a burst of re-copies from
-    // the CTAs that get here early, which would flood the L2 the stragglers are still writing through); the tags stay the proof.
+    // means "every unit is published". It only decides WHEN the copies are worth issuing (a copy issued earlier would carry stale
+    // units for certain); the tags stay the proof.
     long long tg = gprof ? global_ns() : 0;
     auto lap = [&](int k) {
       if (gprof) {
         const long long now = global_ns();
         gprof[k] += now - tg, tg = now;
       }
+    };
+    // chunk c of the vector -> ring stage cs.it + c: this thread is the producer of that stage (the producer warps skip it)
+    auto issue_chunk = [&](int c) {
+      const uint32_t it = cs.it + c, slot = it % DEC_STAGES;
+      mbar_wait(&sh.empty[slot], ((it / DEC_STAGES) & 1) ^ 1);  // all 8 consumer warps are done with the slot's previous stage
+      const uint32_t cbytes = static_cast<uint32_t>(min(1024, units - 1024 * c) * 8);
+      mbar_arrive_expect_tx(&sh.full[slot], static_cast<uint32_t>(__popc(sh.active_mask)) * cbytes);
+      const uint64_t policy = l2_policy_evict_last();
+      for (int q = 0; q < DB_MAXB; ++q)
+        if ((sh.active_mask >> q) & 1) bulk_g2s(ring + slot * DEC_STAGE_BYTES + q * DB_GSEQ_STRIDE, buf + q * seq_stride + 1024 * c, cbytes, &sh.full[slot], policy);
     };
     cbar();  // every warp of this CTA is done with the previous phase: its epilogues' / combines' stores are issued
     lap(0);
@@ -326,7 +336,7 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
       unsigned long long* cnt = static_cast<unsigned long long*>(sync_cnt);
       // relaxed on purpose: a release would put a MEMBAR.GPU (microseconds while the SM's bulk copies are in flight) on the critical path of
       // every exchange. This CTA's LL stores were issued before the barrier above and drain to the L2 ahead of this reduction in practice;
-      // if one ever lags, its tag is stale in the copy and the round is simply copied again.
+      // if one ever lags, its tag is stale in the copy and the reader fetches that unit itself (ll_repair).
       asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(cnt) : "memory");
       const unsigned long long want = (static_cast<unsigned long long>(sh.epoch) * gathers_per_launch + cs.gathers + 1ull) * gridDim.x;
       uint32_t spins = 0;
@@ -340,95 +350,57 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
       asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what the generic proxy has just observed
       lap(1);
       if (gcta) gcta[1] = global_ns();
+      for (int c = 0; c < min(nc, DEC_STAGES); ++c) issue_chunk(c);
+      lap(2);
     }
     ++cs.gathers;
+    // The chunks are ORDINARY ring stages from here on: wait for `full`, read, release `empty` per warp. A slot is handed back as soon as
+    // the 8 warps have read it, so the producer warps refill the ring with the first weight stages of the phase while the later chunks
+    // are still being parked (the hot loop used to start on an empty ring, one loaded-L2 latency after the gather).
 #pragma unroll 1
-    for (int c0 = 0; c0 < nc; c0 += DEC_STAGES) {  // rounds of up to 3 chunks = 3 ring slots
-      const int nr = min(DEC_STAGES, nc - c0);
-      bool first = true;
-      float ss_try;
-#ifdef EMX_GATHER_DEBUG
-      uint32_t dbg_attempts = 0;
-#endif
-      for (;;) {
-        if (threadIdx.x == 0) {
-          uint32_t bytes = 0;
-          for (int j = 0; j < nr; ++j) {
-            const uint32_t it = cs.it + j, slot = it % DEC_STAGES;
-            if (first) {  // the slot is ours once its previous stage has been released; advance its `full` phase (nobody waits on it)
-              mbar_wait(&sh.empty[slot], ((it / DEC_STAGES) & 1) ^ 1);
-              mbar_arrive(&sh.full[slot]);
-            }
-            bytes += static_cast<uint32_t>(__popc(sh.active_mask)) * static_cast<uint32_t>(min(1024, units - 1024 * (c0 + j)) * 8);
-          }
-          lap(2);
-          mbar_arrive_expect_tx(&sh.gbar, bytes);
-          const uint64_t policy = l2_policy_evict_last();
-          for (int j = 0; j < nr; ++j) {
-            const uint32_t slot = (cs.it + j) % DEC_STAGES;
-            const uint32_t cbytes = static_cast<uint32_t>(min(1024, units - 1024 * (c0 + j)) * 8);
-            for (int q = 0; q < DB_MAXB; ++q)
-              if ((sh.active_mask >> q) & 1)
-                bulk_g2s(ring + slot * DEC_STAGE_BYTES + q * DB_GSEQ_STRIDE, buf + q * seq_stride + 1024 * (c0 + j), cbytes, &sh.gbar, policy);
-          }
-        }
-        mbar_wait(&sh.gbar, cs.gph & 1);
-        ++cs.gph;
-        if (threadIdx.x == 0) lap(3);
-        if (gprof && threadIdx.x == 0) gprof[6] += 1;
-        ss_try = 0.f;
-        bool bad = false;
+    for (int c = 0; c < nc; ++c) {
+      const uint32_t it = cs.it + c, slot = it % DEC_STAGES;
+      mbar_wait(&sh.full[slot], (it / DEC_STAGES) & 1);
+      if (c == 0 && threadIdx.x == 0) lap(3);
 #pragma unroll 1
-        for (int hh = 0; hh < 2 * nr; ++hh) {
-          const int hc = 2 * c0 + hh;
-          const int ks = half_ksteps(K, hc, warp);
-          if (ks > 0) {  // warp-uniform
-            const uint32_t base = ring_s + ((cs.it + (hh >> 1)) % DEC_STAGES) * DEC_STAGE_BYTES + n * DB_GSEQ_STRIDE + 128 * (8 * warp + 4 * (hh & 1)) + 32 * t;
-            uint32_t r[16];
-            bool hbad = false;
+      for (int hh = 0; hh < 2; ++hh) {
+        const int hc = 2 * c + hh;
+        const int ks = half_ksteps(K, hc, warp);
+        if (ks > 0) {  // warp-uniform
+          const uint32_t base = ring_s + slot * DEC_STAGE_BYTES + n * DB_GSEQ_STRIDE + 128 * (8 * warp + 4 * hh) + 32 * t;
+          uint32_t r[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              uint4 v = make_uint4(0u, tag, 0u, tag);
-              if (act && i < ks) v = lds128(base + 128 * (i >> 1) + 16 * (i & 1));  // {payload, tag, payload, tag}
-              hbad |= (v.y != tag) | (v.w != tag);
-              r[2 * i] = v.x, r[2 * i + 1] = v.z;
+          for (int i = 0; i < 8; ++i) {
+            uint4 v = make_uint4(0u, tag, 0u, tag);
+            if (act && i < ks) v = lds128(base + 128 * (i >> 1) + 16 * (i & 1));  // {payload, tag, payload, tag}
+            if ((v.y != tag) | (v.w != tag)) {  // (never in practice) not published when the copy read it: fetch the pair from the L2
+              const uint2 fix = ll_repair(buf + n * seq_stride + 1024 * c + 16 * (8 * warp + 4 * hh + (i >> 1)) + 4 * t + 2 * (i & 1), tag);
+              v.x = fix.x, v.z = fix.y;
+              if (gprof) gprof[6] += 1;
             }
-            if (norm) {
+            r[2 * i] = v.x, r[2 * i + 1] = v.z;
+          }
+          if (norm) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) ss_try += sumsq2(r[q]);
-              const int ub = g_unit(hc, warp, 0, 0);  // this trip covers units [ub, ub + 64): own rows of the residual stream among them? (warp-uniform)
-              if (ub < re2 && ub + 64 > rb2) {
+            for (int q = 0; q < 16; ++q) ss += sumsq2(r[q]);
+            const int ub = g_unit(hc, warp, 0, 0);  // this trip covers units [ub, ub + 64): own rows of the residual stream among them? (warp-uniform)
+            if (ub < re2 && ub + 64 > rb2) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  const int u = g_unit(hc, warp, t, q);
-                  if (act && (q >> 1) < ks && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
-                }
+              for (int q = 0; q < 16; ++q) {
+                const int u = g_unit(hc, warp, t, q);
+                if (act && (q >> 1) < ks && u >= rb2 && u < re2) sh.resid[n][u - rb2] = r[q];
               }
             }
-            // (two tcgen05.st to the same columns are not ordered without a wait: never park words that a retry will replace)
-            if (!__any_sync(0xffffffffu, hbad)) tmem_st_32x16(tm + 16 * hc, r);
-            bad |= hbad;
           }
+          tmem_st_32x16(tm + 16 * hc, r);
         }
-        const bool again = vote_any(bad);  // (also: everybody is done reading the slots, they may be overwritten)
-        if (threadIdx.x == 0) lap(4);
-        if (!again) break;
-        first = false;
-        __nanosleep(500);
-#ifdef EMX_GATHER_DEBUG
-        if (++dbg_attempts > 20000u) {
-          if (bad && (threadIdx.x & 31) < 8)
-            printf("gather stuck: cta %d tid %d K %d norm %d c0 %d tag %u it %u gph %u act %d\n", blockIdx.x, threadIdx.x, K, int(norm), c0, tag, cs.it, cs.gph, int(act));
-          break;
-        }
-#endif
       }
-      ss += ss_try;
       __syncwarp();
-      if (lane == 0)
-        for (int j = 0; j < nr; ++j) mbar_arrive(&sh.empty[(cs.it + j) % DEC_STAGES]);
-      cs.it += nr;
+      if (lane == 0) mbar_arrive(&sh.empty[slot]);
+      if (threadIdx.x == 0 && c + DEC_STAGES < nc) issue_chunk(c + DEC_STAGES);  // (waits for the slowest warp's release of chunk c)
     }
+    if (threadIdx.x == 0) lap(4);
+    cs.it += nc;
   }
   if (!norm) {
     tmem_st_wait();
@@ -657,15 +629,26 @@ __device__ __forceinline__ void att_merge(float& M, float& den, float (&num)[4],
 // and publishes the head output in o_proj's exchange order; every other segment is published as a partial. Publishers never wait, and a
 // combiner only waits for segments that were started at the same time as its own, so no CTA ever waits for another one's WHOLE share
 // (the mirror-image choice — combining in the CTA that owns the row's last item — chains every CTA behind its predecessor).
+// What the finishing warp of a row it COMBINES fetches when the row starts, so that the L2 round trips are over when the row ends (a flush
+// that waits for them holds this warp back for ~2 us under the weight stream, and the ring with it: a slot is released by the slowest warp):
+// k and v of the token being decoded, and the partial of the next CTA's segment of the row (published at the START of that CTA's share,
+// i.e. usually long before; if it is not there yet, att_finish polls for it as before).
+struct AttPre {
+  Head4 hk, hv;
+  uint64_t sa[3], sb[3];
+  bool kv, seg;
+};
+
 __device__ void att_finish(const emx_decode_batch_params& p, const BatchShared& sh, const float* pb, int lane, const AttItem& it, int g, int layer,
-                           uint32_t tag, const float (&q)[4], float scale) {
+                           uint32_t tag, const float (&q)[4], float scale, AttPre& pre) {
   const int n = it.seq, H = p.hidden;
   const int row_start = sh.att_off[n] + it.head * it.pp, row_last = row_start + it.pp - 1;
   const int seg_start = max(sh.att_i0, row_start);
   const bool combiner = (seg_start == row_start);
   const uint64_t* qkv = static_cast<const uint64_t*>(p.qkv) + static_cast<long>(n) * (3 * H / 2);
-  Head4 hk, hv;
-  if (combiner) {  // k and v of the token being decoded: in flight while the partials are merged
+  Head4& hk = pre.hk;
+  Head4& hv = pre.hv;
+  if (combiner && !pre.kv) {  // k and v of the token being decoded (normally fetched when the row started)
     hk.issue(qkv + H / 2 + it.head * (DEC_HD / 2), lane);
     hv.issue(qkv + H + it.head * (DEC_HD / 2), lane);
   }
@@ -690,7 +673,17 @@ __device__ void att_finish(const emx_decode_batch_params& p, const BatchShared& 
     const long c = ((gc + 1) * G - 1) / T;
     const uint64_t* src = rowpart + (gc - row_start) * DB_PARTU;
     uint32_t w[6];
-    ll_fetch_pairs<3>([&](int i) -> const uint64_t* { return i == 0 ? src : src + 2 + 4 * lane + 2 * (i - 1); }, w, tag, true);
+    bool have = pre.seg && gc == g + 1;  // the segment fetched ahead is the one that follows ours
+    if (have) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) have &= tag_ok(pre.sa[i], tag) && tag_ok(pre.sb[i], tag);
+    }
+    if (have) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) w[2 * i] = static_cast<uint32_t>(pre.sa[i]), w[2 * i + 1] = static_cast<uint32_t>(pre.sb[i]);
+    } else {
+      ll_fetch_pairs<3>([&](int i) -> const uint64_t* { return i == 0 ? src : src + 2 + 4 * lane + 2 * (i - 1); }, w, tag, true);
+    }
     const float a4[4] = {__uint_as_float(w[2]), __uint_as_float(w[3]), __uint_as_float(w[4]), __uint_as_float(w[5])};
     att_merge(M, den, num, __uint_as_float(w[0]), __uint_as_float(w[1]), a4);
     gc = static_cast<int>(T * (c + 1) / G);
@@ -723,14 +716,39 @@ __device__ __noinline__ void attention_phase_b(const emx_decode_batch_params& p,
   s.row = -1, s.m = -INFINITY, s.l = 0.f;
 #pragma unroll
   for (int e = 0; e < 4; ++e) s.acc[e] = 0.f, s.q[e] = 0.f;
+  const uint64_t* qkv = static_cast<const uint64_t*>(p.qkv);
+  const int H = p.hidden;
+  Head4 hq;
+  bool hq_issued = false;
+  AttPre pre;
+  pre.kv = pre.seg = false;
 #pragma unroll 1
   for (int g = i0; g < i1; ++g) {
     const AttItem it = att_item(sh, g);
     const int row = it.seq * p.heads + it.head;
     const bool new_row = row != s.row;
-    Head4 hq;
-    if (new_row)  // q of (sequence, head) — projected two phases ago, long there: its L2 round trip overlaps the wait for the stage
-      hq.issue(static_cast<const uint64_t*>(p.qkv) + static_cast<long>(it.seq) * (3 * p.hidden / 2) + it.head * (DEC_HD / 2), lane);
+    if (new_row) {
+      // q of (sequence, head) — projected two phases ago, long there. For the first row of the phase its L2 round trip overlaps the wait for
+      // the stage; for every later row it was issued while the last item of the row before was still streaming (see below)
+      if (!hq_issued) hq.issue(qkv + static_cast<long>(it.seq) * (3 * H / 2) + it.head * (DEC_HD / 2), lane);
+      // the warp that will finish this row (the flush below: cs.group does not change before it) fetches what a COMBINER needs now
+      const int row_start = sh.att_off[it.seq] + it.head * it.pp;
+      pre.kv = pre.seg = false;
+      if (warp == static_cast<int>(cs.group % DEC_CWARPS) && g == row_start) {
+        const uint64_t* qs = qkv + static_cast<long>(it.seq) * (3 * H / 2);
+        pre.hk.issue(qs + H / 2 + it.head * (DEC_HD / 2), lane);
+        pre.hv.issue(qs + H + it.head * (DEC_HD / 2), lane);
+        pre.kv = true;
+        if (row_start + it.pp > i1) {  // the row runs on into the next CTA's share: that segment starts at item i1
+          const uint64_t* src = static_cast<const uint64_t*>(p.part) + (static_cast<long>(it.seq) * p.heads + it.head) * (DB_MAXSEG * DB_PARTU) +
+                                static_cast<long>(i1 - row_start) * DB_PARTU;
+          ll_load2(src, pre.sa[0], pre.sb[0]);
+          ll_load2(src + 2 + 4 * lane, pre.sa[1], pre.sb[1]);
+          ll_load2(src + 2 + 4 * lane + 2, pre.sa[2], pre.sb[2]);
+          pre.seg = true;
+        }
+      }
+    }
     const int slot = cs.it % DEC_STAGES;
     const uint32_t ph = (cs.it / DEC_STAGES) & 1;
     mbar_wait(&full[slot], ph);
@@ -739,6 +757,7 @@ __device__ __noinline__ void attention_phase_b(const emx_decode_batch_params& p,
 #pragma unroll
       for (int e = 0; e < 4; ++e) s.acc[e] = 0.f;
       hq.finish(sh.rope[it.seq], lane, tag, s.q);
+      hq_issued = false;
     }
     const int nvalid = min(16, sh.pos[it.seq] - (128 * it.j + 16 * warp));  // cached keys are positions 0 .. pos - 1
     if (nvalid > 0) att_block(ring + slot * DEC_STAGE_BYTES, warp, lane, nvalid, scale, s);
@@ -746,13 +765,18 @@ __device__ __noinline__ void attention_phase_b(const emx_decode_batch_params& p,
     if (lane == 0) mbar_arrive(&empty[slot]);
     ++cs.it;
     if (it.j == it.pp - 1 || g == i1 - 1) {  // end of the row, or of this CTA's share of it
+      if (g + 1 < i1) {  // the next item starts a new row: its q travels while this row is flushed and the next stage lands
+        const AttItem nx = att_item(sh, g + 1);
+        hq.issue(qkv + static_cast<long>(nx.seq) * (3 * H / 2) + nx.head * (DEC_HD / 2), lane);
+        hq_issued = true;
+      }
       const uint32_t buf = cs.group % DEC_PARTBUFS;
       float* pb = part + buf * DB_PART_FLOATS;
       *reinterpret_cast<float4*>(pb + warp * DB_ATT_WSTRIDE + 4 * lane) = make_float4(s.acc[0], s.acc[1], s.acc[2], s.acc[3]);
       if (lane == 0) pb[warp * DB_ATT_WSTRIDE + DEC_HD] = s.m, pb[warp * DB_ATT_WSTRIDE + DEC_HD + 1] = s.l;
       if (warp == static_cast<int>(cs.group % DEC_CWARPS)) {
         part_sync(buf);
-        att_finish(p, sh, pb, lane, it, g, layer, tag, s.q, scale);
+        att_finish(p, sh, pb, lane, it, g, layer, tag, s.q, scale, pre);
         __syncwarp();
       } else {
         part_arrive(buf);
@@ -792,7 +816,6 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
       mbar_init(&sh.full[s], 1);
       mbar_init(&sh.empty[s], DEC_CWARPS);
     }
-    mbar_init(&sh.gbar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -846,7 +869,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) decode_batch_kernel(const emx_d
   const int rb = sh.r_begin[BPH_O], rb2 = rb >> 1, re2 = sh.r_end[BPH_O] >> 1;
   long long* dbg = (PROF && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(p.dbg) : nullptr;
 
-  BCons cs{0, 0, 0, 0};
+  BCons cs{0, 0, 0};
   long long* gprof = (PROF && dbg) ? dbg + 2 * (BPH_STEPS * L + 1) + 8 + 16 * gridDim.x : nullptr;  // (host zeroes it)
   float best = -INFINITY;  // lm_head: this lane's best logit of ITS sequence (lane & 7)
   int best_i = 0x7fffffff;
