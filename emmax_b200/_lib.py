@@ -97,6 +97,7 @@ _SIGNATURES = {
     "emx_swiglu": (_I, [_P, _P, _I, _I, _P]),
     "emx_gemv_bf16": (_I, [_P, _I, _P, _P, _P, _I, _I, _P]),
     "emx_lmhead_argmax": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P]),
+    "emx_argmax_rows_bf16": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "emx_decode_step": (_I, [C.POINTER(DecodeParams), _P]),
     "emx_decode_batch_step": (_I, [C.POINTER(DecodeBatchParams), _P]),
     "emx_decode_batch_smem": (_I, []),

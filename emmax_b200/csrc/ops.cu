@@ -374,6 +374,40 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
   }
 }
 
+// one CTA per row of a bf16 logits matrix: optional fp32 copy of the row + argmax, lowest index wins ties (first tokens of a batched prefill)
+__global__ void __launch_bounds__(1024) argmax_rows_bf16_kernel(const __nv_bfloat16* __restrict__ v, int ld, int n, float* __restrict__ out32,
+                                                                int32_t* __restrict__ out) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const __nv_bfloat16* row = v + static_cast<long>(blockIdx.x) * ld;
+  float* o32 = out32 ? out32 + static_cast<long>(blockIdx.x) * n : nullptr;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = ld_bf16(row + i);
+    if (o32) o32[i] = x;
+    if (x > best) best = x, bi = i;  // indices ascend per thread: strict '>' keeps the lowest
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) best = ob, bi = oi;
+  }
+  if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = best, si[threadIdx.x >> 5] = bi;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = sv[threadIdx.x], bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) best = ob, bi = oi;
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = bi;
+  }
+}
+
 // ---- action de-tokeniser: integer index math + fp64 table, bit-exact with numpy ----------------------------------
 __global__ void detok_kernel(const int32_t* __restrict__ ids, int n, int vocab, int n_bins, const double* __restrict__ q01,
                              const double* __restrict__ q99, const uint8_t* __restrict__ mask, int adim, double* __restrict__ norm,
@@ -478,7 +512,7 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ in, __nv_bflo
 using namespace emx;
 
 extern "C" const char* emx_last_error(void) { return g_err; }
-extern "C" int emx_abi_version(void) { return 4; }
+extern "C" int emx_abi_version(void) { return 5; }
 extern "C" const char* emx_arch(void) { return "sm_100a"; }
 
 #define BF(p) static_cast<const __nv_bfloat16*>(p)
@@ -576,6 +610,12 @@ extern "C" int emx_lmhead_argmax(const void* W, int ldw, const void* x, int N, i
   EMX_REQUIRE(logits != nullptr, "emx_lmhead_argmax: need logits_out or scratch (N floats)");
   gemv_kernel<<<(N + 7) / 8, 256, 0, s>>>(BF(W), ldw, BF(x), nullptr, nullptr, logits, N, K);
   argmax_kernel<<<1, 1024, 0, s>>>(logits, N, token_out);
+  EMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int emx_argmax_rows_bf16(const void* logits, int ld, int rows, int n, float* logits_out, int32_t* tokens_out, cudaStream_t s) {
+  EMX_REQUIRE(logits && tokens_out && rows >= 1 && n >= 1 && ld >= n, "emx_argmax_rows_bf16: bad arguments");
+  argmax_rows_bf16_kernel<<<rows, 1024, 0, s>>>(BF(logits), ld, n, logits_out, tokens_out);
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -215,7 +215,7 @@ class Engine:
         vd, H, I = cfg.vision_embed_dim, t.hidden_size, t.intermediate_size
         ws.update(feats=e(B * P, vd), p1=e(B * P, 4 * vd), p2=e(B * P, H), patches=e(B * P, H),
                   x=e(B * S, H), n=e(B * S, H), qkv=e(B * S, 3 * H), att=e(B * S, H), h=e(B * S, I),
-                  last_n=e(B, H),
+                  last_n=e(B, H), logits_bf16=e(B, t.vocab_size) if B > 1 else None,
                   pixels=torch.empty((B, 6, cfg.image_sizes[0], cfg.image_sizes[0]), dtype=BF16, device=dev),
                   ids=torch.empty((B, n_ids), dtype=torch.int64, device=dev),
                   logits=torch.empty((B, t.vocab_size), dtype=torch.float32, device=dev),
@@ -310,8 +310,12 @@ class Engine:
         x3 = ws["x"].view(B, S, H)
         for b in range(B):
             call("emx_rmsnorm", ptr(x3[b, S - 1]), ptr(self.final_norm), ptr(ws["last_n"][b]), 1, H, t.rms_norm_eps, stream())
-            call("emx_lmhead_argmax", ptr(self.lm_head), H, ptr(ws["last_n"][b]), t.vocab_size, H, ptr(ws["logits"][b]),
-                 ptr(ws["first"][b : b + 1]), None, stream())  # fmt: skip
+            if B == 1:
+                call("emx_lmhead_argmax", ptr(self.lm_head), H, ptr(ws["last_n"][b]), t.vocab_size, H, ptr(ws["logits"][b]),
+                     ptr(ws["first"][b : b + 1]), None, stream())  # fmt: skip
+        if B > 1:  # ONE pass over lm_head (262 MB) for the B last rows instead of B GEMVs: [B, H] x lm_head^T on the tensor cores, row-wise argmax
+            self.gemm(ws["last_n"], self.lm_head, ws["logits_bf16"], scratch=self._scratch[0])
+            call("emx_argmax_rows_bf16", ptr(ws["logits_bf16"]), t.vocab_size, B, t.vocab_size, ptr(ws["logits"]), ptr(ws["first"]), stream())
 
     def _prefill_body(self, ws: dict, B: int, n_ids: int, slot=0) -> None:
         self._vision(ws, B)

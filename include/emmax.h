@@ -113,6 +113,11 @@ int emx_gemv_bf16(const void* W, int ldw, const void* x, void* y, const void* re
 int emx_lmhead_argmax(const void* W, int ldw, const void* x, int N, int K, float* logits_out, int32_t* token_out, void* scratch,
                       emx_stream_t stream);
 
+/* First tokens of a BATCHED prefill (ABI 5): logits [rows][ld] bf16 (= emx_gemm_bf16 of the rows' last hidden states against lm_head: one pass
+ * over lm_head for the whole batch instead of one GEMV per row) -> optional fp32 copy [rows][n] + per-row argmax, lowest index wins ties.
+ * Replaces logits[:, -1].argmax(-1) of the first GenerationMixin step (called at modeling_prismatic.py:519) for B > 1. */
+int emx_argmax_rows_bf16(const void* logits, int ld, int rows, int n, float* logits_out, int32_t* tokens_out, emx_stream_t stream);
+
 /* ---- persistent decode step ---------------------------------------------------------------------------------
  * ONE launch = one new token for one sequence: embedding gather, 32 x (RMSNorm + q|k|v GEMV + RoPE + paged-KV append +
  * split-KV attention + o_proj + residual + RMSNorm + gate/up GEMV + SwiGLU + down GEMV + residual), final norm,

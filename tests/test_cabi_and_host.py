@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [s for s in sorted(declared) if not hasattr(handle, s)]
     assert not missing, missing
     assert set(lib.EXPORTS) == declared, set(lib.EXPORTS) ^ declared
-    assert handle.emx_arch() == b"sm_100a" and handle.emx_abi_version() == 4 and handle.emx_decode_grid() == 148
+    assert handle.emx_arch() == b"sm_100a" and handle.emx_abi_version() == 5 and handle.emx_decode_grid() == 148
 
 
 def test_ctypes_structs_match_c_layout(lib):

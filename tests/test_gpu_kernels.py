@@ -249,6 +249,36 @@ def test_gemv_and_argmax(lib):
     assert int(tok) == int(torch.argmax(logits)) == 7
 
 
+def test_batched_lm_head_rows(lib):
+    """First tokens of a batched prefill: ONE tcgen05 GEMM of the B last hidden rows against lm_head + emx_argmax_rows_bf16, against the
+    per-row GEMV path (emx_lmhead_argmax) and torch: bf16 logits of both within bf16 rounding, same argmax, lowest index on ties, the fp32
+    copy exactly the bf16 values."""
+    from emmax_b200._lib import call, ptr, stream
+    from emmax_b200.engine import Engine
+
+    B, N, K = 5, 32064, 4096
+    w, x = rnd(N, K, scale=K ** -0.5, seed=35), rnd(B, K, seed=36)
+    w[4242] = w[77]  # a tie: row 4242 repeats row 77 ...
+    x[2] = w[77] * 8  # ... and sequence 2 points straight at it
+    lb = torch.empty(B, N, dtype=BF, device="cuda")
+    Engine.gemm(x, w, lb)
+    l32 = torch.empty(B, N, dtype=torch.float32, device="cuda")
+    tok = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    call("emx_argmax_rows_bf16", ptr(lb), N, B, N, ptr(l32), ptr(tok), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(l32, lb.float())
+    want = (x.float() @ w.float().T).to(BF)
+    assert_close_bf16(lb, want, name="batched lm_head logits")
+    for b in range(B):
+        assert int(tok[b]) == int(torch.argmax(l32[b])), b  # torch.argmax returns the first maximum too
+        one = torch.empty(N, dtype=torch.float32, device="cuda")
+        t1 = torch.zeros(1, dtype=torch.int32, device="cuda")
+        call("emx_lmhead_argmax", ptr(w), K, ptr(x[b]), N, K, ptr(one), ptr(t1), None, stream())
+        torch.cuda.synchronize()
+        assert_close_bf16(l32[b], one, name=f"row {b}: GEMM vs GEMV logits")
+    assert int(tok[2]) == 77 and float(l32[2, 77]) == float(l32[2, 4242])
+
+
 def test_vit_frontend_kernels(lib):
     from emmax_b200._lib import call, ptr, stream
 
