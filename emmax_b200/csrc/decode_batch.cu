@@ -114,7 +114,8 @@ __device__ __forceinline__ long kv_page_off(const emx_decode_batch_params& p, in
   return ((static_cast<long>(layer) * p.n_pages + page) * p.heads + head) * (DB_PAGE * DEC_HD);
 }
 
-// virtual ring stages the gather of a K-element vector occupies (see "gathers" below; producers and the prefetch warp skip them)
+// ring stages the gather of a K-element vector occupies (see "gathers" below; their producer is consumer thread 0: the producer warps and the
+// prefetch warp skip them)
 __host__ __device__ __forceinline__ int gather_stages(int K) { return (K + DEC_KC - 1) / DEC_KC; }
 
 // ---- producer warps, L2-prefetch warp ----------------------------------------------------------------------------------------
@@ -271,7 +272,7 @@ __device__ __forceinline__ void ln_fetch_async_b(const __nv_bfloat16* w, uint32_
 }
 
 struct BCons {
-  uint32_t it;     // ring stage counter (weight stages, K/V items and the virtual stages of the gathers)
+  uint32_t it;     // ring stage counter (weight stages, K/V items and the stages of the gathers)
   uint32_t group;  // row groups / attention flushes so far: selects the partial buffer, its named barrier and the rotating warp
   uint32_t gathers;  // exchanges (gathers out of an LL buffer) done so far in this launch
 };
@@ -284,7 +285,8 @@ __device__ __noinline__ void gather_b(const uint64_t* buf, long seq_stride, int 
                                       uint8_t* ring, BCons& cs, const uint32_t* ln_s, float eps, uint32_t parity, int rb2, int re2, int warp, int lane,
                                       void* sync_cnt, uint32_t gathers_per_launch, long long* gprof, long long* gcta) {
   // gcta (instrumented twin, thread 0 of every CTA, layer 1 only): [0] after the entry barrier, [1] arrival counter complete
-  // gprof (instrumented twin, thread 0 only): [0] cbar, [1] arrival counter, [2] free slots, [3] copy landed, [4] read + park + vote, [5] norm tail, [6] attempts
+  // gprof (instrumented twin, thread 0 only): [0] cbar, [1] arrival counter, [2] first chunks issued (free slots), [3] first chunk landed, [4] read + park (incl. the later chunks' landing),
+  // [5] norm tail, [6] units this thread had to repair (stale tag in the copy)
   const int n = lane >> 2, t = lane & 3;
   const bool act = (sh.active_mask >> n) & 1;
   const int nc = gather_stages(K);

@@ -84,7 +84,7 @@ for B, LA in [(int(b), int(la)) for b in args.batches.split(",") for la in args.
               f"(median {(np.median(g2[:, k, 0]) - t0) / 1e3:.1f}), counter seen complete: first {(g2[:, k, 1].min() - t0) / 1e3:.1f} / last {(g2[:, k, 1].max() - t0) / 1e3:.1f}, "
               f"last exit {(g1[:, k, 1].max() - t0) / 1e3:.1f}")
     print(f"   gathers of CTA 0, thread 0, per launch (us): cbar {gp[0] / 1e3:.0f}, arrival counter {gp[1] / 1e3:.0f}, free slots {gp[2] / 1e3:.0f}, copy landed {gp[3] / 1e3:.0f}, "
-          f"read+park+vote {gp[4] / 1e3:.0f} (first loop trip {gp[7] / 1e3:.0f}), norm tail {gp[5] / 1e3:.0f}; attempts {gp[6] * 1.0:.0f} for {4 * L} gathers")
+          f"read+park {gp[4] / 1e3:.0f}, norm tail {gp[5] / 1e3:.0f}; units repaired by thread 0: {gp[6] * 1.0:.0f} in {4 * L} gathers")
     if args.percta:
         ent = np.mean(np.array(entries), axis=0) / 1e3  # [GRID, 4] entry time relative to the earliest CTA, us
         for k, nm in enumerate(["q", "o", "gateup", "down"]):
