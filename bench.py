@@ -475,7 +475,7 @@ def measure_c5(cfg, model, proc, script, dev, world: int, rank: int, K: int, W: 
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "decode_batch_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": btraffic.get("dram_bytes_per_launch"),
-                     "traffic_source": "profiles/decode_batch_traffic.json: ncu --set full capture of this kernel at batch 8, context 365 "
+                     "traffic_source": f"profiles/decode_batch_traffic.json: ncu --set full capture of this kernel at batch {btraffic.get('batch')}, context {btraffic.get('context')} "
                                        f"(algorithmic there: {btraffic.get('algorithmic_bytes_at_that_point')} B, ratio {btraffic.get('ratio_to_algorithmic')})",
                      "peak_source": peak_src + " hbm_gbs", "bytes_per_launch": per_launch,
                      "avg_launch_ms": avg_ms, "launches_timed": acc["launches"], "share_of_step": acc["ms"] / total_ms},
