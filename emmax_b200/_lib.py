@@ -93,6 +93,7 @@ _SIGNATURES = {
     "emx_vit_gather_features": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "emx_attn_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "emx_rope_kvstore": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
+    "emx_gemm_qkv_rope": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "emx_embed_assemble": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _P]),
     "emx_swiglu": (_I, [_P, _P, _I, _I, _P]),
     "emx_gemv_bf16": (_I, [_P, _I, _P, _P, _P, _I, _I, _P]),

@@ -112,7 +112,18 @@ __device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&r)[32]) {
 //   EPI_ANY   : every combination, 32-column chunks in a rolled loop (bias / GELU / LayerScale / residual / SwiGLU tested at run time)
 //   EPI_RESID : bias -> LayerScale -> residual (no GELU, no SwiGLU), chunk loop unrolled over the prefetched residual
 //   EPI_SWIGLU: SwiGLU only
-enum EpiKind { EPI_ANY = 0, EPI_RESID = 1, EPI_SWIGLU = 2 };
+//   EPI_ROPE  : the Llama q|k|v projection of a prefill: RoPE on the q and k heads, K / V rows appended to the paged cache (see epilogue_rope_head)
+enum EpiKind { EPI_ANY = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_ROPE = 3 };
+
+// What the fused q|k|v epilogue needs beyond the GEMM itself (emx_gemm_qkv_rope; the un-fused twin is rope_kvstore_kernel in ops.cu).
+struct RopeParams {
+  const __nv_bfloat16* cos_tab;  // [max_pos][64] bf16
+  const __nv_bfloat16* sin_tab;
+  __nv_bfloat16* k_cache;        // this layer's [page][head][page_size][128]
+  __nv_bfloat16* v_cache;
+  const int32_t* block_table;    // [B][max_pages]
+  int T, pos0, heads, max_pages, page_size;
+};
 
 template <int NC, int EPI>
 struct EpiResid {
@@ -212,6 +223,66 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, int m, int nb, bo
   }
 }
 
+// EPI_ROPE: one epilogue thread = one row m (token t of sequence b) x one HEAD (the 128 accumulator columns at `taddr`, output columns
+// n0 .. n0 + 127 of the packed q|k|v row; head_dim = 128, tiles are 256 columns wide, so a column half is exactly one head of q, k or v).
+//   q, k : x_embed = bf16(bf16(x cos) + bf16(rotate_half(x) sin)), bf16 tables — the arithmetic of rope_kvstore_kernel (ops.cu), which is
+//          transformers' apply_rotary_pos_emb in bf16 (modeling_prismatic.py:404-415 calls it through LlamaFlashAttention2); element d pairs
+//          with d + 64, so the thread works on the 32-column chunks (c, c + 2) together;
+//   k, v : also stored into the paged KV cache [page][head][slot][128] (what DynamicCache.update does in the reference);
+//   all three land in the packed qkv buffer the prefill attention reads.
+// Saves the separate RoPE / KV-store pass over the 12288-wide rows (read + write of q|k|v once more, 96 us per layer at bs = 32).
+__device__ __forceinline__ void epilogue_rope_head(uint32_t taddr, int m, int n0, int M, __nv_bfloat16* C, int ldc, const RopeParams& rp) {
+  const bool row_ok = m < M;
+  const int Hd = rp.heads * 128;
+  const int which = n0 / Hd, head = (n0 - which * Hd) >> 7;  // 0 = q, 1 = k, 2 = v
+  const int b = row_ok ? m / rp.T : 0, t = row_ok ? m - b * rp.T : 0, pos = rp.pos0 + t;
+  long cdst = 0;
+  if (which > 0 && row_ok) {
+    const int page = __ldg(rp.block_table + b * rp.max_pages + pos / rp.page_size), slot = pos % rp.page_size;
+    cdst = ((static_cast<long>(page) * rp.heads + head) * rp.page_size + slot) * 128;
+  }
+  __nv_bfloat16* crow = C + static_cast<long>(m) * ldc + n0;
+  __nv_bfloat16* cache = (which == 1) ? rp.k_cache : rp.v_cache;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t lo[32], hi[32];
+    tmem_ld_32x32(taddr + 32 * c, lo);
+    tmem_ld_32x32(taddr + 64 + 32 * c, hi);
+    uint32_t cw[16], sw[16];
+    if (which < 2 && row_ok) {
+      ld32_bf16(rp.cos_tab + static_cast<long>(pos) * 64 + 32 * c, 32, cw);
+      ld32_bf16(rp.sin_tab + static_cast<long>(pos) * 64 + 32 * c, 32, sw);
+    }
+    tmem_ld_wait_on(lo);
+    tmem_ld_wait_on(hi);
+    if (!row_ok) continue;
+    uint32_t olo[16], ohi[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float x10 = bf16_round(__uint_as_float(lo[2 * j])), x11 = bf16_round(__uint_as_float(lo[2 * j + 1]));  // the Linear's bf16 output
+      const float x20 = bf16_round(__uint_as_float(hi[2 * j])), x21 = bf16_round(__uint_as_float(hi[2 * j + 1]));
+      if (which < 2) {
+        const float c0 = bf16_lo(cw[j]), c1 = bf16_hi(cw[j]), s0 = bf16_lo(sw[j]), s1 = bf16_hi(sw[j]);
+        olo[j] = pack_bf16(bf16_round(x10 * c0) + bf16_round(-x20 * s0), bf16_round(x11 * c1) + bf16_round(-x21 * s1));
+        ohi[j] = pack_bf16(bf16_round(x20 * c0) + bf16_round(x10 * s0), bf16_round(x21 * c1) + bf16_round(x11 * s1));
+      } else {
+        olo[j] = pack_bf16(x10, x11), ohi[j] = pack_bf16(x20, x21);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 vl = make_uint4(olo[4 * j], olo[4 * j + 1], olo[4 * j + 2], olo[4 * j + 3]);
+      const uint4 vh = make_uint4(ohi[4 * j], ohi[4 * j + 1], ohi[4 * j + 2], ohi[4 * j + 3]);
+      reinterpret_cast<uint4*>(crow + 32 * c)[j] = vl;
+      reinterpret_cast<uint4*>(crow + 64 + 32 * c)[j] = vh;
+      if (which > 0) {
+        reinterpret_cast<uint4*>(cache + cdst + 32 * c)[j] = vl;
+        reinterpret_cast<uint4*>(cache + cdst + 64 + 32 * c)[j] = vh;
+      }
+    }
+  }
+}
+
 template <int NC, int EPI>
 __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int m, int n0, int M, int N, __nv_bfloat16* C, int ldc, const EpiParams& ep,
                                               const EpiCtx& ec, const EpiResid<NC, EPI>& res) {
@@ -237,7 +308,7 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int m, int n0, int
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C,
-               int ldc, int M, int N, int K, EpiParams ep) {
+               int ldc, int M, int N, int K, EpiParams ep, RopeParams rp) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -331,8 +402,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       res.load(ep, ec, m0 + q * 32 + lane, n0, M, N);
       mbar_wait(&tmem_full[buf], bph);
       tc_fence_after();
-      epilogue_rows<BN / 2, EPI>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
-                            ep, ec, res);
+      if constexpr (EPI == EPI_ROPE) {
+        static_assert(EPI != EPI_ROPE || BN == 256, "EPI_ROPE: a column half must be one 128-wide head");
+        epilogue_rope_head(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, C, ldc, rp);
+      } else {
+        epilogue_rows<BN / 2, EPI>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
+                              ep, ec, res);
+      }
       // this warp's quarter of the accumulator buffer is read out: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -535,7 +611,7 @@ struct PairCfg {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* C, int ldc, int M,
-                    int N, int K, EpiParams ep) {
+                    int N, int K, EpiParams ep, RopeParams rp) {
   using Cfg = PairCfg;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -630,8 +706,12 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       res.load(ep, ec, m0 + q * 32 + lane, n0, M, N);
       mbar_wait(&tmem_full[buf], bph);
       tc_fence_after();
-      epilogue_rows<BN / 2, EPI>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
-                            ep, ec, res);
+      if constexpr (EPI == EPI_ROPE) {
+        epilogue_rope_head(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, C, ldc, rp);
+      } else {
+        epilogue_rows<BN / 2, EPI>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ch * (BN / 2), m0 + q * 32 + lane, n0, M, N, C, ldc,
+                              ep, ec, res);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
@@ -702,9 +782,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat
   const int n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = n_tiles < sms ? n_tiles : sms;
   switch (epi_kind(ep)) {
-    case EPI_RESID: gemm_tn_kernel<BN, EPI_RESID><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
-    case EPI_SWIGLU: gemm_tn_kernel<BN, EPI_SWIGLU><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
-    default: gemm_tn_kernel<BN, EPI_ANY><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
+    case EPI_RESID: gemm_tn_kernel<BN, EPI_RESID><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, RopeParams{}); break;
+    case EPI_SWIGLU: gemm_tn_kernel<BN, EPI_SWIGLU><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, RopeParams{}); break;
+    default: gemm_tn_kernel<BN, EPI_ANY><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, RopeParams{}); break;
   }
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -763,15 +843,70 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, __nv_b
   const int n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + PairCfg::BN - 1) / PairCfg::BN);
   const int pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
   switch (epi_kind(ep)) {
-    case EPI_RESID: gemm_tn_pair_kernel<EPI_RESID><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
-    case EPI_SWIGLU: gemm_tn_pair_kernel<EPI_SWIGLU><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
-    default: gemm_tn_pair_kernel<EPI_ANY><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep); break;
+    case EPI_RESID: gemm_tn_pair_kernel<EPI_RESID><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, RopeParams{}); break;
+    case EPI_SWIGLU: gemm_tn_pair_kernel<EPI_SWIGLU><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, RopeParams{}); break;
+    default: gemm_tn_pair_kernel<EPI_ANY><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, RopeParams{}); break;
+  }
+  EMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fused q|k|v projection: CTA pairs for large M, the single-CTA 128 x 256 kernel otherwise (both have 128-column epilogue halves = one head)
+static int launch_gemm_rope(bool pair, const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat16* C, int ldc, int M, int N, int K,
+                            const RopeParams& rp, cudaStream_t stream) {
+  bool* attr_set = device_attr_flag(ATTR_GEMM_ROPE);
+  const int sms = device_sms();
+  if (!attr_set || sms < 0) return -2;
+  if (!*attr_set) {
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel<EPI_ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+    EMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<256, EPI_ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes));
+    *attr_set = true;
+  }
+  const EpiParams ep{nullptr, nullptr, nullptr, 0, 0, 0};
+  if (pair) {
+    const int n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + PairCfg::BN - 1) / PairCfg::BN);
+    const int pairs = n_tiles < sms / 2 ? n_tiles : sms / 2;
+    gemm_tn_pair_kernel<EPI_ROPE><<<2 * pairs, kGemmThreads, PairCfg::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, rp);
+  } else {
+    const int n_tiles = ((M + BM - 1) / BM) * ((N + 255) / 256);
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    gemm_tn_kernel<256, EPI_ROPE><<<grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(ta, tb, C, ldc, M, N, K, ep, rp);
   }
   EMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 }  // namespace emx
+
+extern "C" int emx_rope_kvstore(void* qkv, int B, int T, int heads, int hd, const void* cos_tab, const void* sin_tab, int pos0, void* k_cache,
+                                void* v_cache, const int32_t* block_table, int max_pages, int page_size, cudaStream_t s);
+
+extern "C" int emx_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, void* qkv, int B, int T, int heads, int head_dim, int K,
+                                 const void* cos_tab, const void* sin_tab, int pos0, void* k_cache, void* v_cache, const int32_t* block_table,
+                                 int max_pages, int page_size, cudaStream_t stream) {
+  using namespace emx;
+  EMX_REQUIRE(B > 0 && T > 0 && heads > 0 && head_dim > 0 && K > 0, "emx_gemm_qkv_rope: bad shape");
+  EMX_REQUIRE(cos_tab && sin_tab && k_cache && v_cache && block_table && page_size > 0, "emx_gemm_qkv_rope: null pointer");
+  const int M = B * T, N = 3 * heads * head_dim;
+  const int sms = device_sms();
+  if (sms < 0) return -2;
+  const char* fe = getenv("EMX_QKV_ROPE_FUSED");  // A/B switch: 0 = always the two-kernel path
+  const long pair_tiles = static_cast<long>((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+  const bool pair = pair_tiles >= sms / 2 && M >= 4 * BM;
+  const bool wide = static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256) >= static_cast<long>(sms) * 90 / 100;
+  const bool fused = head_dim == 128 && (pair || wide) && !(fe && fe[0] == '0') && lda % 8 == 0 && ldw % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0;
+  if (!fused) {  // shapes the fused epilogue does not cover (other head sizes, problems too small for 256-column tiles): GEMM, then the RoPE / KV pass
+    if (int r = emx_gemm_bf16_ws(A, lda, W, ldw, qkv, N, M, N, K, nullptr, nullptr, nullptr, 0, 0, 0, nullptr, 0, stream)) return r;
+    return emx_rope_kvstore(qkv, B, T, heads, head_dim, cos_tab, sin_tab, pos0, k_cache, v_cache, block_table, max_pages, page_size, stream);
+  }
+  CUtensorMap ta, tb;
+  if (int r = make_tmap(&ta, A, M, K, lda, BM)) return r;
+  if (int r = make_tmap(&tb, W, N, K, ldw, pair ? PairCfg::BN / 2 : 256)) return r;
+  const RopeParams rp{static_cast<const __nv_bfloat16*>(cos_tab), static_cast<const __nv_bfloat16*>(sin_tab), static_cast<__nv_bfloat16*>(k_cache),
+                      static_cast<__nv_bfloat16*>(v_cache), block_table, T, pos0, heads, max_pages, page_size};
+  return launch_gemm_rope(pair, ta, tb, static_cast<__nv_bfloat16*>(qkv), N, M, N, K, rp, stream);
+}
 
 extern "C" int emx_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const void* bias,
                              const void* layerscale, const void* resid, int ldr, int resid_mod, int flags, cudaStream_t stream) {

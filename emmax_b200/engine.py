@@ -297,9 +297,9 @@ class Engine:
         tbl = self._slot_table(slot)
         for l in range(L):
             call("emx_rmsnorm", ptr(ws["x"]), ptr(self.ln1[l]), ptr(ws["n"]), B * S, H, t.rms_norm_eps, stream())
-            self.gemm(ws["n"], self.w_qkv[l], ws["qkv"], scratch=self._scratch[0])
-            call("emx_rope_kvstore", ptr(ws["qkv"]), B, S, heads, hd, ptr(self.cos_tab), ptr(self.sin_tab), 0,
-                 self._layer_cache(self.k_cache, l), self._layer_cache(self.v_cache, l), tbl,
+            # q|k|v projection with RoPE + paged-KV append fused into the GEMM epilogue (two kernels for shapes the fused epilogue does not cover)
+            call("emx_gemm_qkv_rope", ptr(ws["n"]), ws["n"].stride(0), ptr(self.w_qkv[l]), self.w_qkv[l].stride(0), ptr(ws["qkv"]), B, S, heads, hd, H,
+                 ptr(self.cos_tab), ptr(self.sin_tab), 0, self._layer_cache(self.k_cache, l), self._layer_cache(self.v_cache, l), tbl,
                  self.pages_per_seq, self.PAGE, stream())  # fmt: skip
             call("emx_attn_fwd", ptr(ws["qkv"]), ptr(ws["att"]), B, S, heads, hd, 1, hd**-0.5, stream())
             self.gemm(ws["att"], self.w_o[l], ws["x"], resid=ws["x"], scratch=self._scratch[0])

@@ -100,6 +100,16 @@ int emx_attn_fwd(const void* qkv, void* out, int B, int T, int heads, int head_d
  * KV cache page layout: [page][head][page_size][hd] bf16; block_table[b*max_pages + p/page_size] = page id. */
 int emx_rope_kvstore(void* qkv, int B, int T, int heads, int head_dim, const void* cos_tab, const void* sin_tab, int pos0, void* k_cache,
                      void* v_cache, const int32_t* block_table, int max_pages, int page_size, emx_stream_t stream);
+
+/* The Llama q|k|v projection of a prefill with emx_rope_kvstore FUSED into the GEMM epilogue (ABI 5): qkv[B*T, 3*heads*head_dim] =
+ * A[B*T, K] . W[3*heads*head_dim, K]^T, RoPE applied to the q and k heads straight out of the accumulator, K / V rows appended to the paged
+ * cache — one pass less over the 3*hidden-wide rows per layer. Same arithmetic and rounding points as emx_gemm_bf16 followed by
+ * emx_rope_kvstore (bit-identical results); shapes the fused epilogue does not cover (head_dim != 128, problems too small for 256-column tiles) run
+ * exactly those two kernels. Replaces q_proj / k_proj / v_proj + apply_rotary_pos_emb + DynamicCache.update of LlamaFlashAttention2
+ * (transformers 4.40.1, reached from modeling_prismatic.py:404-415). */
+int emx_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, void* qkv, int B, int T, int heads, int head_dim, int K,
+                      const void* cos_tab, const void* sin_tab, int pos0, void* k_cache, void* v_cache, const int32_t* block_table,
+                      int max_pages, int page_size, emx_stream_t stream);
 /* x[b, 0] = E[ids[b,0]]; x[b, 1:1+P] = patches[b]; x[b, 1+P+j] = E[ids[b,1+j]]   (modeling_prismatic.py:380-385) */
 int emx_embed_assemble(const int64_t* ids, int n_ids, const void* embed, const void* patches, int n_patches, void* x, int B, int H,
                        emx_stream_t stream);

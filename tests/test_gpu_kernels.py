@@ -226,6 +226,46 @@ def test_rope_kvstore(lib):
             assert torch.equal(vc[pg, :, t % page], v[b, :, t])
 
 
+@pytest.mark.parametrize("B,T", [(2, 296), (1, 296), (3, 200), (1, 40), (5, 131)])
+def test_gemm_qkv_rope_fused_equals_two_kernels(lib, B, T, monkeypatch):
+    """emx_gemm_qkv_rope: RoPE + paged-KV append fused into the q|k|v GEMM epilogue (CTA-pair kernel for M >= 512, single-CTA 128 x 256 tiles for
+    a bs=1 prompt) must be BIT-identical to emx_gemm_bf16 + emx_rope_kvstore — packed qkv rows, K pages, V pages — with sequences that
+    straddle tiles, a shuffled block table and a position offset; small problems take the two-kernel path inside the same call."""
+    from emmax_b200._lib import call, ptr, stream
+
+    heads, hd, K, page, max_pages, pos0 = 32, 128, 4096, 64, 8, 37
+    H = heads * hd
+    a, w = rnd(B * T, K, seed=51), rnd(3 * H, K, scale=K ** -0.5, seed=52)
+    pos = torch.arange(pos0 + T + 8, device="cuda").float()
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device="cuda").float() / hd))
+    cos, sin = torch.cos(pos[:, None] * inv).to(BF).contiguous(), torch.sin(pos[:, None] * inv).to(BF).contiguous()
+    n_pages = B * max_pages
+    table = torch.randperm(n_pages, generator=torch.Generator().manual_seed(3)).to(torch.int32).cuda().view(B, max_pages).contiguous()
+    outs = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("EMX_QKV_ROPE_FUSED", fused)
+        qkv = torch.zeros(B * T, 3 * H, dtype=BF, device="cuda")
+        kc, vc = torch.zeros(n_pages, heads, page, hd, dtype=BF, device="cuda"), torch.zeros(n_pages, heads, page, hd, dtype=BF, device="cuda")
+        call("emx_gemm_qkv_rope", ptr(a), K, ptr(w), K, ptr(qkv), B, T, heads, hd, K, ptr(cos), ptr(sin), pos0, ptr(kc), ptr(vc), ptr(table),
+             max_pages, page, stream())
+        torch.cuda.synchronize()
+        outs.append((qkv, kc, vc))
+    for name, x, y in zip(("qkv", "k pages", "v pages"), outs[0], outs[1]):
+        assert torch.equal(x, y), f"{name}: fused epilogue differs from gemm + rope_kvstore ({(x != y).sum().item()} elements)"
+    # and the two-kernel path is what the torch restatement says: v untouched, q / k rotated (rotate_half form, bf16 rounding points)
+    qkv = outs[1][0].view(B, T, 3, heads, hd)
+    lin = (a.float() @ w.float().T).to(BF).view(B, T, 3, heads, hd)
+    assert_close_bf16(qkv[:, :, 2], lin[:, :, 2], name="v")
+    c, s_ = cos[pos0 : pos0 + T][None, :, None, :].float(), sin[pos0 : pos0 + T][None, :, None, :].float()
+    x1, x2 = lin[:, :, 0, :, : hd // 2].float(), lin[:, :, 0, :, hd // 2 :].float()
+    want_q = torch.cat(((x1 * c).to(BF) + (-x2 * s_).to(BF), (x2 * c).to(BF) + (x1 * s_).to(BF)), dim=-1)
+    assert_close_bf16(qkv[:, :, 0], want_q, frac=0.9999, name="q rope", scale=lin[:, :, 0].abs().float() + 1)
+    # K rows of sequence b, token t live at page table[b, (pos0 + t) // 64], slot (pos0 + t) % 64
+    b, t = B - 1, T - 1
+    pg, slot = int(table[b, (pos0 + t) // page]), (pos0 + t) % page
+    assert torch.equal(outs[1][1][pg, :, slot], qkv[b, t, 1]) and torch.equal(outs[1][2][pg, :, slot], qkv[b, t, 2])
+
+
 def test_gemv_and_argmax(lib):
     from emmax_b200._lib import call, ptr, stream
 
