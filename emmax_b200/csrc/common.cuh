@@ -20,7 +20,7 @@ constexpr int kNumSMs = 148;  // B200; launchers size their grids from the devic
 // Per-device launch state (ops.cu): SM count of the CURRENT device, and whether the function attributes of kernel family `slot` (dynamic
 // shared-memory opt-in) have been set on it. cudaFuncSetAttribute is per device, so a process driving several GPUs needs it once per GPU.
 constexpr int kMaxDevices = 64;
-enum AttrSlot { ATTR_GEMM128 = 0, ATTR_GEMM256, ATTR_GEMM_PAIR, ATTR_GEMM_SPLITK, ATTR_GEMM_ROPE, ATTR_DECODE, ATTR_DECODE_BATCH, ATTR_ATTN_TC64, ATTR_ATTN_TC72, ATTR_ATTN_TC128, ATTR_MISC, ATTR_SLOTS };
+enum AttrSlot { ATTR_GEMM128 = 0, ATTR_GEMM256, ATTR_GEMM_PAIR, ATTR_GEMM_SPLITK, ATTR_GEMM_ROPE, ATTR_GEMM64, ATTR_DECODE, ATTR_DECODE_BATCH, ATTR_ATTN_TC64, ATTR_ATTN_TC72, ATTR_ATTN_TC128, ATTR_MISC, ATTR_SLOTS };
 int device_sms(int* device = nullptr);  // < 0 on error (emx_last_error set)
 bool* device_attr_flag(int slot);       // nullptr on error
 

@@ -33,7 +33,7 @@ constexpr int kGemmThreads = (4 + kEpiWarps) * 32;  // warps 0..3: TMA producer,
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 64) ? 8 : 6;  // ~192 KB of operands in flight either way
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -770,7 +770,7 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, __nv_bfloat16* C, int ldc, int M, int N, int K, const EpiParams& ep,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  bool* attr_set = device_attr_flag(BN == 128 ? ATTR_GEMM128 : ATTR_GEMM256);  // per device: the opt-in is device state
+  bool* attr_set = device_attr_flag(BN == 128 ? ATTR_GEMM128 : BN == 256 ? ATTR_GEMM256 : ATTR_GEMM64);  // per device: the opt-in is device state
   const int sms = device_sms();
   if (!attr_set || sms < 0) return -2;
   if (!*attr_set) {
@@ -953,8 +953,13 @@ extern "C" int emx_gemm_bf16_ws(const void* A, int lda, const void* W, int ldw, 
       return launch_gemm_splitk(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, splits, workspace, stream);
     }
   }
+  // 128 x 64 tiles when 128 x 128 tiles leave more than half of the SMs idle (ViT proj / fc2 and the projector's fc3 of a bs=1 request: 18-64 tiles):
+  // twice the CTAs, each pulling 24 KB instead of 32 KB per k-block; EMX_GEMM_NARROW=0 switches it off (A/B runs)
+  const char* ne = getenv("EMX_GEMM_NARROW");
+  const bool narrow = !wide && !(ne && ne[0] == '0') && static_cast<long>((M + BM - 1) / BM) * ((N + 127) / 128) * 2 <= sms && N > 64;
   if (int r = make_tmap(&ta, A, M, K, lda, BM)) return r;
-  if (int r = make_tmap(&tb, W, N, K, ldw, wide ? 256 : 128)) return r;
+  if (int r = make_tmap(&tb, W, N, K, ldw, wide ? 256 : narrow ? 64 : 128)) return r;
+  if (narrow) return launch_gemm<64>(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, stream);
   return wide ? launch_gemm<256>(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, stream)
               : launch_gemm<128>(ta, tb, static_cast<__nv_bfloat16*>(C), ldc, M, N, K, ep, stream);
 }
